@@ -1,0 +1,164 @@
+/* pmwd_b200.h -- C ABI of the B200-native particle-mesh hot path.
+ *
+ * Drop-in boundary for the hot path of eelregit/pmwd.  The reference has no native
+ * interface (it is pure JAX); the entry points below are what a `jax.ffi` custom
+ * call (or any other host: ctypes, torch, C++) binds in place of the XLA-generated
+ * scatter-add / gather / elementwise / FFT ops.  Each entry cites the reference
+ * function it replaces (paths relative to the pmwd repository root).
+ *
+ * Conventions (XLA-FFI shaped):
+ *   - every pointer is a DEVICE pointer owned by the caller unless stated otherwise;
+ *   - calls only ENQUEUE work on `stream` (a cudaStream_t passed as void*): no
+ *     synchronisation, no allocation, no use of the default stream;
+ *     the only exceptions are pmwd_ctx_create / pmwd_ctx_reserve / pmwd_ctx_destroy;
+ *   - return value 0 = success; negative = bad argument (PMWD_E*); positive =
+ *     CUDA / cuFFT status (offset by PMWD_CUFFT_BASE for cuFFT).  A message is
+ *     retrievable with pmwd_last_error() (thread-local);
+ *   - arrays are C-order.  Particles are AoS rows: pmid int{8,16,32}[N][dim],
+ *     disp/vel/acc float[N][dim] (pmwd/particles.py:52-59).  Meshes are
+ *     float[n0][n1][n2](+channels last); spectra are float2[n0][n1][n2/2+1];
+ *   - there is NO CPU fallback anywhere behind this ABI.
+ */
+#ifndef PMWD_B200_H_
+#define PMWD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PMWD_B200_ABI_VERSION 1
+
+enum {
+  PMWD_OK = 0,
+  PMWD_EINVAL = -1,      /* bad argument / unsupported combination */
+  PMWD_ENOMEM = -2,      /* caller workspace too small */
+  PMWD_ESTATE = -3,      /* context not prepared for this shape */
+  PMWD_CUFFT_BASE = 100000
+};
+
+/* Scatter accumulation modes (pmwd/scatter.py:80 is an unordered f32 scatter-add on GPU). */
+enum {
+  PMWD_SCATTER_ATOMIC = 0,        /* f32 red.global.add (x2-vectorised where aligned); fastest; run-to-run ulp noise */
+  PMWD_SCATTER_DETERMINISTIC = 1  /* cell-sorted: stable radix sort by cell + fixed-order segmented sum; bitwise reproducible */
+};
+
+/* Geometry of one CIC transfer: mirrors the arguments that scatter/gather hand to
+ * enmesh (pmwd/pm_util.py:33-91; pmwd/scatter.py:69-71). */
+typedef struct pmwd_cic_desc {
+  int32_t dim;            /* 1, 2 or 3 */
+  int32_t pmid_bytes;     /* 1, 2 (reference default int16) or 4 */
+  int64_t ptcl_num;
+  int32_t wrap_shape[3];  /* conf.mesh_shape: periodic wrap of indices (enmesh s1) */
+  int32_t mesh_shape[3];  /* spatial shape of the mesh array (enmesh s2); out-of-range neighbours are dropped */
+  int32_t nchan;          /* product of the channel dims (1 = scalar field); channels last, interleaved */
+  int32_t general;        /* 0: fast float32 branch (cell_size=None, pm_util.py:119-136); 1: float64 branch (pm_util.py:99-118) */
+  double cell_size;       /* conf.cell_size (enmesh a1) */
+  double cell_size2;      /* user cell_size (enmesh a2); ignored unless general */
+  double offset[3];       /* enmesh b12 */
+} pmwd_cic_desc;
+
+/* ---- library / context ------------------------------------------------------------ */
+
+int pmwd_abi_version(void);
+/* Copies the calling thread's last error message; returns its length. */
+int pmwd_last_error(char* buf, size_t len);
+
+typedef struct pmwd_ctx pmwd_ctx;
+/* A context owns the cuFFT plans (keyed by shape) and their shared work area on one
+ * device.  Plans are created by pmwd_ctx_reserve (which allocates and may synchronise);
+ * all other calls taking a ctx only enqueue.  One context must not be used from two
+ * streams concurrently. */
+int pmwd_ctx_create(pmwd_ctx** ctx, int device);
+int pmwd_ctx_destroy(pmwd_ctx* ctx);
+/* Create R2C + C2R plans for a real field of `rank` dims `shape` (float). */
+int pmwd_ctx_reserve(pmwd_ctx* ctx, int rank, const int32_t* shape);
+
+/* ---- FFT: pmwd/pm_util.py:236-344 (fftfwd / fftinv = rfftn / irfftn) -------------- */
+/* out[n0][n1][n2/2+1] = rfftn(in), unnormalised (pmwd/pm_util.py:281). */
+int pmwd_fft_r2c(pmwd_ctx* ctx, void* stream, int rank, const int32_t* shape,
+                 const float* in, void* out_c64);
+/* out = irfftn(in) * scale; pass scale = 1/prod(shape) for numpy 'backward' norm
+ * (pmwd/pm_util.py:336).  `in` is clobbered (cuFFT C2R semantics). */
+int pmwd_fft_c2r(pmwd_ctx* ctx, void* stream, int rank, const int32_t* shape,
+                 void* in_c64, float* out, float scale);
+
+/* ---- CIC scatter / gather and their VJPs ------------------------------------------ */
+/* _scatter (pmwd/scatter.py:33-83): mesh[ind] += val * frac.  `val` is either a device
+ * array float[N][nchan] or NULL, in which case `val_scalar` is broadcast (0-D val).
+ * `mesh` is accumulated in place (the caller zero-fills or copies the input mesh).
+ * Deterministic mode needs scratch (pmwd_scatter_scratch_bytes); atomic mode none. */
+size_t pmwd_scatter_scratch_bytes(const pmwd_cic_desc* d, int mode);
+int pmwd_scatter(void* stream, const pmwd_cic_desc* d, const void* pmid, const float* disp,
+                 const float* val, float val_scalar, float* mesh, int mode,
+                 void* scratch, size_t scratch_bytes);
+
+/* _gather (pmwd/gather.py:33-77): out = val + sum_n mesh[ind] * frac. */
+int pmwd_gather(void* stream, const pmwd_cic_desc* d, const void* pmid, const float* disp,
+                const float* mesh, const float* val, float val_scalar, float* out);
+
+/* _scatter_bwd (pmwd/scatter.py:86-148): disp_cot[N][dim], val_cot[N][nchan] (may be NULL). */
+int pmwd_scatter_adj(void* stream, const pmwd_cic_desc* d, const void* pmid, const float* disp,
+                     const float* mesh_cot, const float* val, float val_scalar,
+                     float* disp_cot, float* val_cot);
+
+/* _gather_bwd (pmwd/gather.py:80-142): disp_cot[N][dim]; mesh_cot accumulated in place
+ * (caller zero-fills; may be NULL to skip).  `val_cot` float[N][nchan] or NULL+scalar. */
+int pmwd_gather_adj(void* stream, const pmwd_cic_desc* d, const void* pmid, const float* disp,
+                    const float* mesh, const float* val_cot, float val_cot_scalar,
+                    float* disp_cot, float* mesh_cot);
+
+/* ---- k-space kernels: pmwd/gravity.py:9-44, pmwd/lpt.py:13-37 ---------------------- */
+/* laplace (gravity.py:9-16): pot = where(k2 != 0, -src/k2, 0); k from fftfreq
+ * (pm_util.py:159-199) with grid `spacing`.  In-place allowed. */
+int pmwd_laplace(void* stream, int rank, const int32_t* shape, double spacing,
+                 const void* src_c64, void* pot_c64);
+/* neg_grad (gravity.py:37-44): out = -i k_axis pot, Nyquist planes zeroed. In-place allowed. */
+int pmwd_neg_grad(void* stream, int rank, const int32_t* shape, double spacing, int axis,
+                  const void* pot_c64, void* out_c64);
+/* Fused forward force spectrum (gravity.py:54-62): for a density spectrum rho_k,
+ * g_j = -i k_j * ( -(scale * rho_k) / k^2 ), j = 0..rank-1, in one pass. */
+int pmwd_kspace_force(void* stream, int rank, const int32_t* shape, double spacing,
+                      float scale, const void* rho_c64, void* const* g_c64);
+/* Fused transpose (what jax.vjp(gravity) evaluates between the gather and scatter VJPs,
+ * pmwd/nbody.py:111-116): out = scale * sum_j (+i k_j) * ( -v_j / k^2 ). */
+int pmwd_kspace_force_adj(void* stream, int rank, const int32_t* shape, double spacing,
+                          float scale, const void* const* v_c64, void* out_c64);
+/* _strain spectrum (lpt.py:13-32): out = -k_i k_j pot (Nyquist zeroed when i != j). */
+int pmwd_strain(void* stream, int rank, const int32_t* shape, double spacing, int i, int j,
+                const void* pot_c64, void* out_c64);
+
+/* ---- fused force: gravity() (pmwd/gravity.py:47-72) -------------------------------- */
+/* Workspace (device bytes) needed by pmwd_force / pmwd_force_adj for this geometry. */
+size_t pmwd_force_workspace_bytes(const pmwd_cic_desc* d, int adjoint, int mode);
+/* acc[N][3] = gravity(ptcl).  If kick_vel != NULL additionally vel += acc * kick_factor
+ * (the second half-kick of pmwd/nbody.py:121-140 fused into the gather).
+ * 3-D only; requires pmwd_ctx_reserve(ctx, 3, mesh_shape). */
+int pmwd_force(pmwd_ctx* ctx, void* stream, const pmwd_cic_desc* d, const void* pmid,
+               const float* disp, double Omega_m, float* acc, float* kick_vel,
+               float kick_factor, int mode, void* workspace, size_t workspace_bytes);
+/* force_adj (pmwd/nbody.py:108-118): acc = gravity(ptcl) and alpha = VJP_disp(gravity)(pi).
+ * The Omega_m cotangent is sum(pi . acc) / Omega_m, which pmwd_kick_adj reduces anyway. */
+int pmwd_force_adj(pmwd_ctx* ctx, void* stream, const pmwd_cic_desc* d, const void* pmid,
+                   const float* disp, double Omega_m, const float* pi, float* acc,
+                   float* alpha, int mode, void* workspace, size_t workspace_bytes);
+
+/* ---- leapfrog updates: pmwd/nbody.py:39-99 ----------------------------------------- */
+/* kick (nbody.py:70-77) then drift (nbody.py:39-46) in one pass over n = N*dim floats:
+ * if do_kick: vel += acc * K;  if do_drift: disp += vel * D.  In place. */
+int pmwd_kick_drift(void* stream, int64_t n, float* disp, float* vel, const float* acc,
+                    float K, float D, int do_kick, int do_drift);
+/* kick_adj (nbody.py:80-99): vel += acc*K; xi -= alpha*K; sums[0] += sum(pi * acc).
+ * drift_adj (nbody.py:49-67): disp += vel*D; pi -= xi*D;  sums[1] += sum(xi * vel).
+ * Fused kick_adj-then-drift_adj in one pass; `sums` is a device double[2] accumulated
+ * atomically (caller zero-fills).  xi = ptcl_cot.disp, pi = ptcl_cot.vel, alpha = ptcl_cot.acc. */
+int pmwd_kick_drift_adj(void* stream, int64_t n, float* disp, float* vel, const float* acc,
+                        float* xi, float* pi, const float* alpha, float K, float D,
+                        int do_kick, int do_drift, double* sums);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* PMWD_B200_H_ */

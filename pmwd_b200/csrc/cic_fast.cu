@@ -1,0 +1,262 @@
+// Fused CIC kernels for the gravity fast path (3-D, int16 pmid, offset 0, cell_size=None,
+// target mesh == conf.mesh_shape): the shapes gravity() and its VJP use
+// (pmwd/gravity.py:47-72, pmwd/nbody.py:102-118).
+//
+//  * scatter_fast<NCH>   : rho (NCH=1, scalar val) or the 3 cotangent meshes V_i = scatter(pi_i)
+//                          (NCH=3, SoA meshes) -- pmwd/scatter.py:60-83 / gather.py:113.
+//  * gather3_kernel      : acc_i = gather(F_i), i=0..2 from 3 SoA force meshes in ONE pass
+//                          (the reference calls gather 3x and recomputes the stencil 3x,
+//                          pmwd/gravity.py:61-69), optionally fused with the trailing half-kick
+//                          vel += acc*K (pmwd/nbody.py:70-77).
+//  * force_adj_gather    : alpha = disp cotangent of gravity: the disp_cot parts of _gather_bwd x3
+//                          (gather.py:106-110) and of _scatter_bwd (scatter.py:112-116) in one pass.
+//
+// All HBM / L2-atomic bound.  Particles arrive in Lagrangian (C-order) sequence, so the 32
+// lanes of a warp touch 2..4 contiguous z-rows of the mesh: loads coalesce and the float32
+// reductions (RED.E.ADD.F32 / .F32x2) land in the same L2 sectors.
+#include "cic.cuh"
+
+namespace pmwd {
+
+struct FastParams {
+  int64_t n;
+  int nx, ny, nz;
+  float cell;
+};
+
+struct Stencil3 {
+  int ix[2], iy[2], iz[2];
+  float wx[2], wy[2], wz[2];
+};
+
+template <bool GRAD>
+struct Stencil3G : Stencil3 {
+  float sx[2], sy[2], sz[2];
+};
+
+__device__ __forceinline__ void axis_fast(int pm, float disp, float cell, int n, int* idx, float* w,
+                                          float* s) {
+  float t = __fdiv_rn(disp, cell);
+  int i0 = (int)floorf(t);
+#pragma unroll
+  for (int b = 0; b < 2; ++b) {
+    float d = __fsub_rn(t, (float)(i0 + b));
+    w[b] = __fsub_rn(1.f, fabsf(d));
+    if (s) s[b] = sign_neg(d);
+  }
+  int i = wrap_index(pm + i0, n);
+  idx[0] = i;
+  idx[1] = (i + 1 == n) ? 0 : i + 1;
+}
+
+__device__ __forceinline__ void red_add(float* p, float v) { atomicAdd(p, v); }
+
+__device__ __forceinline__ void red_add2(float* p, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------
+template <int NCH>
+__global__ void __launch_bounds__(256)
+scatter_fast_kernel(FastParams P, const short* __restrict__ pmid, const float* __restrict__ disp,
+                    const float* __restrict__ val, float val_scalar,
+                    float* __restrict__ m0, float* __restrict__ m1, float* __restrict__ m2) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P.n;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    Stencil3 s;
+    axis_fast(pmid[3 * p + 0], disp[3 * p + 0], P.cell, P.nx, s.ix, s.wx, nullptr);
+    axis_fast(pmid[3 * p + 1], disp[3 * p + 1], P.cell, P.ny, s.iy, s.wy, nullptr);
+    axis_fast(pmid[3 * p + 2], disp[3 * p + 2], P.cell, P.nz, s.iz, s.wz, nullptr);
+    float v[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) v[c] = val ? val[NCH * p + c] : val_scalar;
+    // z-neighbours are adjacent in memory: one 8-byte reduction when the pair is aligned
+    const bool pair = (s.iz[1] == s.iz[0] + 1) && ((s.iz[0] & 1) == 0) && ((P.nz & 1) == 0);
+#pragma unroll
+    for (int bx = 0; bx < 2; ++bx) {
+#pragma unroll
+      for (int by = 0; by < 2; ++by) {
+        float wxy = __fmul_rn(s.wx[bx], s.wy[by]);
+        int64_t row = ((int64_t)s.ix[bx] * P.ny + s.iy[by]) * P.nz;
+        float w0 = __fmul_rn(wxy, s.wz[0]);
+        float w1 = __fmul_rn(wxy, s.wz[1]);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          float* m = c == 0 ? m0 : (c == 1 ? m1 : m2);
+          float a = __fmul_rn(v[c], w0), b = __fmul_rn(v[c], w1);
+          if (pair) {
+            red_add2(m + row + s.iz[0], a, b);
+          } else {
+            red_add(m + row + s.iz[0], a);
+            red_add(m + row + s.iz[1], b);
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+template <bool KICK>
+__global__ void __launch_bounds__(256)
+gather3_kernel(FastParams P, const short* __restrict__ pmid, const float* __restrict__ disp,
+               const float* __restrict__ f0, const float* __restrict__ f1,
+               const float* __restrict__ f2, float* __restrict__ acc, float* __restrict__ vel,
+               float K) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P.n;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    Stencil3 s;
+    axis_fast(pmid[3 * p + 0], disp[3 * p + 0], P.cell, P.nx, s.ix, s.wx, nullptr);
+    axis_fast(pmid[3 * p + 1], disp[3 * p + 1], P.cell, P.ny, s.iy, s.wy, nullptr);
+    axis_fast(pmid[3 * p + 2], disp[3 * p + 2], P.cell, P.nz, s.iz, s.wz, nullptr);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    // neighbour order n = bx + 2 by + 4 bz (axis 0 = LSB, pm_util.py:95-97), summed sequentially
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      const int bx = n & 1, by = (n >> 1) & 1, bz = n >> 2;
+      float w = __fmul_rn(__fmul_rn(s.wx[bx], s.wy[by]), s.wz[bz]);
+      int64_t lin = ((int64_t)s.ix[bx] * P.ny + s.iy[by]) * P.nz + s.iz[bz];
+      a0 = __fadd_rn(a0, __fmul_rn(__ldg(f0 + lin), w));
+      a1 = __fadd_rn(a1, __fmul_rn(__ldg(f1 + lin), w));
+      a2 = __fadd_rn(a2, __fmul_rn(__ldg(f2 + lin), w));
+    }
+    acc[3 * p + 0] = a0;
+    acc[3 * p + 1] = a1;
+    acc[3 * p + 2] = a2;
+    if (KICK) {
+      vel[3 * p + 0] = __fadd_rn(vel[3 * p + 0], __fmul_rn(a0, K));
+      vel[3 * p + 1] = __fadd_rn(vel[3 * p + 1], __fmul_rn(a1, K));
+      vel[3 * p + 2] = __fadd_rn(vel[3 * p + 2], __fmul_rn(a2, K));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// alpha_j = [ sum_i sum_n pi_i F_i[n] g_nj + sum_n (val * rho_cot[n]) g_nj ] / cell
+// evaluated as the reference does: four separate (gather-VJP x3, scatter-VJP) neighbour sums,
+// each divided by cell, then added (gather.py:108-110, scatter.py:114-116, JAX sums the
+// cotangent contributions to ptcl.disp).
+__global__ void __launch_bounds__(256)
+force_adj_gather_kernel(FastParams P, const short* __restrict__ pmid, const float* __restrict__ disp,
+                        const float* __restrict__ f0, const float* __restrict__ f1,
+                        const float* __restrict__ f2, const float* __restrict__ rho_cot,
+                        const float* __restrict__ pi, float val, float* __restrict__ alpha) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P.n;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    Stencil3G<true> s;
+    axis_fast(pmid[3 * p + 0], disp[3 * p + 0], P.cell, P.nx, s.ix, s.wx, s.sx);
+    axis_fast(pmid[3 * p + 1], disp[3 * p + 1], P.cell, P.ny, s.iy, s.wy, s.sy);
+    axis_fast(pmid[3 * p + 2], disp[3 * p + 2], P.cell, P.nz, s.iz, s.wz, s.sz);
+    const float p0 = pi[3 * p + 0], p1 = pi[3 * p + 1], p2 = pi[3 * p + 2];
+    float d[4][3];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) d[q][0] = d[q][1] = d[q][2] = 0.f;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      const int bx = n & 1, by = (n >> 1) & 1, bz = n >> 2;
+      // g_j = sign(-d_j) * prod_{m != j} w_m in axis order (j+1.., 0..j-1)
+      float gx = __fmul_rn(s.sx[bx], __fmul_rn(s.wy[by], s.wz[bz]));
+      float gy = __fmul_rn(s.sy[by], __fmul_rn(s.wz[bz], s.wx[bx]));
+      float gz = __fmul_rn(s.sz[bz], __fmul_rn(s.wx[bx], s.wy[by]));
+      int64_t lin = ((int64_t)s.ix[bx] * P.ny + s.iy[by]) * P.nz + s.iz[bz];
+      float t[4];
+      t[0] = __fmul_rn(p0, __ldg(f0 + lin));
+      t[1] = __fmul_rn(p1, __ldg(f1 + lin));
+      t[2] = __fmul_rn(p2, __ldg(f2 + lin));
+      t[3] = __fmul_rn(__ldg(rho_cot + lin), val);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        d[q][0] = __fadd_rn(d[q][0], __fmul_rn(t[q], gx));
+        d[q][1] = __fadd_rn(d[q][1], __fmul_rn(t[q], gy));
+        d[q][2] = __fadd_rn(d[q][2], __fmul_rn(t[q], gz));
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      float a = __fdiv_rn(d[0][j], P.cell);
+      a = __fadd_rn(a, __fdiv_rn(d[1][j], P.cell));
+      a = __fadd_rn(a, __fdiv_rn(d[2][j], P.cell));
+      a = __fadd_rn(a, __fdiv_rn(d[3][j], P.cell));
+      alpha[3 * p + j] = a;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+static int fast_params(const pmwd_cic_desc* d, FastParams* P) {
+  PMWD_REQUIRE(d && d->dim == 3, "fast path is 3-D");
+  PMWD_REQUIRE(d->pmid_bytes == 2, "fast path needs int16 pmid");
+  PMWD_REQUIRE(!d->general, "fast path needs cell_size=None");
+  for (int a = 0; a < 3; ++a) {
+    PMWD_REQUIRE(d->offset[a] == 0.0, "fast path needs offset 0");
+    PMWD_REQUIRE(d->mesh_shape[a] == d->wrap_shape[a] && d->mesh_shape[a] > 0,
+                 "fast path needs mesh == conf.mesh_shape");
+  }
+  P->n = d->ptcl_num;
+  P->nx = d->mesh_shape[0];
+  P->ny = d->mesh_shape[1];
+  P->nz = d->mesh_shape[2];
+  P->cell = (float)d->cell_size;
+  return PMWD_OK;
+}
+
+bool cic_is_fast(const pmwd_cic_desc* d) {
+  if (!d || d->dim != 3 || d->pmid_bytes != 2 || d->general) return false;
+  for (int a = 0; a < 3; ++a)
+    if (d->offset[a] != 0.0 || d->mesh_shape[a] != d->wrap_shape[a]) return false;
+  return true;
+}
+
+int scatter_fast(cudaStream_t st, const pmwd_cic_desc* d, const void* pmid, const float* disp,
+                 const float* val, float val_scalar, int nch, float* m0, float* m1, float* m2) {
+  FastParams P;
+  int rc = fast_params(d, &P);
+  if (rc) return rc;
+  if (P.n == 0) return PMWD_OK;
+  const int block = 256;
+  int grid = grid_for(P.n, block, 8);
+  if (nch == 1)
+    scatter_fast_kernel<1><<<grid, block, 0, st>>>(P, (const short*)pmid, disp, val, val_scalar,
+                                                   m0, nullptr, nullptr);
+  else if (nch == 3)
+    scatter_fast_kernel<3><<<grid, block, 0, st>>>(P, (const short*)pmid, disp, val, val_scalar,
+                                                   m0, m1, m2);
+  else
+    PMWD_REQUIRE(false, "scatter_fast supports 1 or 3 channels");
+  PMWD_LAUNCH_CHECK();
+  return PMWD_OK;
+}
+
+int gather3_fast(cudaStream_t st, const pmwd_cic_desc* d, const void* pmid, const float* disp,
+                 const float* f0, const float* f1, const float* f2, float* acc, float* vel,
+                 float K) {
+  FastParams P;
+  int rc = fast_params(d, &P);
+  if (rc) return rc;
+  if (P.n == 0) return PMWD_OK;
+  const int block = 256;
+  int grid = grid_for(P.n, block, 8);
+  if (vel)
+    gather3_kernel<true><<<grid, block, 0, st>>>(P, (const short*)pmid, disp, f0, f1, f2, acc, vel, K);
+  else
+    gather3_kernel<false><<<grid, block, 0, st>>>(P, (const short*)pmid, disp, f0, f1, f2, acc, nullptr, 0.f);
+  PMWD_LAUNCH_CHECK();
+  return PMWD_OK;
+}
+
+int force_adj_gather(cudaStream_t st, const pmwd_cic_desc* d, const void* pmid, const float* disp,
+                     const float* f0, const float* f1, const float* f2, const float* rho_cot,
+                     const float* pi, float val, float* alpha) {
+  FastParams P;
+  int rc = fast_params(d, &P);
+  if (rc) return rc;
+  if (P.n == 0) return PMWD_OK;
+  const int block = 256;
+  int grid = grid_for(P.n, block, 8);
+  force_adj_gather_kernel<<<grid, block, 0, st>>>(P, (const short*)pmid, disp, f0, f1, f2, rho_cot,
+                                                  pi, val, alpha);
+  PMWD_LAUNCH_CHECK();
+  return PMWD_OK;
+}
+
+}  // namespace pmwd

@@ -1,0 +1,234 @@
+// Public CIC entry points and the fused force pipeline.
+//
+//   pmwd_force     = gravity()            pmwd/gravity.py:47-72
+//   pmwd_force_adj = force_adj()          pmwd/nbody.py:108-118  (gravity + its VJP w.r.t. disp)
+//
+// Forward force, N_m mesh cells, N_c = n0*n1*(n2/2+1) complex:
+//   memset rho -> scatter (RED.F32) -> cuFFT R2C -> fused k-space (1 read, 3 writes; folds the
+//   1.5*Omega_m factor of gravity.py:54 and the 1/N_m of irfftn; the `dens -= 1` of
+//   gravity.py:52 only changes the k=0 mode, which laplace zeroes) -> 3x cuFFT C2R ->
+//   one 3-mesh gather (+ optional fused half-kick).
+// Adjoint force additionally:
+//   3-channel scatter of pi -> 3x R2C -> fused k-space transpose (3 reads, 1 write) -> C2R ->
+//   one weight-gradient gather over (F_0, F_1, F_2, rho_cot).
+#include "cic.cuh"
+
+struct pmwd_ctx;
+
+namespace pmwd {
+
+// cic_generic.cu
+template <int MODE>
+int cic_generic(cudaStream_t st, const pmwd_cic_desc* d, const void* pmid, const float* disp,
+                const float* a_in, float a_scalar, const float* m_in, float* m_out,
+                float* p_out, float* p_out2);
+// cic_fast.cu
+bool cic_is_fast(const pmwd_cic_desc* d);
+int scatter_fast(cudaStream_t st, const pmwd_cic_desc* d, const void* pmid, const float* disp,
+                 const float* val, float val_scalar, int nch, float* m0, float* m1, float* m2);
+int gather3_fast(cudaStream_t st, const pmwd_cic_desc* d, const void* pmid, const float* disp,
+                 const float* f0, const float* f1, const float* f2, float* acc, float* vel, float K);
+int force_adj_gather(cudaStream_t st, const pmwd_cic_desc* d, const void* pmid, const float* disp,
+                     const float* f0, const float* f1, const float* f2, const float* rho_cot,
+                     const float* pi, float val, float* alpha);
+// scatter_det.cu
+size_t scatter_det_scratch_bytes(const pmwd_cic_desc* d);
+int scatter_det(cudaStream_t st, const pmwd_cic_desc* d, const void* pmid, const float* disp,
+                const float* val, float val_scalar, int nch, float* m0, float* m1, float* m2,
+                void* scratch, size_t scratch_bytes);
+// fft.cu
+int fft_r2c(pmwd_ctx* ctx, cudaStream_t st, int rank, const int32_t* shape, const float* in, void* out);
+int fft_c2r(pmwd_ctx* ctx, cudaStream_t st, int rank, const int32_t* shape, void* in, float* out);
+
+static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+struct ForceLayout {
+  size_t real_bytes, spec_bytes;
+  size_t rho_f0;      // rho, later F_0            (real)
+  size_t f1, f2;      // F_1, F_2                  (real)
+  size_t rho_k;       // rho_k, later rho_cot_k    (spectrum)
+  size_t g[3];        // gradient spectra; adjoint: V_i real, then rho_cot real in g[0]
+  size_t s[3];        // adjoint only: V_i spectra
+  size_t det;         // deterministic-scatter scratch
+  size_t total;
+};
+
+static void force_layout(const pmwd_cic_desc* d, int adjoint, int mode, ForceLayout* L) {
+  int64_t nm = (int64_t)d->mesh_shape[0] * d->mesh_shape[1] * d->mesh_shape[2];
+  int64_t nc = (int64_t)d->mesh_shape[0] * d->mesh_shape[1] * (d->mesh_shape[2] / 2 + 1);
+  L->real_bytes = align_up((size_t)nm * sizeof(float));
+  L->spec_bytes = align_up((size_t)nc * sizeof(float2));
+  size_t off = 0;
+  L->rho_f0 = off; off += L->real_bytes;
+  L->f1 = off;     off += L->real_bytes;
+  L->f2 = off;     off += L->real_bytes;
+  L->rho_k = off;  off += L->spec_bytes;
+  for (int a = 0; a < 3; ++a) { L->g[a] = off; off += L->spec_bytes; }
+  for (int a = 0; a < 3; ++a) { L->s[a] = off; if (adjoint) off += L->spec_bytes; }
+  L->det = off;
+  if (mode == PMWD_SCATTER_DETERMINISTIC) off += align_up(scatter_det_scratch_bytes(d));
+  L->total = off;
+}
+
+static int check_force_args(const pmwd_cic_desc* d) {
+  PMWD_REQUIRE(d != nullptr, "null descriptor");
+  PMWD_REQUIRE(cic_is_fast(d), "pmwd_force needs the 3-D int16 fast path (offset 0, cell_size=None, mesh == conf.mesh_shape)");
+  PMWD_REQUIRE(d->nchan == 1, "pmwd_force: nchan must be 1");
+  return PMWD_OK;
+}
+
+static int force_forward(pmwd_ctx* ctx, cudaStream_t st, const pmwd_cic_desc* d, const void* pmid,
+                         const float* disp, double Omega_m, int mode, char* ws,
+                         const ForceLayout& L, float* val_out) {
+  const int32_t* shape = d->mesh_shape;
+  const int64_t nm = (int64_t)shape[0] * shape[1] * shape[2];
+  float* rho = (float*)(ws + L.rho_f0);
+  // scatter.py:37-39: val = conf.mesh_size / conf.ptcl_num (python float -> float32)
+  const float val = (float)((double)nm / (double)d->ptcl_num);
+  if (val_out) *val_out = val;
+  PMWD_CUDA_TRY(cudaMemsetAsync(rho, 0, (size_t)nm * sizeof(float), st));
+  int rc;
+  if (mode == PMWD_SCATTER_DETERMINISTIC)
+    rc = scatter_det(st, d, pmid, disp, nullptr, val, 1, rho, nullptr, nullptr, ws + L.det,
+                     L.total - L.det);
+  else
+    rc = scatter_fast(st, d, pmid, disp, nullptr, val, 1, rho, nullptr, nullptr);
+  if (rc) return rc;
+  rc = fft_r2c(ctx, st, 3, shape, rho, ws + L.rho_k);
+  if (rc) return rc;
+  void* g[3] = {ws + L.g[0], ws + L.g[1], ws + L.g[2]};
+  const float scale = (float)(1.5 * Omega_m / (double)nm);
+  rc = pmwd_kspace_force(st, 3, shape, d->cell_size, scale, ws + L.rho_k, g);
+  if (rc) return rc;
+  float* F[3] = {(float*)(ws + L.rho_f0), (float*)(ws + L.f1), (float*)(ws + L.f2)};
+  for (int a = 0; a < 3; ++a) {
+    rc = fft_c2r(ctx, st, 3, shape, g[a], F[a]);
+    if (rc) return rc;
+  }
+  return PMWD_OK;
+}
+
+}  // namespace pmwd
+
+using namespace pmwd;
+
+extern "C" size_t pmwd_scatter_scratch_bytes(const pmwd_cic_desc* d, int mode) {
+  if (mode != PMWD_SCATTER_DETERMINISTIC) return 0;
+  return scatter_det_scratch_bytes(d);
+}
+
+extern "C" int pmwd_scatter(void* stream, const pmwd_cic_desc* d, const void* pmid,
+                            const float* disp, const float* val, float val_scalar, float* mesh,
+                            int mode, void* scratch, size_t scratch_bytes) {
+  PMWD_REQUIRE(d && pmid && disp && mesh, "null buffer");
+  cudaStream_t st = as_stream(stream);
+  if (mode == PMWD_SCATTER_DETERMINISTIC) {
+    PMWD_REQUIRE(d->nchan == 1, "deterministic scatter via pmwd_scatter supports scalar fields");
+    return scatter_det(st, d, pmid, disp, val, val_scalar, 1, mesh, nullptr, nullptr, scratch,
+                       scratch_bytes);
+  }
+  PMWD_REQUIRE(mode == PMWD_SCATTER_ATOMIC, "unknown scatter mode");
+  if (cic_is_fast(d) && d->nchan == 1)
+    return scatter_fast(st, d, pmid, disp, val, val_scalar, 1, mesh, nullptr, nullptr);
+  return cic_generic<0>(st, d, pmid, disp, val, val_scalar, nullptr, mesh, nullptr, nullptr);
+}
+
+extern "C" int pmwd_gather(void* stream, const pmwd_cic_desc* d, const void* pmid,
+                           const float* disp, const float* mesh, const float* val,
+                           float val_scalar, float* out) {
+  PMWD_REQUIRE(d && pmid && disp && mesh && out, "null buffer");
+  return cic_generic<1>(as_stream(stream), d, pmid, disp, val, val_scalar, mesh, nullptr, out, nullptr);
+}
+
+extern "C" int pmwd_scatter_adj(void* stream, const pmwd_cic_desc* d, const void* pmid,
+                                const float* disp, const float* mesh_cot, const float* val,
+                                float val_scalar, float* disp_cot, float* val_cot) {
+  PMWD_REQUIRE(d && pmid && disp && mesh_cot && disp_cot, "null buffer");
+  return cic_generic<2>(as_stream(stream), d, pmid, disp, val, val_scalar, mesh_cot, nullptr,
+                        disp_cot, val_cot);
+}
+
+extern "C" int pmwd_gather_adj(void* stream, const pmwd_cic_desc* d, const void* pmid,
+                               const float* disp, const float* mesh, const float* val_cot,
+                               float val_cot_scalar, float* disp_cot, float* mesh_cot) {
+  PMWD_REQUIRE(d && pmid && disp && mesh && disp_cot, "null buffer");
+  return cic_generic<3>(as_stream(stream), d, pmid, disp, val_cot, val_cot_scalar, mesh, mesh_cot,
+                        disp_cot, nullptr);
+}
+
+extern "C" size_t pmwd_force_workspace_bytes(const pmwd_cic_desc* d, int adjoint, int mode) {
+  if (!d || d->dim != 3) return 0;
+  ForceLayout L;
+  force_layout(d, adjoint, mode, &L);
+  return L.total;
+}
+
+extern "C" int pmwd_force(pmwd_ctx* ctx, void* stream, const pmwd_cic_desc* d, const void* pmid,
+                          const float* disp, double Omega_m, float* acc, float* kick_vel,
+                          float kick_factor, int mode, void* workspace, size_t workspace_bytes) {
+  int rc = check_force_args(d);
+  if (rc) return rc;
+  PMWD_REQUIRE(ctx && pmid && disp && acc && workspace, "null buffer");
+  PMWD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+  ForceLayout L;
+  force_layout(d, 0, mode, &L);
+  if (workspace_bytes < L.total) {
+    set_error("pmwd_force needs %zu workspace bytes, got %zu", L.total, workspace_bytes);
+    return PMWD_ENOMEM;
+  }
+  cudaStream_t st = as_stream(stream);
+  char* ws = (char*)workspace;
+  rc = force_forward(ctx, st, d, pmid, disp, Omega_m, mode, ws, L, nullptr);
+  if (rc) return rc;
+  return gather3_fast(st, d, pmid, disp, (float*)(ws + L.rho_f0), (float*)(ws + L.f1),
+                      (float*)(ws + L.f2), acc, kick_vel, kick_factor);
+}
+
+extern "C" int pmwd_force_adj(pmwd_ctx* ctx, void* stream, const pmwd_cic_desc* d,
+                              const void* pmid, const float* disp, double Omega_m,
+                              const float* pi, float* acc, float* alpha, int mode,
+                              void* workspace, size_t workspace_bytes) {
+  int rc = check_force_args(d);
+  if (rc) return rc;
+  PMWD_REQUIRE(ctx && pmid && disp && pi && acc && alpha && workspace, "null buffer");
+  PMWD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+  ForceLayout L;
+  force_layout(d, 1, mode, &L);
+  if (workspace_bytes < L.total) {
+    set_error("pmwd_force_adj needs %zu workspace bytes, got %zu", L.total, workspace_bytes);
+    return PMWD_ENOMEM;
+  }
+  cudaStream_t st = as_stream(stream);
+  char* ws = (char*)workspace;
+  const int32_t* shape = d->mesh_shape;
+  const int64_t nm = (int64_t)shape[0] * shape[1] * shape[2];
+  float val = 0.f;
+  rc = force_forward(ctx, st, d, pmid, disp, Omega_m, mode, ws, L, &val);
+  if (rc) return rc;
+  float* F[3] = {(float*)(ws + L.rho_f0), (float*)(ws + L.f1), (float*)(ws + L.f2)};
+  rc = gather3_fast(st, d, pmid, disp, F[0], F[1], F[2], acc, nullptr, 0.f);
+  if (rc) return rc;
+
+  // V_i = scatter(pi_i): the mesh_cot of _gather_bwd (gather.py:113), SoA, in the (now free)
+  // gradient-spectrum buffers
+  float* V[3] = {(float*)(ws + L.g[0]), (float*)(ws + L.g[1]), (float*)(ws + L.g[2])};
+  for (int a = 0; a < 3; ++a) PMWD_CUDA_TRY(cudaMemsetAsync(V[a], 0, (size_t)nm * sizeof(float), st));
+  if (mode == PMWD_SCATTER_DETERMINISTIC)
+    rc = scatter_det(st, d, pmid, disp, pi, 0.f, 3, V[0], V[1], V[2], ws + L.det, L.total - L.det);
+  else
+    rc = scatter_fast(st, d, pmid, disp, pi, 0.f, 3, V[0], V[1], V[2]);
+  if (rc) return rc;
+  const void* S[3] = {ws + L.s[0], ws + L.s[1], ws + L.s[2]};
+  for (int a = 0; a < 3; ++a) {
+    rc = fft_r2c(ctx, st, 3, shape, V[a], ws + L.s[a]);
+    if (rc) return rc;
+  }
+  // rho_cot_k = (1.5 Omega_m / N_m) * sum_i (+i k_i)(-V_i,k / k^2)   [A_i^T = -A_i]
+  const float scale = (float)(1.5 * Omega_m / (double)nm);
+  rc = pmwd_kspace_force_adj(st, 3, shape, d->cell_size, scale, S, ws + L.rho_k);
+  if (rc) return rc;
+  float* rho_cot = (float*)(ws + L.g[0]);
+  rc = fft_c2r(ctx, st, 3, shape, ws + L.rho_k, rho_cot);
+  if (rc) return rc;
+  return force_adj_gather(st, d, pmid, disp, F[0], F[1], F[2], rho_cot, pi, val, alpha);
+}

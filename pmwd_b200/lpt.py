@@ -1,0 +1,124 @@
+"""Lagrangian perturbation theory initial conditions (``pmwd/lpt.py:13-212``).
+
+The force-call part of LPT (``laplace``, ``neg_grad`` + inverse FFT loop, ``lpt.py:164-173,
+190-208``) uses the same fused k-space kernels as the N-body force, on the particle grid;
+the strain spectra ``-k_i k_j pot`` (``lpt.py:22-32``) come from ``pmwd_strain``.  FFTs go
+through cuFFT (``torch.fft``); the whole function is differentiable by torch autograd
+(the reference uses JAX AD with rematerialisation, ``lpt.py:136-137``).
+"""
+import torch
+
+from . import _lib
+from .boltzmann import growth
+from .cosmology import E2
+from .gravity import laplace, neg_grad
+from .particles import Particles
+from .pm_util import fftfreq, fftfwd, fftinv
+
+
+class _Strain(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pot, shape, spacing, i, j):
+        pot = pot.contiguous()
+        out = torch.empty_like(pot)
+        with torch.cuda.device(pot.device):
+            _lib.check(_lib.lib().pmwd_strain(
+                _lib.stream_ptr(pot.device), len(shape), _lib.shape_arr(shape), float(spacing),
+                i, j, _lib.ptr(pot), _lib.ptr(out)), 'pmwd_strain')
+        ctx.meta = (shape, spacing, i, j)
+        return out
+
+    @staticmethod
+    def backward(ctx, cot):
+        shape, spacing, i, j = ctx.meta          # real multiplier: self-adjoint
+        return _Strain.apply(cot, shape, spacing, i, j), None, None, None, None
+
+
+def _strain(kvec, i, j, pot, conf):
+    """LPT strain component (``pmwd/lpt.py:13-37``); Nyquist planes zeroed when i != j."""
+    if pot.is_cuda and pot.dtype == torch.complex64 and getattr(kvec, 'shape', None) is not None:
+        strain = _Strain.apply(pot, kvec.shape, conf.ptcl_spacing, i, j)
+    else:
+        k_i, k_j = kvec[i], kvec[j]
+        nyquist = torch.pi / conf.ptcl_spacing
+        eps = nyquist * torch.finfo(conf.float_dtype).eps
+        if i != j:
+            k_i = torch.where((k_i.abs() - nyquist).abs() <= eps, torch.zeros_like(k_i), k_i)
+            k_j = torch.where((k_j.abs() - nyquist).abs() <= eps, torch.zeros_like(k_j), k_j)
+        strain = -k_i * k_j * pot
+    strain = fftinv(strain, shape=conf.ptcl_grid_shape)
+    return strain.to(conf.float_dtype)
+
+
+def _L(kvec, pot_m, pot_n, conf):
+    """2LPT source (``pmwd/lpt.py:40-76``)."""
+    m_eq_n = pot_n is None
+    if m_eq_n:
+        pot_n = pot_m
+    L = torch.zeros(conf.ptcl_grid_shape, dtype=conf.float_dtype, device=pot_m.device)
+    for i in range(conf.dim):
+        strain_m = _strain(kvec, i, i, pot_m, conf)
+        for j in range(conf.dim - 1, i, -1):
+            strain_n = _strain(kvec, j, j, pot_n, conf)
+            L = L + strain_m * strain_n
+        if not m_eq_n:
+            for j in range(i - 1, -1, -1):
+                strain_n = _strain(kvec, j, j, pot_n, conf)
+                L = L + strain_m * strain_n
+    if not m_eq_n:
+        L = L * 0.5
+    for i in range(conf.dim - 1):
+        for j in range(i + 1, conf.dim):
+            strain_m = _strain(kvec, i, j, pot_m, conf)
+            strain_n = strain_m
+            if not m_eq_n:
+                strain_n = _strain(kvec, j, i, pot_n, conf)
+            L = L - strain_m * strain_n
+    return L
+
+
+def lpt(modes, cosmo, conf):
+    """Lagrangian perturbation theory at ``conf.lpt_order`` (``pmwd/lpt.py:136-212``).
+
+    Returns ``(ptcl, obsvbl)`` with ``obsvbl = None``.
+    """
+    if conf.dim not in (1, 2, 3):
+        raise ValueError(f'dim={conf.dim} not supported')
+    if conf.lpt_order not in (0, 1, 2, 3):
+        raise ValueError(f'lpt_order={conf.lpt_order} not supported')
+
+    dev = modes.device
+    modes = modes / conf.ptcl_cell_vol
+    kvec = fftfreq(conf.ptcl_grid_shape, conf.ptcl_spacing, dtype=conf.float_dtype, device=dev)
+
+    pot = []
+    if conf.lpt_order > 0:
+        pot_1 = laplace(kvec, modes, cosmo)
+        pot.append(pot_1)
+    if conf.lpt_order > 1:
+        src_2 = _L(kvec, pot_1, None, conf)
+        src_2 = fftfwd(src_2)
+        pot.append(laplace(kvec, src_2, cosmo))
+    if conf.lpt_order > 2:
+        raise NotImplementedError('TODO')
+
+    a = conf.a_start
+    ptcl = Particles.gen_grid(conf, vel=True, device=dev)
+    disp = [ptcl.disp[:, i] for i in range(conf.dim)]
+    vel = [ptcl.vel[:, i] for i in range(conf.dim)]
+
+    for order in range(1, 1 + conf.lpt_order):
+        D = growth(a, cosmo, conf, order=order)
+        dD_dlna = growth(a, cosmo, conf, order=order, deriv=1)
+        a2HDp = a ** 2 * torch.sqrt(E2(a, cosmo)) * dD_dlna
+        D = D.to(conf.float_dtype).to(dev)
+        a2HDp = a2HDp.to(conf.float_dtype).to(dev)
+        for i, k in enumerate(kvec):
+            grad = neg_grad(k, pot[order - 1], conf.ptcl_spacing)
+            grad = fftinv(grad, shape=conf.ptcl_grid_shape).to(conf.float_dtype)
+            grad = grad.reshape(-1)
+            disp[i] = disp[i] + D * grad
+            vel[i] = vel[i] + a2HDp * grad
+
+    ptcl = ptcl.replace(disp=torch.stack(disp, dim=-1), vel=torch.stack(vel, dim=-1))
+    return ptcl, None

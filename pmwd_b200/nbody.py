@@ -1,0 +1,332 @@
+"""N-body time integration and its reverse-time adjoint with the reference's API
+(``pmwd/nbody.py:12-276``).
+
+Per KDK step the GPU runs: one fused kick+drift pass, one fused force pipeline whose final
+gather also applies the trailing half-kick (``pmwd_force``); the adjoint step runs one fused
+kick_adj+drift_adj pass (state + cotangents + float64 dot products), ``pmwd_force_adj``
+and one kick_adj pass.  Step factors are float64 host scalars (``nbody.py:12-36``) cast
+to float32 before touching particles.  ``jax.custom_vjp`` becomes a
+``torch.autograd.Function`` whose residual is only the final state (``nbody.py:263-265``).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .boltzmann import growth
+from .cosmology import E2, H_deriv
+from .gravity import gravity, force_into, force_adj_into
+from .particles import Particles
+
+
+def _G_D(a, cosmo, conf):
+    """Growth factor of ZA canonical velocity in [H_0] (``nbody.py:12-14``)."""
+    return a ** 2 * torch.sqrt(E2(a, cosmo)) * growth(a, cosmo, conf, deriv=1)
+
+
+def _G_K(a, cosmo, conf):
+    """Growth factor of ZA accelerations in [H_0^2] (``nbody.py:17-22``)."""
+    return a ** 3 * E2(a, cosmo) * (
+        growth(a, cosmo, conf, deriv=2)
+        + (2 + H_deriv(a, cosmo)) * growth(a, cosmo, conf, deriv=1))
+
+
+def drift_factor(a_vel, a_prev, a_next, cosmo, conf):
+    """Drift time step factor in [1/H_0] (``nbody.py:25-29``)."""
+    factor = growth(a_next, cosmo, conf) - growth(a_prev, cosmo, conf)
+    return factor / _G_D(a_vel, cosmo, conf)
+
+
+def kick_factor(a_acc, a_prev, a_next, cosmo, conf):
+    """Kick time step factor in [1/H_0] (``nbody.py:32-36``)."""
+    factor = _G_D(a_next, cosmo, conf) - _G_D(a_prev, cosmo, conf)
+    return factor / _G_K(a_acc, cosmo, conf)
+
+
+def _f(a):
+    return float(a)
+
+
+def _f32(x):
+    """``factor.astype(conf.float_dtype)`` (``nbody.py:42,73``)."""
+    return float(np.float32(float(x)))
+
+
+# ------------------------------------------------------------------------------- kernels
+def _kick_drift(ptcl, K, D, do_kick, do_drift):
+    dev = ptcl.disp.device
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().pmwd_kick_drift(
+            _lib.stream_ptr(dev), ptcl.disp.numel(), _lib.ptr(ptcl.disp), _lib.ptr(ptcl.vel),
+            _lib.ptr(ptcl.acc), K, D, int(do_kick), int(do_drift)), 'pmwd_kick_drift')
+
+
+def _owned(ptcl, conf, need_acc=True):
+    """Private, contiguous, writable copies of the dynamic arrays (inputs are immutable)."""
+    _lib.require_cuda(ptcl.pmid, ptcl.disp)
+    if ptcl.vel is None:
+        raise ValueError('nbody needs particle velocities')
+    kw = dict(pmid=ptcl.pmid.contiguous(),
+              disp=ptcl.disp.detach().clone(memory_format=torch.contiguous_format),
+              vel=ptcl.vel.detach().clone(memory_format=torch.contiguous_format))
+    if need_acc:
+        kw['acc'] = (ptcl.acc.detach().clone(memory_format=torch.contiguous_format)
+                     if ptcl.acc is not None else torch.zeros_like(kw['disp']))
+    return Particles(conf, attr=ptcl.attr, **kw)
+
+
+def _fast_ok(ptcl, conf):
+    return conf.dim == 3 and ptcl.pmid.dtype == torch.int16
+
+
+# --------------------------------------------------------------- reference-shaped pieces
+def drift(a_vel, a_prev, a_next, ptcl, cosmo, conf):
+    """``nbody.py:39-46``."""
+    factor = _f32(drift_factor(a_vel, a_prev, a_next, cosmo, conf))
+    return ptcl.replace(disp=ptcl.disp + ptcl.vel * factor)
+
+
+def kick(a_acc, a_prev, a_next, ptcl, cosmo, conf):
+    """``nbody.py:70-77``."""
+    factor = _f32(kick_factor(a_acc, a_prev, a_next, cosmo, conf))
+    return ptcl.replace(vel=ptcl.vel + ptcl.acc * factor)
+
+
+def force(a, ptcl, cosmo, conf):
+    """``nbody.py:102-105``."""
+    with torch.no_grad():
+        acc = gravity(a, ptcl, cosmo, conf)
+    return ptcl.replace(acc=acc)
+
+
+def _integrate_inplace(a_prev, a_next, ptcl, cosmo, conf):
+    """``integrate`` (``nbody.py:121-140``) on owned arrays, with kernel fusion: a kick that
+    is followed by a drift shares its pass; a kick that follows a force rides on the gather."""
+    Om = float(cosmo.Omega_m)
+    fast = _fast_ok(ptcl, conf)
+    D = K = 0
+    a_disp = a_vel = a_acc = a_prev
+    pending_kick = None           # factor of a kick not yet applied (fused with next drift)
+    for d, k in conf.symp_splits:
+        if d != 0:
+            D += d
+            a_disp_next = a_prev * (1 - D) + a_next * D
+            fd = _f32(drift_factor(a_vel, a_disp, a_disp_next, cosmo, conf))
+            if pending_kick is not None:
+                _kick_drift(ptcl, pending_kick, fd, True, True)
+                pending_kick = None
+            else:
+                _kick_drift(ptcl, 0.0, fd, False, True)
+            a_disp = a_disp_next
+            a_acc = a_disp
+            # force, fused with the following kick when there is one in this split
+            if k != 0:
+                K += k
+                a_vel_next = a_prev * (1 - K) + a_next * K
+                fk = _f32(kick_factor(a_acc, a_vel, a_vel_next, cosmo, conf))
+                if fast:
+                    force_into(ptcl.pmid, ptcl.disp, Om, conf, ptcl.acc, ptcl.vel, fk)
+                else:
+                    ptcl.acc.copy_(gravity(a_disp, ptcl, cosmo, conf))
+                    _kick_drift(ptcl, fk, 0.0, True, False)
+                a_vel = a_vel_next
+            else:
+                if fast:
+                    force_into(ptcl.pmid, ptcl.disp, Om, conf, ptcl.acc)
+                else:
+                    ptcl.acc.copy_(gravity(a_disp, ptcl, cosmo, conf))
+            continue
+        if k != 0:
+            K += k
+            a_vel_next = a_prev * (1 - K) + a_next * K
+            fk = _f32(kick_factor(a_acc, a_vel, a_vel_next, cosmo, conf))
+            if pending_kick is not None:
+                _kick_drift(ptcl, pending_kick, 0.0, True, False)
+            pending_kick = fk
+            a_vel = a_vel_next
+    if pending_kick is not None:
+        _kick_drift(ptcl, pending_kick, 0.0, True, False)
+    return ptcl
+
+
+def integrate(a_prev, a_next, ptcl, cosmo, conf):
+    """Symplectic integration for one step (``nbody.py:121-140``); returns new Particles."""
+    with torch.no_grad():
+        return _integrate_inplace(_f(a_prev), _f(a_next), _owned(ptcl, conf), cosmo, conf)
+
+
+def form(a_prev, a_next, ptcl, cosmo, conf):
+    pass
+
+
+def coevolve(a_prev, a_next, ptcl, cosmo, conf):
+    return ptcl
+
+
+def observe(a_prev, a_next, ptcl, obsvbl, cosmo, conf):
+    return obsvbl
+
+
+def nbody_init(a, ptcl, obsvbl, cosmo, conf):
+    """``nbody.py:193-201``."""
+    with torch.no_grad():
+        ptcl = _owned(ptcl, conf)
+        _force_inplace(ptcl, cosmo, conf)
+    return ptcl, obsvbl
+
+
+def _force_inplace(ptcl, cosmo, conf):
+    if _fast_ok(ptcl, conf):
+        force_into(ptcl.pmid, ptcl.disp, float(cosmo.Omega_m), conf, ptcl.acc)
+    else:
+        ptcl.acc.copy_(gravity(0., ptcl, cosmo, conf))
+
+
+def nbody_step(a_prev, a_next, ptcl, obsvbl, cosmo, conf):
+    """``nbody.py:204-212``."""
+    ptcl = integrate(a_prev, a_next, ptcl, cosmo, conf)
+    return ptcl, obsvbl
+
+
+def _nbody_forward(ptcl, cosmo, conf, reverse):
+    a_nbody = conf.a_nbody.tolist()
+    if reverse:
+        a_nbody = a_nbody[::-1]
+    with torch.no_grad():
+        ptcl = _owned(ptcl, conf)
+        _force_inplace(ptcl, cosmo, conf)
+        for a_prev, a_next in zip(a_nbody[:-1], a_nbody[1:]):
+            _integrate_inplace(a_prev, a_next, ptcl, cosmo, conf)
+    return ptcl
+
+
+# ------------------------------------------------------------------------------- adjoint
+_COSMO_LEAVES = ('Omega_m', 'Omega_k_', 'w_0_', 'w_a_', 'growth')
+
+
+def _factor_valgrad(fun, a0, a1, a2, cosmo, conf):
+    """``value_and_grad(fun, argnums=3)`` (``nbody.py:51-52,82-83``) w.r.t. the cosmology
+    leaves a step factor can depend on."""
+    leaves = {n: getattr(cosmo, n).detach().clone().requires_grad_(True)
+              for n in _COSMO_LEAVES if getattr(cosmo, n) is not None}
+    c = cosmo.replace(**leaves)
+    val = fun(a0, a1, a2, c, conf)
+    grads = torch.autograd.grad(val, list(leaves.values()), allow_unused=True)
+    grads = {n: (g if g is not None else torch.zeros_like(leaves[n]))
+             for n, g in zip(leaves, grads)}
+    return float(val), grads
+
+
+def nbody_adj(ptcl, ptcl_cot, obsvbl_cot, cosmo, conf, reverse=False):
+    """N-body time integration with adjoint equation (``nbody.py:226-260``).
+
+    Returns ``(ptcl, ptcl_cot, cosmo_cot)``; ``cosmo_cot`` is a dict leaf-name -> float64
+    tensor over the leaves ``nbody`` can touch (all other leaves of the reference's
+    cotangent pytree are zero).
+    """
+    if not _fast_ok(ptcl, conf):
+        raise NotImplementedError('the reverse-time adjoint runs on the 3-D int16 fast path')
+    a_nbody = conf.a_nbody.tolist()
+    if reverse:
+        a_nbody = a_nbody[::-1]
+    dev = ptcl.disp.device
+    Om = float(cosmo.Omega_m)
+    lib = _lib.lib()
+    with torch.no_grad():
+        ptcl = _owned(ptcl, conf)
+        xi = ptcl_cot.disp.detach().to(conf.float_dtype).clone(memory_format=torch.contiguous_format)
+        pi = ptcl_cot.vel.detach().to(conf.float_dtype).clone(memory_format=torch.contiguous_format)
+        alpha = torch.empty_like(xi)
+        n = xi.numel()
+        pairs = list(zip(a_nbody[:0:-1], a_nbody[-2::-1]))
+        # per kick / drift: float64 dot products kept on the device until the end
+        nsplit = len(conf.symp_splits)
+        sums = torch.zeros((len(pairs) * nsplit + 1, 2), dtype=torch.float64, device=dev)
+        records = []   # (kind, slot, column, factor, grads)
+
+        def kd_adj(K, D, do_kick, do_drift, slot):
+            with torch.cuda.device(dev):
+                _lib.check(lib.pmwd_kick_drift_adj(
+                    _lib.stream_ptr(dev), n, _lib.ptr(ptcl.disp), _lib.ptr(ptcl.vel),
+                    _lib.ptr(ptcl.acc), _lib.ptr(xi), _lib.ptr(pi), _lib.ptr(alpha), K, D,
+                    int(do_kick), int(do_drift), C.c_void_p(sums[slot].data_ptr())),
+                    'pmwd_kick_drift_adj')
+
+        # nbody_adj_init (nbody.py:226-236)
+        force_adj_into(ptcl.pmid, ptcl.disp, Om, conf, pi, ptcl.acc, alpha)
+
+        slot = 0
+        for a_prev, a_next in pairs:
+            # integrate_adj (nbody.py:143-162)
+            K = D = 0
+            a_disp = a_vel = a_acc = a_prev
+            for d, k in reversed(conf.symp_splits):
+                fk = fd = 0.0
+                if k != 0:
+                    K += k
+                    a_vel_next = a_prev * (1 - K) + a_next * K
+                    val, grads = _factor_valgrad(kick_factor, a_acc, a_vel, a_vel_next, cosmo, conf)
+                    fk = _f32(val)
+                    records.append(('kick', slot, 0, fk, grads))
+                    a_vel = a_vel_next
+                if d != 0:
+                    D += d
+                    a_disp_next = a_prev * (1 - D) + a_next * D
+                    val, grads = _factor_valgrad(drift_factor, a_vel, a_disp, a_disp_next, cosmo, conf)
+                    fd = _f32(val)
+                    records.append(('drift', slot, 1, fd, grads))
+                    a_disp = a_disp_next
+                kd_adj(fk, fd, k != 0, d != 0, slot)
+                slot += 1
+                if d != 0:
+                    force_adj_into(ptcl.pmid, ptcl.disp, Om, conf, pi, ptcl.acc, alpha)
+                    a_acc = a_disp
+
+        sums_h = sums.cpu()
+        cosmo_cot = {nme: torch.zeros_like(getattr(cosmo, nme)) for nme in _COSMO_LEAVES
+                     if getattr(cosmo, nme) is not None}
+        for kind, s, col, factor, grads in records:
+            S = sums_h[s, col]
+            for nme in cosmo_cot:                        # nbody.py:64-65, 95-97
+                cosmo_cot[nme] = cosmo_cot[nme] - grads[nme] * S
+            if kind == 'kick':
+                # cosmo_cot_force * factor: gravity's cosmology VJP has the single leaf
+                # Omega_m, equal to sum(pi . acc) / Omega_m (gravity.py:54)
+                cosmo_cot['Omega_m'] = cosmo_cot['Omega_m'] - (S / Om) * factor
+
+    ptcl_cot = Particles(conf, ptcl.pmid, xi, vel=pi, acc=alpha)
+    return ptcl, ptcl_cot, cosmo_cot
+
+
+class _Nbody(torch.autograd.Function):
+    """``nbody`` as a ``custom_vjp`` (``nbody.py:215-223,263-276``)."""
+
+    @staticmethod
+    def forward(ctx, disp, vel, conf, cosmo, pmid, reverse, *leaves):
+        ptcl = Particles(conf, pmid, disp, vel=vel)
+        out = _nbody_forward(ptcl, cosmo, conf, reverse)
+        ctx.save_for_backward(out.disp, out.vel)      # residual = final state only
+        ctx.meta = (conf, cosmo, out.pmid, reverse)
+        ctx.mark_non_differentiable(out.acc)
+        return out.disp, out.vel, out.acc
+
+    @staticmethod
+    def backward(ctx, disp_cot, vel_cot, _acc_cot):
+        conf, cosmo, pmid, reverse = ctx.meta
+        disp, vel = ctx.saved_tensors
+        ptcl = Particles(conf, pmid, disp, vel=vel)
+        zeros = torch.zeros_like(disp)
+        cot = Particles(conf, pmid, disp_cot if disp_cot is not None else zeros,
+                        vel=vel_cot if vel_cot is not None else zeros)
+        _, ptcl_cot, cosmo_cot = nbody_adj(ptcl, cot, None, cosmo, conf, reverse=reverse)
+        leaf_cots = tuple(cosmo_cot[n] for n in _COSMO_LEAVES if getattr(cosmo, n) is not None)
+        return (ptcl_cot.disp, ptcl_cot.vel, None, None, None, None) + leaf_cots
+
+
+def nbody(ptcl, obsvbl, cosmo, conf, reverse=False):
+    """N-body time integration (``nbody.py:215-223``); differentiable w.r.t. ``ptcl.disp``,
+    ``ptcl.vel`` and the cosmology through the reverse-time adjoint."""
+    leaves = tuple(getattr(cosmo, n) for n in _COSMO_LEAVES if getattr(cosmo, n) is not None)
+    disp, vel, acc = _Nbody.apply(ptcl.disp, ptcl.vel, conf, cosmo, ptcl.pmid, reverse, *leaves)
+    return Particles(conf, ptcl.pmid, disp, vel=vel, acc=acc, attr=ptcl.attr), obsvbl

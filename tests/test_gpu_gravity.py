@@ -1,0 +1,407 @@
+"""GPU parity of the k-space kernels, the fused force pipeline, the leapfrog kernels, LPT,
+the N-body integration and its reverse-time adjoint against the oracle.
+
+Stated float32 tolerances (BASELINE.json north_star): per-cell density rel. err <= 1e-5,
+final positions within 1e-4 cell, P(k) within 0.1 % at all k, adjoint gradients with
+cosine similarity >= 0.9999."""
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _pm():
+    import pmwd_b200
+    return pmwd_b200
+
+
+def _confs(shape, mesh_shape=2, spacing=1., **kw):
+    pm = _pm()
+    return (pm.Configuration(spacing, shape, mesh_shape=mesh_shape, **kw),
+            O.Conf(spacing, shape, mesh_shape=mesh_shape,
+                   **{k: v for k, v in kw.items() if k != 'scatter_mode'}))
+
+
+def _cos(a, b):
+    a = np.asarray(a, dtype=np.float64).ravel()
+    b = np.asarray(b, dtype=np.float64).ravel()
+    return float(a @ b / np.sqrt((a @ a) * (b @ b)))
+
+
+def _rms(x):
+    return float(np.sqrt(np.mean(np.square(np.asarray(x, dtype=np.float64)))))
+
+
+# ------------------------------------------------------------------------- k-space kernels
+@pytest.mark.parametrize('shape', [(16,), (6, 9), (7, 8), (8, 8, 8), (6, 5, 4), (12, 10, 9)])
+def test_kspace_kernels_vs_oracle(shape):
+    """laplace / neg_grad / strain (gravity.py:9-44, lpt.py:13-32) incl. even/odd meshes
+    (Nyquist zeroing) and ranks 1-3; same float32 operation order -> agreement to 1 ulp."""
+    pm = _pm()
+    from pmwd_b200.lpt import _Strain
+    spacing = 0.7
+    rng = np.random.default_rng(0)
+    cshape = shape[:-1] + (shape[-1] // 2 + 1,)
+    src = (rng.standard_normal(cshape) + 1j * rng.standard_normal(cshape)).astype(np.complex64)
+    okvec = O.fftfreq(shape, spacing, dtype=np.float32)
+    kvec = pm.fftfreq(shape, spacing, dtype=torch.float32, device='cuda')
+    for a, b in zip(okvec, kvec):
+        np.testing.assert_array_equal(a, b.cpu().numpy())
+    tsrc = torch.from_numpy(src).cuda()
+    ref = O.laplace(okvec, src)
+    got = pm.laplace(kvec, tsrc).cpu().numpy()
+    np.testing.assert_allclose(got, ref, rtol=2e-7, atol=0)
+    for ax in range(len(shape)):
+        ref = O.neg_grad(okvec[ax], src, spacing)
+        got = pm.neg_grad(kvec[ax], tsrc, spacing).cpu().numpy()
+        np.testing.assert_allclose(got, ref, rtol=2e-7, atol=0)
+    if len(shape) == 3:
+        oc = O.Conf(spacing, shape)
+        for i in range(3):
+            for j in range(i, 3):
+                k_i, k_j = okvec[i], okvec[j]
+                nyq = np.pi / spacing
+                eps = nyq * np.finfo(np.float32).eps
+                if i != j:
+                    k_i = np.where(np.abs(np.abs(k_i) - nyq) <= eps, 0, k_i)
+                    k_j = np.where(np.abs(np.abs(k_j) - nyq) <= eps, 0, k_j)
+                ref = (-k_i * k_j * src).astype(np.complex64)
+                got = _Strain.apply(tsrc, shape, spacing, i, j).cpu().numpy()
+                np.testing.assert_allclose(got, ref, rtol=2e-7, atol=0)
+
+
+def test_plane_wave_force_gpu():
+    """Closed-form pin of the whole mesh pipeline on the GPU: particles displaced by a
+    single long-wavelength mode feel acc_x = -1.5 Om A sin(kx)/k x (CIC window)^2."""
+    pm = _pm()
+    n = 32
+    conf, oconf = _confs((n, n, n))
+    cosmo = pm.SimpleLCDM(conf)
+    ptcl = pm.Particles.gen_grid(conf)
+    kf = 2 * np.pi / n                   # fundamental of the box (box = n * spacing)
+    A = 0.01
+    q = ptcl.pos(dtype=torch.float64, wrap=False)[:, 0]
+    # displacement psi = -(A/k) sin(kq) gives delta = A cos(kq) to first order
+    disp = torch.zeros_like(ptcl.disp)
+    disp[:, 0] = (-(A / kf) * torch.sin(kf * q)).float()
+    p = ptcl.replace(disp=disp)
+    acc = pm.gravity(1., p, cosmo, conf).cpu().numpy()
+    x = (q + disp[:, 0].double()).cpu().numpy()
+    w = np.sinc(kf * conf.cell_size / 2 / np.pi) ** 2      # CIC assignment window
+    expect = -1.5 * 0.3 * A * np.sin(kf * x) / kf * w ** 2
+    assert np.abs(acc[:, 0] - expect).max() <= 2e-2 * np.abs(expect).max()   # O(A) nonlinearity
+    assert np.abs(acc[:, 1:]).max() <= 1e-6 * np.abs(expect).max() + 1e-7
+
+
+@pytest.mark.parametrize('n, disp_std', [(16, 0.5), (32, 4.0), (64, 8.0)])
+@pytest.mark.parametrize('mode', ['atomic', 'deterministic'])
+def test_gravity_vs_oracle(n, disp_std, mode):
+    """acc rel-RMS error <= 1e-5 against the float64 oracle and the float32 oracle."""
+    pm = _pm()
+    conf, oconf = _confs((n, n, n), scatter_mode=mode)
+    cosmo = pm.SimpleLCDM(conf)
+    pmid, disp, _, _ = O.gen_grid(oconf)
+    rng = np.random.default_rng(1)
+    disp = (disp + disp_std * rng.standard_normal(disp.shape)).astype(np.float32)
+    ptcl = pm.Particles(conf, torch.from_numpy(pmid).cuda(), torch.from_numpy(disp).cuda())
+    acc = pm.gravity(1., ptcl, cosmo, conf).cpu().numpy()
+    ref32 = O.gravity(pmid, disp, 0.3, oconf)
+    o64 = O.Conf(1., (n, n, n), mesh_shape=2, float_dtype=np.float64)
+    ref64 = O.gravity(pmid, disp.astype(np.float64), 0.3, o64)
+    scale = _rms(ref64)
+    assert _rms(acc - ref64) <= 1e-5 * scale
+    assert _rms(acc - ref32) <= 1e-5 * scale
+    # our error vs float64 is of the same order as the float32 oracle's own
+    assert _rms(acc - ref64) <= 3 * _rms(ref32 - ref64) + 1e-7 * scale
+
+
+@pytest.mark.parametrize('mode', ['atomic', 'deterministic'])
+def test_gravity_vjp_vs_oracle(mode):
+    """pmwd_force_adj vs the oracle's chain of the reference VJP rules (cos >= 0.9999,
+    rel-RMS <= 1e-4), and the Omega_m cotangent."""
+    pm = _pm()
+    n = 16
+    conf, oconf = _confs((n, n, n), scatter_mode=mode)
+    pmid, disp, _, _ = O.gen_grid(oconf)
+    rng = np.random.default_rng(2)
+    disp = (disp + 1.5 * rng.standard_normal(disp.shape)).astype(np.float32)
+    pi = rng.standard_normal(disp.shape).astype(np.float32)
+    Om = torch.tensor(0.3, dtype=torch.float64, requires_grad=True)
+    cosmo = pm.SimpleLCDM(conf, Omega_m=Om)
+    d = torch.from_numpy(disp).cuda().requires_grad_(True)
+    ptcl = pm.Particles(conf, torch.from_numpy(pmid).cuda(), d)
+    acc = pm.gravity(1., ptcl, cosmo, conf)
+    acc.backward(torch.from_numpy(pi).cuda())
+    o64 = O.Conf(1., (n, n, n), mesh_shape=2, float_dtype=np.float64)
+    acc_ref, dcot_ref, Om_ref = O.gravity_vjp(pmid, disp.astype(np.float64), 0.3, o64, pi)
+    got = d.grad.cpu().numpy()
+    assert _cos(got, dcot_ref) >= 0.9999
+    assert _rms(got - dcot_ref) <= 1e-4 * _rms(dcot_ref)
+    np.testing.assert_allclose(Om.grad.item(), Om_ref, rtol=1e-4)
+    # and the float32 oracle
+    _, dcot32, _ = O.gravity_vjp(pmid, disp, 0.3, oconf, pi)
+    assert _rms(got - dcot32) <= 1e-4 * _rms(dcot_ref)
+
+
+def test_gravity_general_dims():
+    """1-D / 2-D gravity (composition path) vs oracle, incl. autograd VJP vs oracle VJP."""
+    pm = _pm()
+    for shape in [(16,), (6, 9), (7, 8)]:
+        conf, oconf = _confs(shape, mesh_shape=1, spacing=1.3)
+        cosmo = pm.SimpleLCDM(conf)
+        pmid, disp, _, _ = O.gen_grid(oconf)
+        rng = np.random.default_rng(4)
+        disp = (disp + 1.1 * rng.standard_normal(disp.shape)).astype(np.float32)
+        d = torch.from_numpy(disp).cuda().requires_grad_(True)
+        ptcl = pm.Particles(conf, torch.from_numpy(pmid).cuda(), d)
+        acc = pm.gravity(1., ptcl, cosmo, conf)
+        ref = O.gravity(pmid, disp, 0.3, oconf)
+        np.testing.assert_allclose(acc.detach().cpu().numpy(), ref, rtol=2e-4, atol=2e-5 * _rms(ref))
+        pi = rng.standard_normal(disp.shape).astype(np.float32)
+        acc.backward(torch.from_numpy(pi).cuda())
+        o64 = O.Conf(1.3, shape, mesh_shape=1, float_dtype=np.float64)
+        _, dcot, _ = O.gravity_vjp(pmid, disp.astype(np.float64), 0.3, o64, pi)
+        assert _cos(d.grad.cpu().numpy(), dcot) >= 0.9999
+
+
+# --------------------------------------------------------------------------- leapfrog
+def test_kick_drift_bit_exact():
+    """nbody.py:39-46,70-77: mul-then-add in float32 -> bitwise equal to NumPy."""
+    from pmwd_b200 import _lib
+    rng = np.random.default_rng(0)
+    for n in (3, 1000, 3 * 12345):
+        disp, vel, acc = (rng.standard_normal(n).astype(np.float32) for _ in range(3))
+        K, D = np.float32(0.37), np.float32(-1.91)
+        td, tv, ta = (torch.from_numpy(x.copy()).cuda() for x in (disp, vel, acc))
+        _lib.check(_lib.lib().pmwd_kick_drift(_lib.stream_ptr(), n, _lib.ptr(td), _lib.ptr(tv),
+                                              _lib.ptr(ta), float(K), float(D), 1, 1), 'kd')
+        v = vel + acc * K
+        x = disp + v * D
+        np.testing.assert_array_equal(tv.cpu().numpy(), v)
+        np.testing.assert_array_equal(td.cpu().numpy(), x)
+
+
+def test_kick_drift_adj_vs_numpy():
+    from pmwd_b200 import _lib
+    rng = np.random.default_rng(1)
+    n = 3 * 5001
+    disp, vel, acc, xi, pi, alpha = (rng.standard_normal(n).astype(np.float32) for _ in range(6))
+    K, D = np.float32(0.21), np.float32(0.83)
+    t = [torch.from_numpy(x.copy()).cuda() for x in (disp, vel, acc, xi, pi, alpha)]
+    sums = torch.zeros(2, dtype=torch.float64, device='cuda')
+    _lib.check(_lib.lib().pmwd_kick_drift_adj(
+        _lib.stream_ptr(), n, *[_lib.ptr(x) for x in t], float(K), float(D), 1, 1, _lib.ptr(sums)), 'kda')
+    v = vel + acc * K
+    x_ = xi - alpha * K
+    s_pa = np.sum(pi.astype(np.float64) * acc)
+    d_ = disp + v * D
+    p_ = pi - x_ * D
+    s_xv = np.sum(x_.astype(np.float64) * v)
+    np.testing.assert_array_equal(t[1].cpu().numpy(), v)
+    np.testing.assert_array_equal(t[3].cpu().numpy(), x_)
+    np.testing.assert_array_equal(t[0].cpu().numpy(), d_)
+    np.testing.assert_array_equal(t[4].cpu().numpy(), p_)
+    np.testing.assert_allclose(sums.cpu().numpy(), [s_pa, s_xv], rtol=1e-12)
+
+
+def test_step_factors_vs_oracle():
+    """nbody.py:12-36 in float64: torch host code vs the NumPy/scipy oracle, and the
+    autograd factor gradients vs the oracle's finite differences."""
+    pm = _pm()
+    from pmwd_b200.nbody import kick_factor, drift_factor, _factor_valgrad
+    conf, oconf = _confs((4, 4, 4))
+    cosmo = pm.boltzmann(pm.SimpleLCDM(conf), conf)
+    ocosmo = O.boltzmann(O.SimpleLCDM(oconf), oconf)
+    ocosmo_same = ocosmo.replace(growth=cosmo.growth.numpy())      # identical table
+    a = oconf.a_nbody
+    for i in (0, 10, 40, 62):
+        a0, a1 = a[i], a[i + 1]
+        am = 0.5 * (a0 + a1)
+        for fun, ofun, args in ((kick_factor, O.kick_factor, (a0, a0, am)),
+                                (drift_factor, O.drift_factor, (am, a0, a1)),
+                                (kick_factor, O.kick_factor, (a1, am, a1))):
+            val, grads = _factor_valgrad(fun, *args, cosmo, conf)
+            np.testing.assert_allclose(val, ofun(*args, ocosmo_same, oconf), rtol=1e-12)
+            np.testing.assert_allclose(val, ofun(*args, ocosmo, oconf), rtol=1e-6)
+            _, og = O.factor_grads(ofun, *args, ocosmo_same, oconf)
+            np.testing.assert_allclose(grads['Omega_m'].item(), og['Omega_m'], rtol=1e-6)
+            np.testing.assert_allclose(grads['growth'].numpy(), og['growth'], rtol=1e-5, atol=1e-9)
+
+
+# ------------------------------------------------------------------------------- LPT
+@pytest.mark.parametrize('order', [1, 2])
+def test_lpt_vs_oracle(order):
+    pm = _pm()
+    n = 32
+    conf, oconf = _confs((n, n, n), lpt_order=order)
+    cosmo = pm.boltzmann(pm.SimpleLCDM(conf), conf)
+    ocosmo = O.boltzmann(O.SimpleLCDM(oconf), oconf).replace(growth=cosmo.growth.numpy())
+    omodes = O.linear_modes(O.white_noise(0, oconf), ocosmo, oconf)
+    modes = pm.linear_modes(pm.white_noise(0, conf), cosmo, conf)
+    np.testing.assert_allclose(modes.cpu().numpy(), omodes, rtol=1e-5, atol=1e-6 * np.abs(omodes).max())
+    ptcl, _ = pm.lpt(modes, cosmo, conf)
+    ref = O.lpt(omodes, ocosmo, oconf)
+    assert torch.equal(ptcl.pmid.cpu(), torch.from_numpy(ref['pmid']))
+    assert _rms(ptcl.disp.cpu().numpy() - ref['disp']) <= 1e-5 * _rms(ref['disp'])
+    assert _rms(ptcl.vel.cpu().numpy() - ref['vel']) <= 1e-5 * _rms(ref['vel'])
+
+
+# ------------------------------------------------------------------------------ N-body
+def _ic(n, seed=0, **kw):
+    pm = _pm()
+    conf, oconf = _confs((n, n, n), **kw)
+    cosmo = pm.boltzmann(pm.SimpleLCDM(conf), conf)
+    ocosmo = O.boltzmann(O.SimpleLCDM(oconf), oconf).replace(growth=cosmo.growth.numpy())
+    omodes = O.linear_modes(O.white_noise(seed, oconf), ocosmo, oconf)
+    ic = O.lpt(omodes, ocosmo, oconf)
+    ptcl = pm.Particles(conf, torch.from_numpy(ic['pmid']).cuda(), torch.from_numpy(ic['disp']).cuda(),
+                        vel=torch.from_numpy(ic['vel']).cuda())
+    return pm, conf, oconf, cosmo, ocosmo, ic, ptcl
+
+
+@pytest.mark.parametrize('mode', ['atomic', 'deterministic'])
+def test_nbody_config1_vs_oracle(mode):
+    """BASELINE config 1: 64^3 particles, 128^3 mesh, 2LPT + 10 leapfrog steps.  Final
+    positions within 1e-4 cell (max-norm), P(k) within 0.1 % at all k."""
+    pm, conf, oconf, cosmo, ocosmo, ic, ptcl = _ic(64, a_nbody_maxstep=0.1, scatter_mode=mode)
+    assert conf.a_nbody_num == 10
+    out, _ = pm.nbody(ptcl, None, cosmo, conf)
+    ref = O.nbody(dict(ic), ocosmo, oconf)
+    cell = conf.cell_size
+    dpos = np.abs(out.disp.cpu().numpy() - ref['disp']) / cell
+    assert dpos.max() <= 1e-4, dpos.max()
+    dvel = _rms(out.vel.cpu().numpy() - ref['vel']) / _rms(ref['vel'])
+    assert dvel <= 1e-5
+    assert _rms(out.acc.cpu().numpy() - ref['acc']) <= 1e-5 * _rms(ref['acc'])
+    dens = pm.scatter(out, conf).cpu().numpy()
+    oden = O.scatter(ref['pmid'], ref['disp'], oconf)
+    k, P, N, _ = O.powspec(dens, conf.cell_size)
+    k2, P2, _, _ = O.powspec(oden, conf.cell_size)
+    assert np.abs(P / P2 - 1).max() <= 1e-3
+    # 3-digit sanity of the physics (growth of structure): disp std grows by ~D(1)/D(1/64)
+    assert 30 < out.disp.std().item() / ptcl.disp.std().item() < 60
+
+
+def test_nbody_reversibility():
+    """pm_test.py:177-192: forward then reverse integration returns the initial state to
+    float32 round-off (RMSD/sigma of the order of the reference's table, adjoint.tex:1534-1541)."""
+    pm, conf, oconf, cosmo, ocosmo, ic, ptcl = _ic(32, a_nbody_maxstep=0.1)
+    out, _ = pm.nbody(ptcl, None, cosmo, conf)
+    back, _ = pm.nbody(out, None, cosmo, conf, reverse=True)
+    r_disp = _rms((back.disp - ptcl.disp).cpu().numpy()) / _rms(ptcl.disp.cpu().numpy())
+    r_vel = _rms((back.vel - ptcl.vel).cpu().numpy()) / _rms(ptcl.vel.cpu().numpy())
+    assert r_disp < 5e-2 and r_vel < 7e-2
+    # same statistic from the oracle: ours must not be worse than 3x
+    oref = O.nbody(O.nbody(dict(ic), ocosmo, oconf), ocosmo, oconf, reverse=True)
+    o_disp = _rms(oref['disp'] - ic['disp']) / _rms(ic['disp'])
+    assert r_disp <= 3 * o_disp + 1e-6
+
+
+def test_nbody_step_api_matches_nbody():
+    """nbody_init / nbody_step (imported by user scripts, demo_data_time_evo.py:17) give the
+    same trajectory as nbody, and never modify their inputs."""
+    pm, conf, oconf, cosmo, ocosmo, ic, ptcl = _ic(16, a_nbody_maxstep=0.25, scatter_mode='deterministic')
+    d0 = ptcl.disp.clone()
+    out, _ = pm.nbody(ptcl, None, cosmo, conf)
+    a = conf.a_nbody
+    p, obs = pm.nbody_init(a[0], ptcl, None, cosmo, conf)
+    for a0, a1 in zip(a[:-1], a[1:]):
+        p, obs = pm.nbody_step(a0, a1, p, obs, cosmo, conf)
+    assert torch.equal(p.disp, out.disp) and torch.equal(p.vel, out.vel)
+    assert torch.equal(ptcl.disp, d0)
+
+
+@pytest.mark.parametrize('mode', ['atomic', 'deterministic'])
+def test_nbody_adjoint_vs_oracle(mode):
+    """Reverse-time adjoint (nbody.py:226-276) vs the oracle's: particle cotangents with
+    cosine >= 0.9999, cosmology cotangent leaves within 1e-3 relative."""
+    pm, conf, oconf, cosmo, ocosmo, ic, ptcl = _ic(16, a_nbody_maxstep=0.125, scatter_mode=mode)
+    rng = np.random.default_rng(5)
+    w_disp = rng.standard_normal(ic['disp'].shape).astype(np.float32)
+    w_vel = rng.standard_normal(ic['disp'].shape).astype(np.float32)
+
+    Om = torch.tensor(0.3, dtype=torch.float64, requires_grad=True)
+    gt = cosmo.growth.detach().clone().requires_grad_(True)
+    c = cosmo.replace(Omega_m=Om, growth=gt)
+    d = ptcl.disp.clone().requires_grad_(True)
+    v = ptcl.vel.clone().requires_grad_(True)
+    out, _ = pm.nbody(ptcl.replace(disp=d, vel=v), None, c, conf)
+    obj = (out.disp * torch.from_numpy(w_disp).cuda()).sum() + (out.vel * torch.from_numpy(w_vel).cuda()).sum()
+    obj.backward()
+
+    o64 = O.Conf(1., (16,) * 3, mesh_shape=2, float_dtype=np.float64, a_nbody_maxstep=0.125)
+    ic64 = dict(pmid=ic['pmid'], disp=ic['disp'].astype(np.float64), vel=ic['vel'].astype(np.float64))
+    final = O.nbody(ic64, ocosmo, o64)
+    cot = dict(disp=w_disp.astype(np.float64), vel=w_vel.astype(np.float64),
+               acc=np.zeros_like(ic64['disp']))
+    _, pc, cc = O.nbody_adj(final, cot, ocosmo, o64)
+    assert _cos(d.grad.cpu().numpy(), pc['disp']) >= 0.9999
+    assert _cos(v.grad.cpu().numpy(), pc['vel']) >= 0.9999
+    assert _rms(d.grad.cpu().numpy() - pc['disp']) <= 1e-3 * _rms(pc['disp'])
+    np.testing.assert_allclose(Om.grad.item(), cc['Omega_m'], rtol=1e-3)
+    assert _cos(gt.grad.numpy(), cc['growth']) >= 0.9999
+
+
+def test_full_gradient_pipeline():
+    """grads.py model: obj = var(scatter(nbody(lpt(linear_modes(white)))) - target).
+    Gradient w.r.t. the real white-noise modes vs the oracle adjoint chain (cos >= 0.9999);
+    gradient w.r.t. (A_s, n_s, Omega_m, Omega_b, h) vs float64 finite differences of the
+    oracle pipeline (cos >= 0.9999)."""
+    pm = _pm()
+    n = 16
+    kw = dict(a_start=1 / 16, a_nbody_maxstep=1 / 8)
+    conf, oconf = _confs((n, n, n), **kw)
+    o64 = O.Conf(1., (n,) * 3, mesh_shape=2, float_dtype=np.float64, **kw)
+    names = ('A_s_1e9', 'n_s', 'Omega_m', 'Omega_b', 'h')
+    vals = dict(A_s_1e9=2.0, n_s=0.96, Omega_m=0.3, Omega_b=0.05, h=0.7)
+    white = O.white_noise(1, oconf, real=True)
+    tgt_white = O.white_noise(0, oconf, real=True)
+
+    def omodel(w, p, conf_):
+        c = O.boltzmann(O.Cosmo(conf_, **p), conf_)
+        ic = O.lpt(O.linear_modes(w.astype(conf_.float_dtype), c, conf_), c, conf_)
+        out = O.nbody(ic, c, conf_)
+        return O.scatter(out['pmid'], out['disp'], conf_), out, c
+
+    target, _, _ = omodel(tgt_white, vals, o64)
+
+    # ---- ours
+    theta = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in vals.items()}
+    cosmo = pm.boltzmann(pm.Cosmology(conf, **theta), conf)
+    w = torch.from_numpy(white).cuda().requires_grad_(True)
+    modes = pm.linear_modes(w, cosmo, conf)
+    ptcl, obs = pm.lpt(modes, cosmo, conf)
+    ptcl, obs = pm.nbody(ptcl, obs, cosmo, conf)
+    dens = pm.scatter(ptcl, conf)
+    obj = (dens - torch.from_numpy(target.astype(np.float32)).cuda()).var(unbiased=False)
+    obj.backward()
+
+    # ---- oracle: objective value
+    dens64, out64, c64 = omodel(white, vals, o64)
+    obj64 = np.var(dens64 - target)
+    np.testing.assert_allclose(obj.item(), obj64, rtol=1e-3)
+
+    # ---- oracle: white-noise gradient by the adjoint chain in float64
+    dens_cot = 2 * (dens64 - target - np.mean(dens64 - target)) / dens64.size
+    dcot, _ = O.scatter_adj(out64['pmid'], out64['disp'], o64, dens_cot)
+    cot = dict(disp=dcot, vel=np.zeros_like(dcot), acc=np.zeros_like(dcot))
+    _, pc, _ = O.nbody_adj(out64, cot, c64, o64)
+    gw = O.lpt_vjp_modes(white.astype(np.float64), c64, o64, pc['disp'], pc['vel'])
+    assert _cos(w.grad.cpu().numpy(), gw) >= 0.9999
+    assert _rms(w.grad.cpu().numpy() - gw) <= 2e-2 * _rms(gw)
+
+    # ---- oracle: cosmology gradient by central finite differences of the whole model
+    fd = []
+    for nme in names:
+        h = 1e-6 * abs(vals[nme])   # small: CIC is only piecewise smooth
+        pp = dict(vals); pp[nme] += h
+        pm_ = dict(vals); pm_[nme] -= h
+        fp = np.var(omodel(white, pp, o64)[0] - target)
+        fm = np.var(omodel(white, pm_, o64)[0] - target)
+        fd.append((fp - fm) / (2 * h))
+    got = [theta[nme].grad.item() for nme in names]
+    assert _cos(got, fd) >= 0.9999, (got, fd)
+    np.testing.assert_allclose(got, fd, rtol=2e-2)
