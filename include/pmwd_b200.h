@@ -76,6 +76,19 @@ int pmwd_ctx_destroy(pmwd_ctx* ctx);
 /* Create R2C + C2R plans for a real field of `rank` dims `shape` (float). */
 int pmwd_ctx_reserve(pmwd_ctx* ctx, int rank, const int32_t* shape);
 
+/* ---- instrumentation (no reference counterpart; used by bench.py) -------------------- */
+/* Number of hand-written kernels launched by this process so far. */
+long long pmwd_launch_count(void);
+/* Per-stage CUDA-event timing of the kernels enqueued by pmwd_force / pmwd_force_adj /
+ * pmwd_kick_drift(_adj) / pmwd_scatter: events are recorded on the caller's stream around
+ * each stage while enabled.  pmwd_profile_read synchronises the device, returns accumulated
+ * milliseconds and call counts per stage (arrays of pmwd_profile_stage_count() entries) and
+ * resets the records. */
+int pmwd_profile_enable(int on);
+int pmwd_profile_stage_count(void);
+const char* pmwd_profile_stage_name(int stage);
+int pmwd_profile_read(double* ms, long long* calls);
+
 /* ---- FFT: pmwd/pm_util.py:236-344 (fftfwd / fftinv = rfftn / irfftn) -------------- */
 /* out[n0][n1][n2/2+1] = rfftn(in), unnormalised (pmwd/pm_util.py:281). */
 int pmwd_fft_r2c(pmwd_ctx* ctx, void* stream, int rank, const int32_t* shape,

@@ -46,6 +46,11 @@ _i32p = C.POINTER(C.c_int32)
 _SIGNATURES = {
     'pmwd_abi_version': (_i, []),
     'pmwd_last_error': (_i, [C.c_char_p, _sz]),
+    'pmwd_launch_count': (C.c_longlong, []),
+    'pmwd_profile_enable': (_i, [_i]),
+    'pmwd_profile_stage_count': (_i, []),
+    'pmwd_profile_stage_name': (C.c_char_p, [_i]),
+    'pmwd_profile_read': (_i, [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     'pmwd_ctx_create': (_i, [C.POINTER(_vp), _i]),
     'pmwd_ctx_destroy': (_i, [_vp]),
     'pmwd_ctx_reserve': (_i, [_vp, _i, _i32p]),
@@ -102,6 +107,23 @@ def last_error():
 def check(rc, what):
     if rc != 0:
         raise PmwdError(f'{what} failed with status {rc}: {last_error()}')
+
+
+def profile_enable(on):
+    check(lib().pmwd_profile_enable(int(bool(on))), 'pmwd_profile_enable')
+
+
+def profile_read():
+    """{stage name: (milliseconds, calls)} accumulated since the last read (synchronises)."""
+    n = lib().pmwd_profile_stage_count()
+    ms = (C.c_double * n)()
+    calls = (C.c_longlong * n)()
+    check(lib().pmwd_profile_read(ms, calls), 'pmwd_profile_read')
+    return {lib().pmwd_profile_stage_name(i).decode(): (ms[i], calls[i]) for i in range(n)}
+
+
+def launch_count():
+    return int(lib().pmwd_launch_count())
 
 
 def stream_ptr(device=None):

@@ -42,7 +42,25 @@ void set_error(const char* fmt, ...);
     }                                                                               \
   } while (0)
 
-#define PMWD_LAUNCH_CHECK() PMWD_CUDA_TRY(cudaPeekAtLastError())
+// every hand-written kernel launch goes through this: error check + launch counter
+void count_launch();
+#define PMWD_LAUNCH_CHECK()                    \
+  do {                                         \
+    ::pmwd::count_launch();                    \
+    PMWD_CUDA_TRY(cudaPeekAtLastError());      \
+  } while (0)
+
+// Optional per-stage CUDA-event profiling (off by default; used by bench.py for the roofline).
+enum Stage {
+  ST_MEMSET = 0, ST_SCATTER, ST_FFT_R2C, ST_KSPACE, ST_FFT_C2R, ST_GATHER, ST_KICK_DRIFT,
+  ST_SCATTER3, ST_KSPACE_ADJ, ST_GATHER_ADJ, ST_KICK_DRIFT_ADJ, ST_OTHER, ST_COUNT
+};
+struct StageTimer {
+  StageTimer(int stage, cudaStream_t st);
+  ~StageTimer();
+  int idx;
+  cudaStream_t st;
+};
 
 // B200: 148 SMs.  Grid-stride kernels are launched with a multiple of the SM count.
 int sm_count();

@@ -86,22 +86,35 @@ static int force_forward(pmwd_ctx* ctx, cudaStream_t st, const pmwd_cic_desc* d,
   // scatter.py:37-39: val = conf.mesh_size / conf.ptcl_num (python float -> float32)
   const float val = (float)((double)nm / (double)d->ptcl_num);
   if (val_out) *val_out = val;
-  PMWD_CUDA_TRY(cudaMemsetAsync(rho, 0, (size_t)nm * sizeof(float), st));
+  {
+    StageTimer t(ST_MEMSET, st);
+    PMWD_CUDA_TRY(cudaMemsetAsync(rho, 0, (size_t)nm * sizeof(float), st));
+  }
   int rc;
-  if (mode == PMWD_SCATTER_DETERMINISTIC)
-    rc = scatter_det(st, d, pmid, disp, nullptr, val, 1, rho, nullptr, nullptr, ws + L.det,
-                     L.total - L.det);
-  else
-    rc = scatter_fast(st, d, pmid, disp, nullptr, val, 1, rho, nullptr, nullptr);
+  {
+    StageTimer t(ST_SCATTER, st);
+    if (mode == PMWD_SCATTER_DETERMINISTIC)
+      rc = scatter_det(st, d, pmid, disp, nullptr, val, 1, rho, nullptr, nullptr, ws + L.det,
+                       L.total - L.det);
+    else
+      rc = scatter_fast(st, d, pmid, disp, nullptr, val, 1, rho, nullptr, nullptr);
+  }
   if (rc) return rc;
-  rc = fft_r2c(ctx, st, 3, shape, rho, ws + L.rho_k);
+  {
+    StageTimer t(ST_FFT_R2C, st);
+    rc = fft_r2c(ctx, st, 3, shape, rho, ws + L.rho_k);
+  }
   if (rc) return rc;
   void* g[3] = {ws + L.g[0], ws + L.g[1], ws + L.g[2]};
   const float scale = (float)(1.5 * Omega_m / (double)nm);
-  rc = pmwd_kspace_force(st, 3, shape, d->cell_size, scale, ws + L.rho_k, g);
+  {
+    StageTimer t(ST_KSPACE, st);
+    rc = pmwd_kspace_force(st, 3, shape, d->cell_size, scale, ws + L.rho_k, g);
+  }
   if (rc) return rc;
   float* F[3] = {(float*)(ws + L.rho_f0), (float*)(ws + L.f1), (float*)(ws + L.f2)};
   for (int a = 0; a < 3; ++a) {
+    StageTimer t(ST_FFT_C2R, st);
     rc = fft_c2r(ctx, st, 3, shape, g[a], F[a]);
     if (rc) return rc;
   }
@@ -120,7 +133,7 @@ extern "C" size_t pmwd_scatter_scratch_bytes(const pmwd_cic_desc* d, int mode) {
 extern "C" int pmwd_scatter(void* stream, const pmwd_cic_desc* d, const void* pmid,
                             const float* disp, const float* val, float val_scalar, float* mesh,
                             int mode, void* scratch, size_t scratch_bytes) {
-  PMWD_REQUIRE(d && pmid && disp && mesh, "null buffer");
+  PMWD_REQUIRE(d && mesh && (d->ptcl_num == 0 || (pmid && disp)), "null buffer");
   cudaStream_t st = as_stream(stream);
   if (mode == PMWD_SCATTER_DETERMINISTIC) {
     PMWD_REQUIRE(d->nchan == 1, "deterministic scatter via pmwd_scatter supports scalar fields");
@@ -136,14 +149,14 @@ extern "C" int pmwd_scatter(void* stream, const pmwd_cic_desc* d, const void* pm
 extern "C" int pmwd_gather(void* stream, const pmwd_cic_desc* d, const void* pmid,
                            const float* disp, const float* mesh, const float* val,
                            float val_scalar, float* out) {
-  PMWD_REQUIRE(d && pmid && disp && mesh && out, "null buffer");
+  PMWD_REQUIRE(d && mesh && (d->ptcl_num == 0 || (pmid && disp && out)), "null buffer");
   return cic_generic<1>(as_stream(stream), d, pmid, disp, val, val_scalar, mesh, nullptr, out, nullptr);
 }
 
 extern "C" int pmwd_scatter_adj(void* stream, const pmwd_cic_desc* d, const void* pmid,
                                 const float* disp, const float* mesh_cot, const float* val,
                                 float val_scalar, float* disp_cot, float* val_cot) {
-  PMWD_REQUIRE(d && pmid && disp && mesh_cot && disp_cot, "null buffer");
+  PMWD_REQUIRE(d && mesh_cot && (d->ptcl_num == 0 || (pmid && disp && disp_cot)), "null buffer");
   return cic_generic<2>(as_stream(stream), d, pmid, disp, val, val_scalar, mesh_cot, nullptr,
                         disp_cot, val_cot);
 }
@@ -151,7 +164,7 @@ extern "C" int pmwd_scatter_adj(void* stream, const pmwd_cic_desc* d, const void
 extern "C" int pmwd_gather_adj(void* stream, const pmwd_cic_desc* d, const void* pmid,
                                const float* disp, const float* mesh, const float* val_cot,
                                float val_cot_scalar, float* disp_cot, float* mesh_cot) {
-  PMWD_REQUIRE(d && pmid && disp && mesh && disp_cot, "null buffer");
+  PMWD_REQUIRE(d && mesh && (d->ptcl_num == 0 || (pmid && disp && disp_cot)), "null buffer");
   return cic_generic<3>(as_stream(stream), d, pmid, disp, val_cot, val_cot_scalar, mesh, mesh_cot,
                         disp_cot, nullptr);
 }
@@ -180,6 +193,7 @@ extern "C" int pmwd_force(pmwd_ctx* ctx, void* stream, const pmwd_cic_desc* d, c
   char* ws = (char*)workspace;
   rc = force_forward(ctx, st, d, pmid, disp, Omega_m, mode, ws, L, nullptr);
   if (rc) return rc;
+  StageTimer t(ST_GATHER, st);
   return gather3_fast(st, d, pmid, disp, (float*)(ws + L.rho_f0), (float*)(ws + L.f1),
                       (float*)(ws + L.f2), acc, kick_vel, kick_factor);
 }
@@ -206,29 +220,46 @@ extern "C" int pmwd_force_adj(pmwd_ctx* ctx, void* stream, const pmwd_cic_desc* 
   rc = force_forward(ctx, st, d, pmid, disp, Omega_m, mode, ws, L, &val);
   if (rc) return rc;
   float* F[3] = {(float*)(ws + L.rho_f0), (float*)(ws + L.f1), (float*)(ws + L.f2)};
-  rc = gather3_fast(st, d, pmid, disp, F[0], F[1], F[2], acc, nullptr, 0.f);
+  {
+    StageTimer t(ST_GATHER, st);
+    rc = gather3_fast(st, d, pmid, disp, F[0], F[1], F[2], acc, nullptr, 0.f);
+  }
   if (rc) return rc;
 
   // V_i = scatter(pi_i): the mesh_cot of _gather_bwd (gather.py:113), SoA, in the (now free)
   // gradient-spectrum buffers
   float* V[3] = {(float*)(ws + L.g[0]), (float*)(ws + L.g[1]), (float*)(ws + L.g[2])};
-  for (int a = 0; a < 3; ++a) PMWD_CUDA_TRY(cudaMemsetAsync(V[a], 0, (size_t)nm * sizeof(float), st));
-  if (mode == PMWD_SCATTER_DETERMINISTIC)
-    rc = scatter_det(st, d, pmid, disp, pi, 0.f, 3, V[0], V[1], V[2], ws + L.det, L.total - L.det);
-  else
-    rc = scatter_fast(st, d, pmid, disp, pi, 0.f, 3, V[0], V[1], V[2]);
+  {
+    StageTimer t(ST_MEMSET, st);
+    for (int a = 0; a < 3; ++a) PMWD_CUDA_TRY(cudaMemsetAsync(V[a], 0, (size_t)nm * sizeof(float), st));
+  }
+  {
+    StageTimer t(ST_SCATTER3, st);
+    if (mode == PMWD_SCATTER_DETERMINISTIC)
+      rc = scatter_det(st, d, pmid, disp, pi, 0.f, 3, V[0], V[1], V[2], ws + L.det, L.total - L.det);
+    else
+      rc = scatter_fast(st, d, pmid, disp, pi, 0.f, 3, V[0], V[1], V[2]);
+  }
   if (rc) return rc;
   const void* S[3] = {ws + L.s[0], ws + L.s[1], ws + L.s[2]};
   for (int a = 0; a < 3; ++a) {
+    StageTimer t(ST_FFT_R2C, st);
     rc = fft_r2c(ctx, st, 3, shape, V[a], ws + L.s[a]);
     if (rc) return rc;
   }
   // rho_cot_k = (1.5 Omega_m / N_m) * sum_i (+i k_i)(-V_i,k / k^2)   [A_i^T = -A_i]
   const float scale = (float)(1.5 * Omega_m / (double)nm);
-  rc = pmwd_kspace_force_adj(st, 3, shape, d->cell_size, scale, S, ws + L.rho_k);
+  {
+    StageTimer t(ST_KSPACE_ADJ, st);
+    rc = pmwd_kspace_force_adj(st, 3, shape, d->cell_size, scale, S, ws + L.rho_k);
+  }
   if (rc) return rc;
   float* rho_cot = (float*)(ws + L.g[0]);
-  rc = fft_c2r(ctx, st, 3, shape, ws + L.rho_k, rho_cot);
+  {
+    StageTimer t(ST_FFT_C2R, st);
+    rc = fft_c2r(ctx, st, 3, shape, ws + L.rho_k, rho_cot);
+  }
   if (rc) return rc;
+  StageTimer t(ST_GATHER_ADJ, st);
   return force_adj_gather(st, d, pmid, disp, F[0], F[1], F[2], rho_cot, pi, val, alpha);
 }

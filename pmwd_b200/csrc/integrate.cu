@@ -140,6 +140,7 @@ extern "C" int pmwd_kick_drift(void* stream, int64_t n, float* disp, float* vel,
   PMWD_REQUIRE(aligned16(disp) && aligned16(vel) && aligned16(acc), "arrays must be 16-byte aligned");
   if (n == 0 || (!do_kick && !do_drift)) return PMWD_OK;
   cudaStream_t st = as_stream(stream);
+  StageTimer timer(ST_KICK_DRIFT, st);
   int grid = grid_for((n + 3) / 4, 256, 8);
   if (do_kick && do_drift) kick_drift_kernel<true, true><<<grid, 256, 0, st>>>(n, disp, vel, acc, K, D);
   else if (do_kick) kick_drift_kernel<true, false><<<grid, 256, 0, st>>>(n, disp, vel, acc, K, D);
@@ -159,6 +160,7 @@ extern "C" int pmwd_kick_drift_adj(void* stream, int64_t n, float* disp, float* 
                aligned16(pi) && aligned16(alpha), "arrays must be 16-byte aligned");
   if (n == 0 || (!do_kick && !do_drift)) return PMWD_OK;
   cudaStream_t st = as_stream(stream);
+  StageTimer timer(ST_KICK_DRIFT_ADJ, st);
   int grid = grid_for((n + 3) / 4, 256, 8);
   if (do_kick && do_drift)
     kick_drift_adj_kernel<true, true><<<grid, 256, 0, st>>>(n, disp, vel, acc, xi, pi, alpha, K, D, sums);

@@ -208,14 +208,15 @@ _COSMO_LEAVES = ('Omega_m', 'Omega_k_', 'w_0_', 'w_a_', 'growth')
 def _factor_valgrad(fun, a0, a1, a2, cosmo, conf):
     """``value_and_grad(fun, argnums=3)`` (``nbody.py:51-52,82-83``) w.r.t. the cosmology
     leaves a step factor can depend on."""
-    leaves = {n: getattr(cosmo, n).detach().clone().requires_grad_(True)
-              for n in _COSMO_LEAVES if getattr(cosmo, n) is not None}
-    c = cosmo.replace(**leaves)
-    val = fun(a0, a1, a2, c, conf)
-    grads = torch.autograd.grad(val, list(leaves.values()), allow_unused=True)
+    with torch.enable_grad():
+        leaves = {n: getattr(cosmo, n).detach().clone().requires_grad_(True)
+                  for n in _COSMO_LEAVES if getattr(cosmo, n) is not None}
+        c = cosmo.replace(**leaves)
+        val = fun(a0, a1, a2, c, conf)
+        grads = torch.autograd.grad(val, list(leaves.values()), allow_unused=True)
     grads = {n: (g if g is not None else torch.zeros_like(leaves[n]))
              for n, g in zip(leaves, grads)}
-    return float(val), grads
+    return float(val.detach()), grads
 
 
 def nbody_adj(ptcl, ptcl_cot, obsvbl_cot, cosmo, conf, reverse=False):
