@@ -151,6 +151,7 @@ def workload_config(args, ngpu):
                         f'first W+K steps of the 63-step schedule to a=1',
             'ptcl_grid': list(shape), 'mesh': [2 * s for s in shape], 'ptcl_spacing_mpc_h': 1.0,
             'cosmology': 'SimpleLCDM', 'seed': 0, 'scatter_mode': args.scatter_mode,
+            'reorder_every': args.reorder_every,
             'cache': 'inputs (>= 5 GB particle state, 4 GB meshes) far exceed the 126 MB L2; no flush needed',
             'parallelism': f'slab{ngpu}' if ngpu > 1 else 'single'}
 
@@ -172,7 +173,7 @@ def run_ours(args):
     import torch
     import pmwd_b200 as pm
     from pmwd_b200 import _lib
-    from pmwd_b200.nbody import _integrate_inplace, _force_inplace, _owned
+    from pmwd_b200.nbody import _integrate_inplace, _force_inplace, _store_from
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -187,7 +188,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     n = args.n
-    conf = pm.Configuration(1., (n, n, n), mesh_shape=2, scatter_mode=args.scatter_mode, device=dev)
+    conf = pm.Configuration(1., (n, n, n), mesh_shape=2, scatter_mode=args.scatter_mode, device=dev,
+                            reorder_every=args.reorder_every, reorder_min_disp=args.reorder_min_disp)
     cosmo = pm.boltzmann(pm.SimpleLCDM(conf), conf)
     with torch.no_grad():
         modes = pm.linear_modes(pm.white_noise(0, conf), cosmo, conf)
@@ -199,18 +201,18 @@ def run_ours(args):
     Np, Nm = conf.ptcl_num, conf.mesh_size
 
     def fresh():
-        p = _owned(ic, conf)
-        _force_inplace(p, cosmo, conf)
-        return p
+        st = _store_from(ic, conf)
+        _force_inplace(st.ptcl, cosmo, conf)
+        return st
 
     W, K = args.warmup, args.steps
     with torch.no_grad():
-        ptcl = fresh()
+        store = fresh()
         i = 0
         for _ in range(W):
             if i == nsched:
-                ptcl, i = fresh(), 0
-            _integrate_inplace(a[i], a[i + 1], ptcl, cosmo, conf); i += 1
+                store, i = fresh(), 0
+            _integrate_inplace(a[i], a[i + 1], store.ptcl, cosmo, conf); store.maybe_reorder(); i += 1
         torch.cuda.synchronize()
         sampler = ClockSampler(local); sampler.start()
         _lib.profile_enable(True); _lib.profile_read()
@@ -220,8 +222,8 @@ def run_ours(args):
         e0.record()
         for _ in range(K):
             if i == nsched:
-                ptcl, i = fresh(), 0
-            _integrate_inplace(a[i], a[i + 1], ptcl, cosmo, conf); i += 1
+                store, i = fresh(), 0
+            _integrate_inplace(a[i], a[i + 1], store.ptcl, cosmo, conf); store.maybe_reorder(); i += 1
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
@@ -229,7 +231,8 @@ def run_ours(args):
         stages = _lib.profile_read()
         _lib.profile_enable(False)
         clocks = sampler.stop()
-    assert torch.isfinite(ptcl.disp).all()
+    assert torch.isfinite(store.arrays['disp']).all()
+    reorders = store.reorders
     value = Np * K / (ms * 1e-3)
 
     # ---- per-stage roofline: algorithmic bytes per launch (SURVEY.md 8d / DESIGN.md)
@@ -238,13 +241,16 @@ def run_ours(args):
            'kspace_force': 16 * Nm, 'fft_c2r': 8 * Nm, 'gather3': 54 * Np + 12 * Nm}
     kernels = {}
     for name, (tms, calls) in stages.items():
-        if calls == 0 or name not in alg:
+        if calls == 0:
+            continue
+        if name not in alg:      # e.g. 'other' = cell sort + permutation of the particle storage
+            kernels[name] = {'ms_total': round(tms, 3), 'launches': calls, 'share_of_step': round(tms / ms, 4)}
             continue
         per = tms / calls
         ach = alg[name] / per / 1e6
         kernels[name] = {'ms_per_launch': round(per, 4), 'launches': calls, 'share_of_step': round(tms / ms, 4),
                          'alg_bytes': alg[name], 'achieved_GBps': round(ach, 1), 'frac': round(ach / peak, 4)}
-    ours = [k for k in kernels if not k.startswith('fft_') and k != 'memset']
+    ours = [k for k in kernels if k in alg and not k.startswith('fft_') and k != 'memset']
     dom = max(ours, key=lambda k: kernels[k]['share_of_step'])
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
@@ -266,7 +272,7 @@ def run_ours(args):
     p0, _ = pm.nbody_init(a[0], ic, None, cosmo, conf)
     for k in host:
         host[k].copy_(getattr(p0, k))
-    del p0, ptcl
+    del p0, store
     torch.cuda.empty_cache()
     h2d = sum(t.numel() * t.element_size() for t in host.values())
     d2h = sum(host[k].numel() * host[k].element_size() for k in ('disp', 'vel', 'acc'))
@@ -307,7 +313,7 @@ def run_ours(args):
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': workload_config(args, 1),
         'steps_per_sec': K / (ms * 1e-3),
-        'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches,
+        'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'storage_reorders': reorders,
         'roofline': roofline, 'kernels': kernels, 'cpu_baseline': cpu,
         'context': {'h100_pcie_jax_derived_updates_per_s': 6.5e8,
                     'note': 'BASELINE.md derived figure for the same geometry on other hardware; not a published '
@@ -325,6 +331,8 @@ def main():
     ap.add_argument('--n', type=int, default=512, help='particles per side per GPU (mesh is 2x)')
     ap.add_argument('--scatter-mode', default='atomic', choices=['atomic', 'deterministic'])
     ap.add_argument('--e2e-steps', type=int, default=4)
+    ap.add_argument('--reorder-every', type=int, default=4)
+    ap.add_argument('--reorder-min-disp', type=float, default=1.5)
     ap.add_argument('--cpu-n', type=int, default=96)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()

@@ -143,6 +143,31 @@ int pmwd_kspace_force_adj(void* stream, int rank, const int32_t* shape, double s
 int pmwd_strain(void* stream, int rank, const int32_t* shape, double spacing, int i, int j,
                 const void* pot_c64, void* out_c64);
 
+/* ---- slab-decomposed (multi-GPU) building blocks ------------------------------------- */
+/* The reference's own (offset, mesh shape) semantics describe a slab: a mesh array holding
+ * d->mesh_shape[0] x-planes starting at global plane d->offset[0] / cell_size of the periodic
+ * mesh d->wrap_shape; neighbours outside the array are dropped (pm_util.py:119-141).
+ * SoA scatter of 1 or 3 channels (rho, or the three V_i = scatter(pi_i) of gather.py:113): */
+int pmwd_scatter_soa(void* stream, const pmwd_cic_desc* d, const void* pmid, const float* disp,
+                     const float* val, float val_scalar, int nch, float* m0, float* m1, float* m2);
+/* acc[N][3] = (gather(f0), gather(f1), gather(f2)) in one pass (gravity.py:61-70), optionally
+ * followed by vel += acc * kick_factor (nbody.py:70-77). */
+int pmwd_gather3(void* stream, const pmwd_cic_desc* d, const void* pmid, const float* disp,
+                 const float* f0, const float* f1, const float* f2, float* acc, float* kick_vel,
+                 float kick_factor);
+/* alpha = disp cotangent of gravity from the three force meshes and rho_cot
+ * (gather.py:106-110 x3 + scatter.py:112-116). */
+int pmwd_force_adj_gather(void* stream, const pmwd_cic_desc* d, const void* pmid,
+                          const float* disp, const float* f0, const float* f1, const float* f2,
+                          const float* rho_cot, const float* pi, float val, float* alpha);
+/* k-space kernels on the transposed slab [n0][ny_local][n2/2+1] that holds global rows
+ * y0 .. y0+ny_local-1 of axis 1 (layout after the distributed FFT's all-to-all). */
+int pmwd_kspace_force_slab(void* stream, const int32_t* shape, int y0, int ny_local,
+                           double spacing, float scale, const void* rho_c64, void* const* g_c64);
+int pmwd_kspace_force_adj_slab(void* stream, const int32_t* shape, int y0, int ny_local,
+                               double spacing, float scale, const void* const* v_c64,
+                               void* out_c64);
+
 /* ---- fused force: gravity() (pmwd/gravity.py:47-72) -------------------------------- */
 /* Workspace (device bytes) needed by pmwd_force / pmwd_force_adj for this geometry. */
 size_t pmwd_force_workspace_bytes(const pmwd_cic_desc* d, int adjoint, int mode);
@@ -157,6 +182,20 @@ int pmwd_force(pmwd_ctx* ctx, void* stream, const pmwd_cic_desc* d, const void* 
 int pmwd_force_adj(pmwd_ctx* ctx, void* stream, const pmwd_cic_desc* d, const void* pmid,
                    const float* disp, double Omega_m, const float* pi, float* acc,
                    float* alpha, int mode, void* workspace, size_t workspace_bytes);
+
+/* ---- Eulerian re-ordering of the particle storage (no reference counterpart) ---------- */
+/* The reference stores particles in Lagrangian order (pmwd/particles.py:135-139); the
+ * integrator here periodically re-sorts its private copies by mesh cell so that scatter /
+ * gather stay coalesced, and restores the reference order on output.
+ * perm[i] = storage index of the particle that moves to sorted slot i (stable by cell). */
+size_t pmwd_cell_sort_scratch_bytes(const pmwd_cic_desc* d);
+int pmwd_cell_sort_perm(void* stream, const pmwd_cic_desc* d, const void* pmid, const float* disp,
+                        uint32_t* perm, void* scratch, size_t scratch_bytes);
+/* For each of `narr` row-major arrays (row_bytes[a] bytes per particle, even):
+ * inverse == 0: dst[i] = src[perm[i]];  inverse != 0: dst[perm[i]] = src[i]. */
+int pmwd_permute_rows(void* stream, int64_t n, const uint32_t* perm, int narr,
+                      const void* const* src, void* const* dst, const int32_t* row_bytes,
+                      int inverse);
 
 /* ---- leapfrog updates: pmwd/nbody.py:39-99 ----------------------------------------- */
 /* kick (nbody.py:70-77) then drift (nbody.py:39-46) in one pass over n = N*dim floats:

@@ -66,9 +66,17 @@ _SIGNATURES = {
     'pmwd_kspace_force': (_i, [_vp, _i, _i32p, _d, _f, _vp, C.POINTER(_vp)]),
     'pmwd_kspace_force_adj': (_i, [_vp, _i, _i32p, _d, _f, C.POINTER(_vp), _vp]),
     'pmwd_strain': (_i, [_vp, _i, _i32p, _d, _i, _i, _vp, _vp]),
+    'pmwd_scatter_soa': (_i, [_vp, _descp, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp]),
+    'pmwd_gather3': (_i, [_vp, _descp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f]),
+    'pmwd_force_adj_gather': (_i, [_vp, _descp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp]),
+    'pmwd_kspace_force_slab': (_i, [_vp, _i32p, _i, _i, _d, _f, _vp, C.POINTER(_vp)]),
+    'pmwd_kspace_force_adj_slab': (_i, [_vp, _i32p, _i, _i, _d, _f, C.POINTER(_vp), _vp]),
     'pmwd_force_workspace_bytes': (_sz, [_descp, _i, _i]),
     'pmwd_force': (_i, [_vp, _vp, _descp, _vp, _vp, _d, _vp, _vp, _f, _i, _vp, _sz]),
     'pmwd_force_adj': (_i, [_vp, _vp, _descp, _vp, _vp, _d, _vp, _vp, _vp, _i, _vp, _sz]),
+    'pmwd_cell_sort_scratch_bytes': (_sz, [_descp]),
+    'pmwd_cell_sort_perm': (_i, [_vp, _descp, _vp, _vp, _vp, _vp, _sz]),
+    'pmwd_permute_rows': (_i, [_vp, _i64, _vp, _i, C.POINTER(_vp), C.POINTER(_vp), _i32p, _i]),
     'pmwd_kick_drift': (_i, [_vp, _i64, _vp, _vp, _vp, _f, _f, _i, _i]),
     'pmwd_kick_drift_adj': (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _i, _vp]),
 }

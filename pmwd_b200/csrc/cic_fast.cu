@@ -20,9 +20,14 @@ namespace pmwd {
 
 struct FastParams {
   int64_t n;
-  int nx, ny, nz;
+  int nx, ny, nz;   // periodic wrap shape (conf.mesh_shape; the GLOBAL mesh on a slab)
+  int nx_ext;       // x planes held by the mesh array (== nx on one GPU; slab + halos otherwise)
+  int xoff;         // global x index of plane 0 of the array (offset / cell, an integer)
   float cell;
 };
+
+int slab_xoff(const pmwd_cic_desc* d);
+bool cic_is_fast(const pmwd_cic_desc* d);
 
 struct Stencil3 {
   int ix[2], iy[2], iz[2];
@@ -49,6 +54,18 @@ __device__ __forceinline__ void axis_fast(int pm, float disp, float cell, int n,
   idx[1] = (i + 1 == n) ? 0 : i + 1;
 }
 
+// Global (wrapped) x index -> plane of the local array, or -1 if the array does not hold it
+// (enmesh's s2 drop, pm_util.py:140-141 + jax `mode='drop'`).
+__device__ __forceinline__ void localize_x(const FastParams& P, int* ix) {
+  if (P.xoff == 0 && P.nx_ext == P.nx) return;
+#pragma unroll
+  for (int b = 0; b < 2; ++b) {
+    int l = ix[b] - P.xoff;
+    if (l < 0) l += P.nx;
+    ix[b] = l < P.nx_ext ? l : -1;
+  }
+}
+
 __device__ __forceinline__ void red_add(float* p, float v) { atomicAdd(p, v); }
 
 __device__ __forceinline__ void red_add2(float* p, float a, float b) {
@@ -67,6 +84,7 @@ scatter_fast_kernel(FastParams P, const short* __restrict__ pmid, const float* _
     axis_fast(pmid[3 * p + 0], disp[3 * p + 0], P.cell, P.nx, s.ix, s.wx, nullptr);
     axis_fast(pmid[3 * p + 1], disp[3 * p + 1], P.cell, P.ny, s.iy, s.wy, nullptr);
     axis_fast(pmid[3 * p + 2], disp[3 * p + 2], P.cell, P.nz, s.iz, s.wz, nullptr);
+    localize_x(P, s.ix);
     float v[NCH];
 #pragma unroll
     for (int c = 0; c < NCH; ++c) v[c] = val ? val[NCH * p + c] : val_scalar;
@@ -74,6 +92,7 @@ scatter_fast_kernel(FastParams P, const short* __restrict__ pmid, const float* _
     const bool pair = (s.iz[1] == s.iz[0] + 1) && ((s.iz[0] & 1) == 0) && ((P.nz & 1) == 0);
 #pragma unroll
     for (int bx = 0; bx < 2; ++bx) {
+      if (s.ix[bx] < 0) continue;
 #pragma unroll
       for (int by = 0; by < 2; ++by) {
         float wxy = __fmul_rn(s.wx[bx], s.wy[by]);
@@ -109,16 +128,18 @@ gather3_kernel(FastParams P, const short* __restrict__ pmid, const float* __rest
     axis_fast(pmid[3 * p + 0], disp[3 * p + 0], P.cell, P.nx, s.ix, s.wx, nullptr);
     axis_fast(pmid[3 * p + 1], disp[3 * p + 1], P.cell, P.ny, s.iy, s.wy, nullptr);
     axis_fast(pmid[3 * p + 2], disp[3 * p + 2], P.cell, P.nz, s.iz, s.wz, nullptr);
+    localize_x(P, s.ix);
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
     // neighbour order n = bx + 2 by + 4 bz (axis 0 = LSB, pm_util.py:95-97), summed sequentially
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
       const int bx = n & 1, by = (n >> 1) & 1, bz = n >> 2;
       float w = __fmul_rn(__fmul_rn(s.wx[bx], s.wy[by]), s.wz[bz]);
-      int64_t lin = ((int64_t)s.ix[bx] * P.ny + s.iy[by]) * P.nz + s.iz[bz];
-      a0 = __fadd_rn(a0, __fmul_rn(__ldg(f0 + lin), w));
-      a1 = __fadd_rn(a1, __fmul_rn(__ldg(f1 + lin), w));
-      a2 = __fadd_rn(a2, __fmul_rn(__ldg(f2 + lin), w));
+      const bool ok = s.ix[bx] >= 0;           // dropped neighbour reads 0 (fill_value=0)
+      int64_t lin = ((int64_t)(ok ? s.ix[bx] : 0) * P.ny + s.iy[by]) * P.nz + s.iz[bz];
+      a0 = __fadd_rn(a0, __fmul_rn(ok ? __ldg(f0 + lin) : 0.f, w));
+      a1 = __fadd_rn(a1, __fmul_rn(ok ? __ldg(f1 + lin) : 0.f, w));
+      a2 = __fadd_rn(a2, __fmul_rn(ok ? __ldg(f2 + lin) : 0.f, w));
     }
     acc[3 * p + 0] = a0;
     acc[3 * p + 1] = a1;
@@ -147,6 +168,7 @@ force_adj_gather_kernel(FastParams P, const short* __restrict__ pmid, const floa
     axis_fast(pmid[3 * p + 0], disp[3 * p + 0], P.cell, P.nx, s.ix, s.wx, s.sx);
     axis_fast(pmid[3 * p + 1], disp[3 * p + 1], P.cell, P.ny, s.iy, s.wy, s.sy);
     axis_fast(pmid[3 * p + 2], disp[3 * p + 2], P.cell, P.nz, s.iz, s.wz, s.sz);
+    localize_x(P, s.ix);
     const float p0 = pi[3 * p + 0], p1 = pi[3 * p + 1], p2 = pi[3 * p + 2];
     float d[4][3];
 #pragma unroll
@@ -158,12 +180,13 @@ force_adj_gather_kernel(FastParams P, const short* __restrict__ pmid, const floa
       float gx = __fmul_rn(s.sx[bx], __fmul_rn(s.wy[by], s.wz[bz]));
       float gy = __fmul_rn(s.sy[by], __fmul_rn(s.wz[bz], s.wx[bx]));
       float gz = __fmul_rn(s.sz[bz], __fmul_rn(s.wx[bx], s.wy[by]));
-      int64_t lin = ((int64_t)s.ix[bx] * P.ny + s.iy[by]) * P.nz + s.iz[bz];
+      const bool ok = s.ix[bx] >= 0;
+      int64_t lin = ((int64_t)(ok ? s.ix[bx] : 0) * P.ny + s.iy[by]) * P.nz + s.iz[bz];
       float t[4];
-      t[0] = __fmul_rn(p0, __ldg(f0 + lin));
-      t[1] = __fmul_rn(p1, __ldg(f1 + lin));
-      t[2] = __fmul_rn(p2, __ldg(f2 + lin));
-      t[3] = __fmul_rn(__ldg(rho_cot + lin), val);
+      t[0] = __fmul_rn(p0, ok ? __ldg(f0 + lin) : 0.f);
+      t[1] = __fmul_rn(p1, ok ? __ldg(f1 + lin) : 0.f);
+      t[2] = __fmul_rn(p2, ok ? __ldg(f2 + lin) : 0.f);
+      t[3] = __fmul_rn(ok ? __ldg(rho_cot + lin) : 0.f, val);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         d[q][0] = __fadd_rn(d[q][0], __fmul_rn(t[q], gx));
@@ -187,24 +210,40 @@ static int fast_params(const pmwd_cic_desc* d, FastParams* P) {
   PMWD_REQUIRE(d && d->dim == 3, "fast path is 3-D");
   PMWD_REQUIRE(d->pmid_bytes == 2, "fast path needs int16 pmid");
   PMWD_REQUIRE(!d->general, "fast path needs cell_size=None");
-  for (int a = 0; a < 3; ++a) {
-    PMWD_REQUIRE(d->offset[a] == 0.0, "fast path needs offset 0");
-    PMWD_REQUIRE(d->mesh_shape[a] == d->wrap_shape[a] && d->mesh_shape[a] > 0,
-                 "fast path needs mesh == conf.mesh_shape");
-  }
+  PMWD_REQUIRE(cic_is_fast(d), "fast path needs offset (k*cell, 0, 0), mesh == conf.mesh_shape in y, z");
   P->n = d->ptcl_num;
-  P->nx = d->mesh_shape[0];
-  P->ny = d->mesh_shape[1];
-  P->nz = d->mesh_shape[2];
+  P->nx = d->wrap_shape[0];
+  P->ny = d->wrap_shape[1];
+  P->nz = d->wrap_shape[2];
+  P->nx_ext = d->mesh_shape[0];
   P->cell = (float)d->cell_size;
+  P->xoff = slab_xoff(d);
   return PMWD_OK;
+}
+
+// x offset in whole cells: divmod(b12, a1) with a1 the float32 cell size (pm_util.py:120)
+// must have zero remainder for the fast path.
+int slab_xoff(const pmwd_cic_desc* d) {
+  double a1 = (double)(float)d->cell_size;
+  double q = floor(d->offset[0] / a1);
+  int off = (int)q % d->wrap_shape[0];
+  return off < 0 ? off + d->wrap_shape[0] : off;
 }
 
 bool cic_is_fast(const pmwd_cic_desc* d) {
   if (!d || d->dim != 3 || d->pmid_bytes != 2 || d->general) return false;
-  for (int a = 0; a < 3; ++a)
-    if (d->offset[a] != 0.0 || d->mesh_shape[a] != d->wrap_shape[a]) return false;
+  for (int a = 0; a < 3; ++a) if (d->wrap_shape[a] <= 0 || d->mesh_shape[a] <= 0) return false;
+  if (d->offset[1] != 0.0 || d->offset[2] != 0.0) return false;
+  if (d->mesh_shape[1] != d->wrap_shape[1] || d->mesh_shape[2] != d->wrap_shape[2]) return false;
+  if (d->mesh_shape[0] > d->wrap_shape[0]) return false;
+  double a1 = (double)(float)d->cell_size;
+  double q = floor(d->offset[0] / a1);
+  if (d->offset[0] - q * a1 != 0.0) return false;            // whole cells only
   return true;
+}
+
+bool cic_is_full_mesh(const pmwd_cic_desc* d) {
+  return cic_is_fast(d) && d->offset[0] == 0.0 && d->mesh_shape[0] == d->wrap_shape[0];
 }
 
 int scatter_fast(cudaStream_t st, const pmwd_cic_desc* d, const void* pmid, const float* disp,

@@ -24,6 +24,7 @@ int cic_generic(cudaStream_t st, const pmwd_cic_desc* d, const void* pmid, const
                 float* p_out, float* p_out2);
 // cic_fast.cu
 bool cic_is_fast(const pmwd_cic_desc* d);
+bool cic_is_full_mesh(const pmwd_cic_desc* d);
 int scatter_fast(cudaStream_t st, const pmwd_cic_desc* d, const void* pmid, const float* disp,
                  const float* val, float val_scalar, int nch, float* m0, float* m1, float* m2);
 int gather3_fast(cudaStream_t st, const pmwd_cic_desc* d, const void* pmid, const float* disp,
@@ -72,7 +73,7 @@ static void force_layout(const pmwd_cic_desc* d, int adjoint, int mode, ForceLay
 
 static int check_force_args(const pmwd_cic_desc* d) {
   PMWD_REQUIRE(d != nullptr, "null descriptor");
-  PMWD_REQUIRE(cic_is_fast(d), "pmwd_force needs the 3-D int16 fast path (offset 0, cell_size=None, mesh == conf.mesh_shape)");
+  PMWD_REQUIRE(cic_is_full_mesh(d), "pmwd_force needs the 3-D int16 fast path (offset 0, cell_size=None, mesh == conf.mesh_shape)");
   PMWD_REQUIRE(d->nchan == 1, "pmwd_force: nchan must be 1");
   return PMWD_OK;
 }
@@ -167,6 +168,36 @@ extern "C" int pmwd_gather_adj(void* stream, const pmwd_cic_desc* d, const void*
   PMWD_REQUIRE(d && mesh && (d->ptcl_num == 0 || (pmid && disp && disp_cot)), "null buffer");
   return cic_generic<3>(as_stream(stream), d, pmid, disp, val_cot, val_cot_scalar, mesh, mesh_cot,
                         disp_cot, nullptr);
+}
+
+// ---- SoA building blocks of the force pipeline, exposed for the slab-decomposed (multi-GPU)
+// composition in pmwd_b200/dist.py: the mesh arrays may be x-slabs with halos, described by
+// d->mesh_shape[0] (planes held) and d->offset[0] (= first plane * cell_size).
+extern "C" int pmwd_scatter_soa(void* stream, const pmwd_cic_desc* d, const void* pmid,
+                                const float* disp, const float* val, float val_scalar, int nch,
+                                float* m0, float* m1, float* m2) {
+  PMWD_REQUIRE(d && m0 && (d->ptcl_num == 0 || (pmid && disp)), "null buffer");
+  PMWD_REQUIRE(nch == 1 || (nch == 3 && m1 && m2), "nch must be 1 or 3 (with three meshes)");
+  StageTimer t(nch == 1 ? ST_SCATTER : ST_SCATTER3, as_stream(stream));
+  return scatter_fast(as_stream(stream), d, pmid, disp, val, val_scalar, nch, m0, m1, m2);
+}
+
+extern "C" int pmwd_gather3(void* stream, const pmwd_cic_desc* d, const void* pmid,
+                            const float* disp, const float* f0, const float* f1, const float* f2,
+                            float* acc, float* kick_vel, float kick_factor) {
+  PMWD_REQUIRE(d && f0 && f1 && f2 && (d->ptcl_num == 0 || (pmid && disp && acc)), "null buffer");
+  StageTimer t(ST_GATHER, as_stream(stream));
+  return gather3_fast(as_stream(stream), d, pmid, disp, f0, f1, f2, acc, kick_vel, kick_factor);
+}
+
+extern "C" int pmwd_force_adj_gather(void* stream, const pmwd_cic_desc* d, const void* pmid,
+                                     const float* disp, const float* f0, const float* f1,
+                                     const float* f2, const float* rho_cot, const float* pi,
+                                     float val, float* alpha) {
+  PMWD_REQUIRE(d && f0 && f1 && f2 && rho_cot && (d->ptcl_num == 0 || (pmid && disp && pi && alpha)),
+               "null buffer");
+  StageTimer t(ST_GATHER_ADJ, as_stream(stream));
+  return force_adj_gather(as_stream(stream), d, pmid, disp, f0, f1, f2, rho_cot, pi, val, alpha);
 }
 
 extern "C" size_t pmwd_force_workspace_bytes(const pmwd_cic_desc* d, int adjoint, int mode) {

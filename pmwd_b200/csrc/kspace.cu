@@ -21,6 +21,8 @@ struct KsParams {
   int nc;          // n[2]/2 + 1
   double period;   // 2 pi / spacing
   float nyq, eps;  // pi / spacing and nyq * eps(float32)   (gravity.py:38-39)
+  int n1_global;   // full length of axis 1 (== n[1] unless the spectrum is a y-slab)
+  int i1_off;      // global index of local row 0 along axis 1
   int ax_i, ax_j;  // padded axis ids for NEG_GRAD / STRAIN
   float scale;
   const float2* in[3];
@@ -43,7 +45,8 @@ __global__ void __launch_bounds__(256) kspace_kernel(KsParams P) {
   float* k2tab = tab;            // axis 2 (last, rfftfreq), nc entries
   float* k1tab = tab + P.nc;     // axis 1, n[1] entries
   for (int i = threadIdx.x; i < P.nc; i += blockDim.x) k2tab[i] = kval(i, P.n[2], P.period, true);
-  for (int i = threadIdx.x; i < P.n[1]; i += blockDim.x) k1tab[i] = kval(i, P.n[1], P.period, false);
+  for (int i = threadIdx.x; i < P.n[1]; i += blockDim.x)
+    k1tab[i] = kval(i + P.i1_off, P.n1_global, P.period, false);
   __syncthreads();
 
   const int first = 3 - P.rank;  // first real axis among the padded three
@@ -58,65 +61,81 @@ __global__ void __launch_bounds__(256) kspace_kernel(KsParams P) {
     const float k0 = first <= 0 ? kval(i0, P.n[0], P.period, false) : 0.f;
     const float k1 = first <= 1 ? k1tab[i1] : 0.f;
     const int64_t base = row * P.nc;
-    for (int i2 = lane; i2 < P.nc; i2 += 32) {
-      const float k2 = k2tab[i2];
-      float kv[3] = {k0, k1, k2};
-      // k^2 = ((0 + k_a^2) + k_b^2) + k_c^2 over the real axes in order
-      float ksq = 0.f;
+    // 4 independent loads in flight per lane before any dependent work (latency-bound otherwise)
+    constexpr int U = 4;
+    constexpr int NIN = MODE == KS_FORCE_ADJ ? 3 : 1;
+    for (int i2b = lane; i2b < P.nc; i2b += 32 * U) {
+      float2 in[U][NIN];
 #pragma unroll
-      for (int a = 0; a < 3; ++a)
-        if (a >= first) ksq = __fadd_rn(ksq, __fmul_rn(kv[a], kv[a]));
-      const int64_t e = base + i2;
+      for (int u = 0; u < U; ++u) {
+        const int i2 = i2b + 32 * u;
+#pragma unroll
+        for (int q = 0; q < NIN; ++q) {
+          in[u][q] = make_float2(0.f, 0.f);
+          if (i2 < P.nc && (NIN == 1 || q + first < 3)) in[u][q] = __ldcs(P.in[q] + base + i2);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i2 = i2b + 32 * u;
+        if (i2 >= P.nc) break;
+        const float k2 = k2tab[i2];
+        const float kv[3] = {k0, k1, k2};
+        // k^2 = ((0 + k_a^2) + k_b^2) + k_c^2 over the real axes in order
+        float ksq = 0.f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+          if (a >= first) ksq = __fadd_rn(ksq, __fmul_rn(kv[a], kv[a]));
+        const int64_t e = base + i2;
+        const float2 s = in[u][0];
 
-      if (MODE == KS_LAPLACE) {
-        float2 s = P.in[0][e];
-        float2 o = make_float2(0.f, 0.f);
-        if (ksq != 0.f) o = make_float2(__fdiv_rn(-s.x, ksq), __fdiv_rn(-s.y, ksq));
-        P.out[0][e] = o;
-      } else if (MODE == KS_NEG_GRAD) {
-        float2 s = P.in[0][e];
-        float k = kv[P.ax_i];
-        float2 o = make_float2(0.f, 0.f);
-        if (!is_nyq(k, P.nyq, P.eps)) o = make_float2(__fmul_rn(k, s.y), -__fmul_rn(k, s.x));
-        P.out[0][e] = o;
-      } else if (MODE == KS_FORCE) {
-        float2 s = P.in[0][e];
-        float2 pot = make_float2(0.f, 0.f);
-        if (ksq != 0.f)
-          pot = make_float2(__fdiv_rn(-__fmul_rn(P.scale, s.x), ksq),
-                            __fdiv_rn(-__fmul_rn(P.scale, s.y), ksq));
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          if (a < first) continue;
-          float k = kv[a];
+        if (MODE == KS_LAPLACE) {
           float2 o = make_float2(0.f, 0.f);
-          if (!is_nyq(k, P.nyq, P.eps)) o = make_float2(__fmul_rn(k, pot.y), -__fmul_rn(k, pot.x));
-          P.out[a - first][e] = o;
-        }
-      } else if (MODE == KS_FORCE_ADJ) {
-        float2 acc = make_float2(0.f, 0.f);
+          if (ksq != 0.f) o = make_float2(__fdiv_rn(-s.x, ksq), __fdiv_rn(-s.y, ksq));
+          __stcs(P.out[0] + e, o);
+        } else if (MODE == KS_NEG_GRAD) {
+          const float k = P.ax_i == 0 ? k0 : (P.ax_i == 1 ? k1 : k2);
+          float2 o = make_float2(0.f, 0.f);
+          if (!is_nyq(k, P.nyq, P.eps)) o = make_float2(__fmul_rn(k, s.y), -__fmul_rn(k, s.x));
+          __stcs(P.out[0] + e, o);
+        } else if (MODE == KS_FORCE) {
+          float2 pot = make_float2(0.f, 0.f);
+          if (ksq != 0.f)
+            pot = make_float2(__fdiv_rn(-__fmul_rn(P.scale, s.x), ksq),
+                              __fdiv_rn(-__fmul_rn(P.scale, s.y), ksq));
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          if (a < first) continue;
-          float k = kv[a];
-          if (ksq != 0.f && !is_nyq(k, P.nyq, P.eps)) {
-            float2 v = P.in[a - first][e];
-            float2 phi = make_float2(__fdiv_rn(-v.x, ksq), __fdiv_rn(-v.y, ksq));
-            // -( -i k phi ) = +i k phi = (-k phi.y, k phi.x)
-            acc.x = __fsub_rn(acc.x, __fmul_rn(k, phi.y));
-            acc.y = __fadd_rn(acc.y, __fmul_rn(k, phi.x));
+          for (int a = 0; a < 3; ++a) {
+            if (a < first) continue;
+            const float k = kv[a];
+            float2 o = make_float2(0.f, 0.f);
+            if (!is_nyq(k, P.nyq, P.eps)) o = make_float2(__fmul_rn(k, pot.y), -__fmul_rn(k, pot.x));
+            __stcs(P.out[a - first] + e, o);
           }
+        } else if (MODE == KS_FORCE_ADJ) {
+          float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            if (a < first) continue;
+            const float k = kv[a];
+            if (ksq != 0.f && !is_nyq(k, P.nyq, P.eps)) {
+              const float2 v = in[u][a - first];
+              float2 phi = make_float2(__fdiv_rn(-v.x, ksq), __fdiv_rn(-v.y, ksq));
+              // -( -i k phi ) = +i k phi = (-k phi.y, k phi.x)
+              acc.x = __fsub_rn(acc.x, __fmul_rn(k, phi.y));
+              acc.y = __fadd_rn(acc.y, __fmul_rn(k, phi.x));
+            }
+          }
+          __stcs(P.out[0] + e, make_float2(__fmul_rn(P.scale, acc.x), __fmul_rn(P.scale, acc.y)));
+        } else if (MODE == KS_STRAIN) {
+          float ki = P.ax_i == 0 ? k0 : (P.ax_i == 1 ? k1 : k2);
+          float kj = P.ax_j == 0 ? k0 : (P.ax_j == 1 ? k1 : k2);
+          if (P.ax_i != P.ax_j) {
+            if (is_nyq(ki, P.nyq, P.eps)) ki = 0.f;
+            if (is_nyq(kj, P.nyq, P.eps)) kj = 0.f;
+          }
+          const float m = __fmul_rn(-ki, kj);
+          __stcs(P.out[0] + e, make_float2(__fmul_rn(m, s.x), __fmul_rn(m, s.y)));
         }
-        P.out[0][e] = make_float2(__fmul_rn(P.scale, acc.x), __fmul_rn(P.scale, acc.y));
-      } else if (MODE == KS_STRAIN) {
-        float2 s = P.in[0][e];
-        float ki = kv[P.ax_i], kj = kv[P.ax_j];
-        if (P.ax_i != P.ax_j) {
-          if (is_nyq(ki, P.nyq, P.eps)) ki = 0.f;
-          if (is_nyq(kj, P.nyq, P.eps)) kj = 0.f;
-        }
-        float m = __fmul_rn(-ki, kj);
-        P.out[0][e] = make_float2(__fmul_rn(m, s.x), __fmul_rn(m, s.y));
       }
     }
   }
@@ -134,6 +153,8 @@ static int ks_setup(KsParams* P, int rank, const int32_t* shape, double spacing)
     P->n[3 - rank + a] = shape[a];
   }
   P->nc = P->n[2] / 2 + 1;
+  P->n1_global = P->n[1];
+  P->i1_off = 0;
   const double pi = 3.141592653589793238462643383279502884;
   P->period = 2.0 * pi / spacing;
   double nyq = pi / spacing;
@@ -213,6 +234,39 @@ extern "C" int pmwd_kspace_force_adj(void* stream, int rank, const int32_t* shap
     PMWD_REQUIRE(v[a] != nullptr, "null input spectrum");
     P.in[a] = (const float2*)v[a];
   }
+  P.out[0] = (float2*)out;
+  return ks_launch<KS_FORCE_ADJ>(as_stream(stream), P);
+}
+
+// Slab (multi-GPU) variants: the spectrum is the transposed slab [n0][ny_local][n2/2+1] holding
+// global rows y0 .. y0+ny_local-1 of axis 1 (after the distributed FFT's all-to-all).
+extern "C" int pmwd_kspace_force_slab(void* stream, const int32_t* shape, int y0, int ny_local,
+                                      double spacing, float scale, const void* rho, void* const* g) {
+  KsParams P;
+  int rc = ks_setup(&P, 3, shape, spacing);
+  if (rc) return rc;
+  PMWD_REQUIRE(rho && g && g[0] && g[1] && g[2], "null buffer");
+  PMWD_REQUIRE(y0 >= 0 && ny_local > 0 && y0 + ny_local <= shape[1], "bad y slab");
+  P.n[1] = ny_local;
+  P.i1_off = y0;
+  P.scale = scale;
+  P.in[0] = (const float2*)rho;
+  for (int a = 0; a < 3; ++a) P.out[a] = (float2*)g[a];
+  return ks_launch<KS_FORCE>(as_stream(stream), P);
+}
+
+extern "C" int pmwd_kspace_force_adj_slab(void* stream, const int32_t* shape, int y0, int ny_local,
+                                          double spacing, float scale, const void* const* v,
+                                          void* out) {
+  KsParams P;
+  int rc = ks_setup(&P, 3, shape, spacing);
+  if (rc) return rc;
+  PMWD_REQUIRE(v && out && v[0] && v[1] && v[2], "null buffer");
+  PMWD_REQUIRE(y0 >= 0 && ny_local > 0 && y0 + ny_local <= shape[1], "bad y slab");
+  P.n[1] = ny_local;
+  P.i1_off = y0;
+  P.scale = scale;
+  for (int a = 0; a < 3; ++a) P.in[a] = (const float2*)v[a];
   P.out[0] = (float2*)out;
   return ks_launch<KS_FORCE_ADJ>(as_stream(stream), P);
 }

@@ -1,0 +1,175 @@
+// Eulerian re-ordering of the particle storage.
+//
+// The reference keeps particles in Lagrangian order forever (pmwd/particles.py:135-139).  Once
+// particles have moved several cells, a warp of 32 consecutive particles touches 32 unrelated
+// mesh rows: ncu shows the 3-mesh gather moving 6x its algorithmic bytes and the scatter 4x
+// (profiles/r01_ncu_full_late_step46.txt).  The integrator therefore periodically re-sorts its
+// private copy of the particle arrays by mesh cell (stable LSD radix sort on the linear cell
+// index, cub::DeviceRadixSort) and carries the Lagrangian index along so that outputs are
+// returned in the reference's order.  Per-particle arithmetic is unchanged; only the order of
+// the (already unordered) float32 scatter additions differs.
+//
+//   pmwd_cell_sort_perm : perm[i] = storage index of the particle that goes to sorted slot i
+//   pmwd_permute_rows   : dst[i] = src[perm[i]]  (gather)   or  dst[perm[i]] = src[i]  (scatter)
+#include <cub/device/device_radix_sort.cuh>
+
+#include "cic.cuh"
+
+namespace pmwd {
+
+int slab_xoff(const pmwd_cic_desc* d);
+bool cic_is_fast(const pmwd_cic_desc* d);
+
+struct SortParams {
+  int64_t n;
+  int nx, ny, nz;   // periodic wrap shape
+  int nx_ext, xoff; // slab: planes held locally and global index of the first one
+  float cell;
+};
+
+__global__ void __launch_bounds__(256)
+sort_keys_kernel(SortParams P, const short* __restrict__ pmid, const float* __restrict__ disp,
+                 uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P.n;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    int c[3];
+    const int nn[3] = {P.nx, P.ny, P.nz};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      float t = __fdiv_rn(disp[3 * p + a], P.cell);
+      c[a] = wrap_index((int)pmid[3 * p + a] + (int)floorf(t), nn[a]);
+    }
+    int lx = c[0] - P.xoff;           // slab-local plane keeps the key below 2^32 on big meshes
+    if (lx < 0) lx += P.nx;
+    if (lx >= P.nx_ext) lx = P.nx_ext - 1;
+    keys[p] = (uint32_t)(((int64_t)lx * P.ny + c[1]) * P.nz + c[2]);
+    vals[p] = (uint32_t)p;
+  }
+}
+
+struct RowArgs {
+  int narr;
+  const void* src[8];
+  void* dst[8];
+  int words[8];     // row size in 2-byte words (3 for int16[3], 6 for float[3], 2 for uint32)
+};
+
+template <bool INVERSE>
+__global__ void __launch_bounds__(256)
+permute_rows_kernel(int64_t n, const uint32_t* __restrict__ perm, RowArgs A) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = perm[i];
+    const int64_t from = INVERSE ? i : j, to = INVERSE ? j : i;
+    for (int a = 0; a < A.narr; ++a) {
+      const int w = A.words[a];
+      if ((w & 1) == 0) {   // rows of 4-byte words
+        const uint32_t* s = reinterpret_cast<const uint32_t*>(A.src[a]) + from * (w >> 1);
+        uint32_t* d = reinterpret_cast<uint32_t*>(A.dst[a]) + to * (w >> 1);
+        for (int k = 0; k < (w >> 1); ++k) d[k] = __ldg(s + k);
+      } else {
+        const uint16_t* s = reinterpret_cast<const uint16_t*>(A.src[a]) + from * w;
+        uint16_t* d = reinterpret_cast<uint16_t*>(A.dst[a]) + to * w;
+        for (int k = 0; k < w; ++k) d[k] = __ldg(s + k);
+      }
+    }
+  }
+}
+
+static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+static int ilog2_ceil(int64_t x) { int b = 0; while (((int64_t)1 << b) < x) ++b; return b; }
+
+struct SortLayout { size_t keys_in, vals_in, keys_out, cub, total, cub_bytes; };
+
+static int sort_layout(int64_t n, int end_bit, SortLayout* L) {
+  size_t cub_bytes = 0;
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr,
+                                                  (uint32_t*)nullptr, (const uint32_t*)nullptr,
+                                                  (uint32_t*)nullptr, n, 0, end_bit);
+  if (e != cudaSuccess) { set_error("cub temp query failed: %s", cudaGetErrorString(e)); return (int)e; }
+  size_t off = 0;
+  L->keys_in = off;  off += align_up((size_t)n * 4);
+  L->vals_in = off;  off += align_up((size_t)n * 4);
+  L->keys_out = off; off += align_up((size_t)n * 4);
+  L->cub = off;      off += align_up(cub_bytes);
+  L->cub_bytes = cub_bytes;
+  L->total = off;
+  return PMWD_OK;
+}
+
+}  // namespace pmwd
+
+using namespace pmwd;
+
+extern "C" size_t pmwd_cell_sort_scratch_bytes(const pmwd_cic_desc* d) {
+  if (!d || d->dim != 3) return 0;
+  int64_t ncell = (int64_t)d->mesh_shape[0] * d->mesh_shape[1] * d->mesh_shape[2];
+  SortLayout L;
+  if (sort_layout(d->ptcl_num, ilog2_ceil(ncell) < 1 ? 1 : ilog2_ceil(ncell), &L)) return 0;
+  return L.total;
+}
+
+extern "C" int pmwd_cell_sort_perm(void* stream, const pmwd_cic_desc* d, const void* pmid,
+                                   const float* disp, uint32_t* perm, void* scratch,
+                                   size_t scratch_bytes) {
+  PMWD_REQUIRE(d && d->dim == 3 && d->pmid_bytes == 2 && !d->general,
+               "cell sort supports the 3-D int16 fast path");
+  PMWD_REQUIRE(perm && scratch, "null buffer");
+  SortParams P;
+  P.n = d->ptcl_num;
+  P.nx = d->wrap_shape[0]; P.ny = d->wrap_shape[1]; P.nz = d->wrap_shape[2];
+  P.nx_ext = d->mesh_shape[0];
+  P.xoff = slab_xoff(d);
+  P.cell = (float)d->cell_size;
+  PMWD_REQUIRE(cic_is_fast(d), "cell sort needs a fast-path (slab) descriptor");
+  int64_t ncell = (int64_t)P.nx_ext * P.ny * P.nz;
+  PMWD_REQUIRE(ncell <= ((int64_t)1 << 32) && P.n < ((int64_t)1 << 32),
+               "cell sort needs mesh_size <= 2^32 and ptcl_num < 2^32 per device");
+  if (P.n == 0) return PMWD_OK;
+  PMWD_REQUIRE(pmid && disp, "null buffer");
+  int end_bit = ilog2_ceil(ncell);
+  if (end_bit < 1) end_bit = 1;
+  SortLayout L;
+  int rc = sort_layout(P.n, end_bit, &L);
+  if (rc) return rc;
+  if (scratch_bytes < L.total) {
+    set_error("cell sort needs %zu bytes of scratch, got %zu", L.total, scratch_bytes);
+    return PMWD_ENOMEM;
+  }
+  cudaStream_t st = as_stream(stream);
+  StageTimer timer(ST_OTHER, st);
+  char* base = (char*)scratch;
+  uint32_t* keys_in = (uint32_t*)(base + L.keys_in);
+  uint32_t* vals_in = (uint32_t*)(base + L.vals_in);
+  uint32_t* keys_out = (uint32_t*)(base + L.keys_out);
+  sort_keys_kernel<<<grid_for(P.n, 256, 8), 256, 0, st>>>(P, (const short*)pmid, disp, keys_in, vals_in);
+  PMWD_LAUNCH_CHECK();
+  size_t cub_bytes = L.cub_bytes;
+  PMWD_CUDA_TRY(cub::DeviceRadixSort::SortPairs(base + L.cub, cub_bytes, keys_in, keys_out, vals_in,
+                                                perm, P.n, 0, end_bit, st));
+  return PMWD_OK;
+}
+
+extern "C" int pmwd_permute_rows(void* stream, int64_t n, const uint32_t* perm, int narr,
+                                 const void* const* src, void* const* dst, const int32_t* row_bytes,
+                                 int inverse) {
+  PMWD_REQUIRE(n >= 0 && narr >= 1 && narr <= 8, "bad sizes");
+  PMWD_REQUIRE(perm && src && dst && row_bytes, "null buffer");
+  if (n == 0) return PMWD_OK;
+  RowArgs A;
+  A.narr = narr;
+  for (int a = 0; a < narr; ++a) {
+    PMWD_REQUIRE(src[a] && dst[a] && src[a] != dst[a], "permute needs distinct non-null buffers");
+    PMWD_REQUIRE(row_bytes[a] > 0 && row_bytes[a] % 2 == 0 && row_bytes[a] <= 64, "bad row size");
+    A.src[a] = src[a];
+    A.dst[a] = dst[a];
+    A.words[a] = row_bytes[a] / 2;
+  }
+  cudaStream_t st = as_stream(stream);
+  StageTimer timer(ST_OTHER, st);
+  int grid = grid_for(n, 256, 8);
+  if (inverse) permute_rows_kernel<true><<<grid, 256, 0, st>>>(n, perm, A);
+  else permute_rows_kernel<false><<<grid, 256, 0, st>>>(n, perm, A);
+  PMWD_LAUNCH_CHECK();
+  return PMWD_OK;
+}

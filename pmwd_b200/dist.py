@@ -1,0 +1,460 @@
+"""Slab-decomposed (multi-GPU) particle-mesh path: one process per GPU, torch.distributed
+(NCCL over NVLink / NVSwitch; gloo on CPU for the host-logic tests).
+
+The reference is single-device (docs/papers/adjoint/adjoint.tex:1743-1744); this is new design
+(SURVEY.md 8e):
+
+  * mesh: x-slabs, ``Mx / P`` planes per rank; spectra after the distributed FFT are y-slabs
+    ``[Mx][My / P][Mz/2+1]`` (no transpose back: the k-space kernel runs on that layout);
+  * particles: Lagrangian x-slabs = contiguous ranges of the reference's C-ordered arrays, so
+    outputs concatenate to the reference order and nothing migrates;
+  * per force: scatter into slab + halo planes -> neighbour reduce-add of halos -> slab FFT
+    (local 2-D R2C over (y, z), ONE all-to-all, 1-D C2C over x) -> fused k-space kernel ->
+    3 x (1-D inverse, all-to-all, local 2-D C2R) -> neighbour halo copy -> 3-mesh gather;
+  * the halo width follows the all-reduced max |disp_x| every step;
+  * the adjoint uses the same plumbing; its float64 dot products are all-reduced once.
+
+A slab is described to the kernels with the reference's own ``(offset, mesh shape)`` enmesh
+semantics (pmwd/pm_util.py:119-141), so the CIC kernels are the single-GPU ones.
+"""
+import ctypes as C
+import math
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .boltzmann import growth, linear_power
+from .cosmology import E2
+from .particles import Particles
+from .scatter import make_desc
+
+
+class SlabComm:
+    """Geometry and collectives of one rank of the slab decomposition."""
+
+    def __init__(self, conf, group=None):
+        self.conf = conf
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.size = dist.get_world_size(group)
+        P = self.size
+        if conf.dim != 3:
+            raise ValueError('the slab decomposition is 3-D')
+        Mx, My, Mz = conf.mesh_shape
+        nx, ny, nz = conf.ptcl_grid_shape
+        if Mx % P or My % P or nx % P or ny % P:
+            raise ValueError(f'mesh {conf.mesh_shape} / particle grid {conf.ptcl_grid_shape} '
+                             f'not divisible by {P} ranks along x and y')
+        self.mx, self.my = Mx // P, My // P
+        self.x0, self.y0 = self.rank * self.mx, self.rank * self.my
+        self.pnx = nx // P                       # particle-grid planes per rank
+        self.px0 = self.rank * self.pnx
+        self.ptcl_num_local = self.pnx * ny * nz
+        self.left, self.right = (self.rank - 1) % P, (self.rank + 1) % P
+
+    # ---- particles -----------------------------------------------------------------------
+    def local_slice(self):
+        """Range of this rank in the reference's (global, C-ordered) particle arrays."""
+        lo = self.rank * self.ptcl_num_local
+        return slice(lo, lo + self.ptcl_num_local)
+
+    # ---- all-to-all transposes of the distributed FFT ------------------------------------
+    def _a2a(self, send):
+        send = send.contiguous()
+        recv = torch.empty_like(send)
+        s, r = (torch.view_as_real(send), torch.view_as_real(recv)) if send.is_complex() else (send, recv)
+        dist.all_to_all_single(r, s, group=self.group)
+        return recv
+
+    def rfftn(self, real, shape=None):
+        """x-slab real ``[mx][My][Mz]`` -> y-slab spectrum ``[Mx][my][Mz/2+1]`` (unnormalised,
+        = numpy rfftn of the global field, pmwd/pm_util.py:281)."""
+        P = self.size
+        mx, My, Mz = real.shape
+        my = My // P
+        s = torch.fft.rfft2(real)                                   # local 2-D R2C over (y, z)
+        nzc = s.shape[-1]
+        s = s.reshape(mx, P, my, nzc).permute(1, 0, 2, 3).contiguous()   # pack per destination
+        s = self._a2a(s).reshape(P * mx, my, nzc)                   # blocks arrive in x order
+        return torch.fft.fft(s, dim=0)                              # 1-D C2C over x
+
+    def irfftn(self, spec, My, Mz):
+        """Inverse of :meth:`rfftn` WITHOUT the 1/N (callers fold it into their scale)."""
+        P = self.size
+        Mx, my, nzc = spec.shape
+        mx = Mx // P
+        s = torch.fft.ifft(spec, dim=0, norm='forward')             # unnormalised inverse over x
+        s = self._a2a(s.reshape(P, mx, my, nzc))                    # [p] = y-chunk p of my planes
+        s = s.permute(1, 0, 2, 3).reshape(mx, My, nzc)              # unpack
+        return torch.fft.irfft2(s, s=(My, Mz), norm='forward')
+
+    # ---- halos ---------------------------------------------------------------------------
+    def _exchange(self, to_left, to_right):
+        """Send one tensor to each x-neighbour, receive theirs: (from_left, from_right)."""
+        from_left, from_right = torch.empty_like(to_right), torch.empty_like(to_left)
+        if self.size == 1:
+            from_left.copy_(to_right); from_right.copy_(to_left)
+            return from_left, from_right
+        ops = [dist.P2POp(dist.isend, to_right, self.right, self.group),
+               dist.P2POp(dist.isend, to_left, self.left, self.group),
+               dist.P2POp(dist.irecv, from_left, self.left, self.group),
+               dist.P2POp(dist.irecv, from_right, self.right, self.group)]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        return from_left, from_right
+
+    def halo_reduce(self, ext, h):
+        """``ext[..., mx + 2h, My, Mz]`` deposited with halos -> adds the halo planes into the
+        owning neighbours; returns the owned slab view ``ext[..., h:h+mx]``."""
+        mx = self.mx
+        lo = ext[..., :h, :, :].contiguous()           # planes x0-h .. x0-1   -> left neighbour
+        hi = ext[..., h + mx:, :, :].contiguous()      # planes x0+mx ..       -> right neighbour
+        from_left, from_right = self._exchange(lo, hi)
+        ext[..., h:2 * h, :, :] += from_left            # their upper halo = my first planes
+        ext[..., mx:mx + h, :, :] += from_right         # their lower halo = my last planes
+        return ext[..., h:h + mx, :, :]
+
+    def halo_fill(self, ext, h):
+        """Owned planes ``ext[..., h:h+mx]`` are valid; fetch the halos from the neighbours."""
+        mx = self.mx
+        first = ext[..., h:2 * h, :, :].contiguous()    # -> left neighbour's upper halo
+        last = ext[..., mx:mx + h, :, :].contiguous()   # -> right neighbour's lower halo
+        from_left, from_right = self._exchange(first, last)
+        ext[..., :h, :, :] = from_left
+        ext[..., h + mx:, :, :] = from_right
+        return ext
+
+    def allreduce_max(self, x):
+        t = x.detach().reshape(1).clone()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return float(t)
+
+    def allreduce_sum_(self, t):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+
+# ------------------------------------------------------------------------------------------
+class SlabForce:
+    """``gravity`` (pmwd/gravity.py:47-72) and ``force_adj`` (pmwd/nbody.py:108-118) on slabs."""
+
+    def __init__(self, conf, comm):
+        self.conf, self.comm = conf, comm
+        self.h_alloc = 0
+        self._ext1 = self._ext3 = None
+        self._F = None           # force meshes with halos kept for the adjoint gather
+        self._h = None
+
+    def _halo(self, disp):
+        conf, comm = self.conf, self.comm
+        m = comm.allreduce_max(disp[:, 0].abs().max())
+        h = int(math.ceil(m / conf.cell_size)) + 1
+        if h > comm.mx:
+            raise RuntimeError(f'halo of {h} planes exceeds the slab width {comm.mx}: use fewer ranks')
+        if h > self.h_alloc:
+            self.h_alloc = min(comm.mx, (h + 7) // 8 * 8)
+            self._ext1 = self._ext3 = None
+        return self.h_alloc
+
+    def _desc(self, pmid, h):
+        conf, comm = self.conf, self.comm
+        _, My, Mz = conf.mesh_shape
+        off = ((comm.x0 - h) * conf.cell_size, 0.0, 0.0)
+        return make_desc(conf, pmid, (comm.mx + 2 * h, My, Mz), 1, off, None)
+
+    def _buffers(self, dev, h):
+        conf, comm = self.conf, self.comm
+        _, My, Mz = conf.mesh_shape
+        shape = (comm.mx + 2 * h, My, Mz)
+        if self._ext1 is None or self._ext1.shape != shape:
+            self._ext1 = torch.empty(shape, dtype=conf.float_dtype, device=dev)
+            self._ext3 = torch.empty((3,) + shape, dtype=conf.float_dtype, device=dev)
+        return self._ext1, self._ext3
+
+    def _mesh_forces(self, pmid, disp, Om, h):
+        """Particles -> the three force meshes with halos, ``[3][mx+2h][My][Mz]``."""
+        conf, comm = self.conf, self.comm
+        lib = _lib.lib()
+        dev = disp.device
+        Mx, My, Mz = conf.mesh_shape
+        ext1, ext3 = self._buffers(dev, h)
+        desc = self._desc(pmid, h)
+        st = _lib.stream_ptr(dev)
+        val = float(np.float32(conf.mesh_size / conf.ptcl_num))       # scatter.py:37-39
+        ext1.zero_()
+        _lib.check(lib.pmwd_scatter_soa(st, C.byref(desc), _lib.ptr(pmid), _lib.ptr(disp), None, val, 1,
+                                        _lib.ptr(ext1), None, None), 'pmwd_scatter_soa')
+        rho = comm.halo_reduce(ext1, h)
+        spec = comm.rfftn(rho)
+        g = [torch.empty_like(spec) for _ in range(3)]
+        scale = float(np.float32(1.5 * Om / conf.mesh_size))          # 1.5 Omega_m and irfftn's 1/N
+        arr = (C.c_void_p * 3)(*[t.data_ptr() for t in g])
+        _lib.check(lib.pmwd_kspace_force_slab(st, _lib.shape_arr(conf.mesh_shape), comm.y0, comm.my,
+                                              float(conf.cell_size), scale, _lib.ptr(spec), arr),
+                   'pmwd_kspace_force_slab')
+        del spec
+        for i in range(3):
+            ext3[i, h:h + comm.mx] = comm.irfftn(g[i], My, Mz)
+            g[i] = None
+        comm.halo_fill(ext3, h)
+        return desc, ext3, val
+
+    def force(self, pmid, disp, Om, acc, kick_vel=None, kick_factor=0.0):
+        h = self._halo(disp)
+        desc, F, _ = self._mesh_forces(pmid, disp, Om, h)
+        _lib.check(_lib.lib().pmwd_gather3(
+            _lib.stream_ptr(disp.device), C.byref(desc), _lib.ptr(pmid), _lib.ptr(disp), _lib.ptr(F[0]),
+            _lib.ptr(F[1]), _lib.ptr(F[2]), _lib.ptr(acc), _lib.ptr(kick_vel), float(kick_factor)),
+            'pmwd_gather3')
+
+    def force_adj(self, pmid, disp, Om, pi, acc, alpha):
+        conf, comm = self.conf, self.comm
+        lib = _lib.lib()
+        dev = disp.device
+        Mx, My, Mz = conf.mesh_shape
+        h = self._halo(disp)
+        desc, F, val = self._mesh_forces(pmid, disp, Om, h)
+        st = _lib.stream_ptr(dev)
+        _lib.check(lib.pmwd_gather3(st, C.byref(desc), _lib.ptr(pmid), _lib.ptr(disp), _lib.ptr(F[0]),
+                                    _lib.ptr(F[1]), _lib.ptr(F[2]), _lib.ptr(acc), None, 0.0), 'pmwd_gather3')
+        # V_i = scatter(pi_i) (gather.py:113), halos reduced
+        V = torch.zeros_like(F)
+        _lib.check(lib.pmwd_scatter_soa(st, C.byref(desc), _lib.ptr(pmid), _lib.ptr(disp), _lib.ptr(pi), 0.0, 3,
+                                        _lib.ptr(V[0]), _lib.ptr(V[1]), _lib.ptr(V[2])), 'pmwd_scatter_soa')
+        Vs = comm.halo_reduce(V, h)
+        S = [comm.rfftn(Vs[i].contiguous()) for i in range(3)]
+        del V, Vs
+        out = torch.empty_like(S[0])
+        scale = float(np.float32(1.5 * Om / conf.mesh_size))
+        arr = (C.c_void_p * 3)(*[t.data_ptr() for t in S])
+        _lib.check(lib.pmwd_kspace_force_adj_slab(st, _lib.shape_arr(conf.mesh_shape), comm.y0, comm.my,
+                                                  float(conf.cell_size), scale, arr, _lib.ptr(out)),
+                   'pmwd_kspace_force_adj_slab')
+        del S
+        rc = torch.empty_like(F[0])
+        rc[h:h + comm.mx] = comm.irfftn(out, My, Mz)
+        comm.halo_fill(rc, h)
+        _lib.check(lib.pmwd_force_adj_gather(st, C.byref(desc), _lib.ptr(pmid), _lib.ptr(disp), _lib.ptr(F[0]),
+                                             _lib.ptr(F[1]), _lib.ptr(F[2]), _lib.ptr(rc), _lib.ptr(pi), val,
+                                             _lib.ptr(alpha)), 'pmwd_force_adj_gather')
+
+
+# ------------------------------------------------------------------------------------------
+def _kvec_T(conf, comm, shape, spacing, dev):
+    """Wavevectors of the transposed slab layout [n0][n1/P][n2/2+1] (pm_util.py:159-199)."""
+    P, r = comm.size, comm.rank
+    period = 2 * math.pi / spacing
+    k0 = torch.from_numpy(np.fft.fftfreq(shape[0]) * period).to(conf.float_dtype).to(dev).reshape(-1, 1, 1)
+    n1l = shape[1] // P
+    k1 = np.fft.fftfreq(shape[1])[r * n1l:(r + 1) * n1l] * period
+    k1 = torch.from_numpy(k1).to(conf.float_dtype).to(dev).reshape(1, -1, 1)
+    k2 = torch.from_numpy(np.fft.rfftfreq(shape[2]) * period).to(conf.float_dtype).to(dev).reshape(1, 1, -1)
+    return [k0, k1, k2]
+
+
+def white_noise_slab(seed, conf, comm, dev, exact=True):
+    """This rank's x-slab of the real white-noise field.  ``exact``: slice of the single-GPU
+    stream (numpy default_rng(seed) over the whole grid; for parity tests); otherwise an
+    independent per-rank stream (large runs)."""
+    nx, ny, nz = conf.ptcl_grid_shape
+    if exact:
+        full = np.random.default_rng(seed).standard_normal(conf.ptcl_grid_shape, dtype=np.float32)
+        return torch.from_numpy(full[comm.px0:comm.px0 + comm.pnx].copy()).to(dev)
+    g = torch.Generator(device=dev).manual_seed(seed * 1000003 + comm.rank)
+    return torch.randn((comm.pnx, ny, nz), device=dev, generator=g, dtype=conf.float_dtype)
+
+
+def lpt_slab(white, cosmo, conf, comm):
+    """``linear_modes`` + ``lpt`` (pmwd/modes.py:67-84, pmwd/lpt.py:136-212) on particle-grid
+    slabs from a real white-noise slab; elementwise k-space work in torch (run once, off the
+    hot path).  Returns this rank's ``Particles`` (Lagrangian x-slab)."""
+    dev = white.device
+    fdt = conf.float_dtype
+    nx, ny, nz = conf.ptcl_grid_shape
+    N = conf.ptcl_num
+    kvec = _kvec_T(conf, comm, conf.ptcl_grid_shape, conf.ptcl_spacing, dev)
+    k2 = kvec[0] ** 2 + kvec[1] ** 2 + kvec[2] ** 2
+    kk = torch.sqrt(k2)
+    Plin = linear_power(kk, None, cosmo, conf)
+    modes = comm.rfftn(white) / math.sqrt(N)                        # norm='ortho'
+    modes = modes * torch.sqrt(Plin * conf.box_vol).to(fdt)
+    modes = modes / conf.ptcl_cell_vol
+    inv = torch.where(k2 != 0, -1 / torch.where(k2 != 0, k2, torch.ones_like(k2)), torch.zeros_like(k2))
+    nyq = math.pi / conf.ptcl_spacing
+    eps = nyq * torch.finfo(fdt).eps
+    km = [torch.where((k.abs() - nyq).abs() <= eps, torch.zeros_like(k), k) for k in kvec]
+
+    def inv_fft(s):
+        return comm.irfftn(s, ny, nz) / N
+
+    pot = [modes * inv]
+    if conf.lpt_order > 1:
+        def strain(i, j):
+            m = -kvec[i] * kvec[j] if i == j else -km[i] * km[j]
+            return inv_fft(m * pot[0])
+        d = [strain(i, i) for i in range(3)]
+        L = d[0] * d[2] + d[0] * d[1] + d[1] * d[2]
+        for i in range(2):
+            for j in range(i + 1, 3):
+                s = strain(i, j)
+                L = L - s * s
+        pot.append(comm.rfftn(L) * inv)
+    if conf.lpt_order > 2:
+        raise NotImplementedError('TODO')
+
+    # gen_grid for this slab (particles.py:109-144); integer mesh ratio assumed exact here
+    full = Particles.gen_grid(conf.replace(ptcl_grid_shape=(1, ny, nz),
+                                           mesh_shape=(conf.mesh_shape[0] // nx,) + conf.mesh_shape[1:]),
+                              device=dev)
+    ratio = conf.mesh_shape[0] / nx
+    ix = torch.arange(comm.px0, comm.px0 + comm.pnx, device=dev)
+    pm_x = torch.round(ix * ratio).to(conf.pmid_dtype)
+    dx = ((ix * conf.mesh_shape[0] - pm_x.to(torch.int64) * nx) * (conf.cell_size / nx)).to(fdt)
+    pmid = full.pmid.reshape(1, ny * nz, 3).repeat(comm.pnx, 1, 1)
+    pmid[:, :, 0] = pm_x[:, None]
+    disp = full.disp.reshape(1, ny * nz, 3).repeat(comm.pnx, 1, 1)
+    disp[:, :, 0] = dx[:, None]
+    pmid = pmid.reshape(-1, 3).contiguous()
+    disp = disp.reshape(-1, 3).contiguous()
+    vel = torch.zeros_like(disp)
+
+    a = conf.a_start
+    for order in range(1, 1 + conf.lpt_order):
+        D = growth(a, cosmo, conf, order=order)
+        a2HDp = a ** 2 * torch.sqrt(E2(a, cosmo)) * growth(a, cosmo, conf, order=order, deriv=1)
+        D = float(np.float32(float(D)))
+        a2HDp = float(np.float32(float(a2HDp)))
+        for i in range(3):
+            grad = inv_fft(-1j * km[i] * pot[order - 1]).to(fdt).reshape(-1)
+            disp[:, i] += D * grad
+            vel[:, i] += a2HDp * grad
+    return Particles(conf, pmid, disp, vel=vel)
+
+
+# ------------------------------------------------------------------------------------------
+def nbody_slab(ptcl, cosmo, conf, comm, reverse=False, force=None):
+    """``nbody`` (pmwd/nbody.py:215-223) on this rank's Lagrangian slab of particles."""
+    from .nbody import _Store, _owned, drift_factor, kick_factor, _f32, _kick_drift
+    force = force or SlabForce(conf, comm)
+    a_nbody = conf.a_nbody.tolist()
+    if reverse:
+        a_nbody = a_nbody[::-1]
+    Om = float(cosmo.Omega_m)
+    with torch.no_grad():
+        p = _owned(ptcl, conf)
+        store = _Store(conf, dict(pmid=p.pmid.clone(), disp=p.disp, vel=p.vel, acc=p.acc))
+        store.desc_fn = lambda pmid: force._desc(pmid, max(force.h_alloc, 1))
+        a = store.arrays
+        force.force(a['pmid'], a['disp'], Om, a['acc'])
+        for a_prev, a_next in zip(a_nbody[:-1], a_nbody[1:]):
+            step_slab(a_prev, a_next, store, cosmo, conf, force)
+            store.maybe_reorder(sync_max=comm.allreduce_max)
+        disp, vel, acc = store.lagrangian('disp', 'vel', 'acc')
+    return Particles(conf, ptcl.pmid, disp, vel=vel, acc=acc)
+
+
+def step_slab(a_prev, a_next, store, cosmo, conf, force):
+    """One KDK step (default ``symp_splits``; nbody.py:121-140) on the store's arrays."""
+    from .nbody import drift_factor, kick_factor, _f32, _kick_drift
+    if tuple(conf.symp_splits) != ((0, 0.5), (1, 0.5)):
+        raise NotImplementedError('the slab integrator implements the default KDK splitting')
+    Om = float(cosmo.Omega_m)
+    a_mid = a_prev * 0.5 + a_next * 0.5
+    k1 = _f32(kick_factor(a_prev, a_prev, a_mid, cosmo, conf))
+    d = _f32(drift_factor(a_mid, a_prev, a_next, cosmo, conf))
+    k2 = _f32(kick_factor(a_next, a_mid, a_next, cosmo, conf))
+    _kick_drift(store.ptcl, k1, d, True, True)
+    a = store.arrays
+    force.force(a['pmid'], a['disp'], Om, a['acc'], a['vel'], k2)
+
+
+# ------------------------------------------------------------------------------------------
+def init_process_group():
+    if dist.is_initialized():
+        return
+    backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+    if torch.cuda.is_available():
+        torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+    dist.init_process_group(backend)
+
+
+def run_bench(args):
+    """bench.py at N > 1: weak scaling, per-GPU work fixed at n^3 particles / (2n)^3 cells."""
+    import json
+    import bench as B
+    init_process_group()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    dev = torch.device('cuda', local)
+    import pmwd_b200 as pm
+    shape = B.rank_grid(args.n, world)
+    conf = pm.Configuration(1., shape, mesh_shape=2, device=dev, reorder_every=args.reorder_every,
+                            reorder_min_disp=args.reorder_min_disp)
+    comm = SlabComm(conf)
+    cosmo = pm.boltzmann(pm.SimpleLCDM(conf), conf)
+    with torch.no_grad():
+        white = white_noise_slab(0, conf, comm, dev, exact=False)
+        ic = lpt_slab(white, cosmo, conf, comm)
+        del white
+    torch.cuda.empty_cache()
+    from .nbody import _Store, _owned
+    force = SlabForce(conf, comm)
+    a = conf.a_nbody.tolist()
+    nsched = len(a) - 1
+    Om = float(cosmo.Omega_m)
+
+    def fresh():
+        p = _owned(ic, conf)
+        st = _Store(conf, dict(pmid=p.pmid.clone(), disp=p.disp, vel=p.vel, acc=p.acc))
+        st.desc_fn = lambda pmid: force._desc(pmid, max(force.h_alloc, 1))
+        ar = st.arrays
+        force.force(ar['pmid'], ar['disp'], Om, ar['acc'])
+        return st
+
+    W, K = args.warmup, args.steps
+    with torch.no_grad():
+        store, i = fresh(), 0
+        for _ in range(W):
+            if i == nsched:
+                store, i = fresh(), 0
+            step_slab(a[i], a[i + 1], store, cosmo, conf, force); store.maybe_reorder(sync_max=comm.allreduce_max); i += 1
+        torch.cuda.synchronize(); dist.barrier()
+        sampler = B.ClockSampler(local); sampler.start()
+        l0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(K):
+            if i == nsched:
+                store, i = fresh(), 0
+            step_slab(a[i], a[i + 1], store, cosmo, conf, force); store.maybe_reorder(sync_max=comm.allreduce_max); i += 1
+        e1.record()
+        torch.cuda.synchronize(); dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = float(ms)
+        launches = _lib.launch_count() - l0
+        clocks = sampler.stop()
+    assert torch.isfinite(store.arrays['disp']).all()
+    Np = conf.ptcl_num
+    if rank == 0:
+        Nm = conf.mesh_size
+        peak, peak_src = B._peaks()
+        line = {
+            'metric': 'particle_updates_per_sec', 'value': Np * K / (ms * 1e-3),
+            'unit': 'particle-updates/s', 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms / K,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic', 'config': B.workload_config(args, world),
+            'steps_per_sec': K / (ms * 1e-3), 'clocks': clocks, 'gpu_launches': launches,
+            'halo_planes': force.h_alloc,
+            'roofline': {'bound': 'hbm', 'unit': 'GB/s', 'peak': peak, 'peak_source': peak_src,
+                         'kernel': 'whole step (per GPU)', 'traffic': None,
+                         'achieved': (132 * Np + 68 * Nm) / world / (ms / K) / 1e6,
+                         'frac': (132 * Np + 68 * Nm) / world / (ms / K) / 1e6 / peak},
+            'e2e': None, 'cpu_baseline': None,
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()

@@ -16,7 +16,7 @@ import torch
 from . import _lib
 from .boltzmann import growth
 from .cosmology import E2, H_deriv
-from .gravity import gravity, force_into, force_adj_into
+from .gravity import gravity, force_into, force_adj_into, _force_desc
 from .particles import Particles
 
 
@@ -78,6 +78,109 @@ def _owned(ptcl, conf, need_acc=True):
 
 def _fast_ok(ptcl, conf):
     return conf.dim == 3 and ptcl.pmid.dtype == torch.int16
+
+
+class _Store:
+    """The integrator's private particle arrays, optionally kept in mesh-cell order.
+
+    ``arrays`` maps name -> (N, 3) tensor (``pmid`` int16, the rest float32).  ``reorder()``
+    re-sorts all of them by the particles' current mesh cell (``pmwd_cell_sort_perm`` +
+    ``pmwd_permute_rows``); ``lagrangian(name)`` returns an array restored to the reference's
+    Lagrangian order.  Per-particle arithmetic does not depend on the storage order."""
+
+    def __init__(self, conf, arrays):
+        self.conf = conf
+        self.arrays = dict(arrays)
+        self.lag = None            # uint32 view as int32 tensor: Lagrangian index of each slot
+        self._alt = None
+        self._perm = None
+        self._scratch = None
+        self.steps_since = 0
+        self.active = False
+        self.reorders = 0
+        self.desc_fn = None        # pmid -> pmwd_cic_desc used for the sort keys (slab runs)
+
+    @property
+    def ptcl(self):
+        a = self.arrays
+        return Particles(self.conf, a['pmid'], a['disp'], vel=a['vel'], acc=a['acc'])
+
+    def maybe_reorder(self, sync_max=None):
+        conf = self.conf
+        if conf.reorder_every <= 0 or conf.dim != 3 or self.arrays['pmid'].dtype != torch.int16:
+            return False
+        self.steps_since += 1
+        if self.steps_since < conf.reorder_every:
+            return False
+        self.steps_since = 0
+        if not self.active:
+            # one cheap reduction + sync every `reorder_every` steps until structure has formed
+            m = self.arrays['disp'].abs().max()
+            m = sync_max(m) if sync_max is not None else float(m)
+            if m < conf.reorder_min_disp * conf.cell_size:
+                return False
+            self.active = True
+        self.reorder()
+        return True
+
+    def reorder(self):
+        conf, a = self.conf, self.arrays
+        dev = a['disp'].device
+        n = a['disp'].shape[0]
+        lib = _lib.lib()
+        desc = self.desc_fn(a['pmid']) if self.desc_fn is not None else _force_desc(a['pmid'], conf)
+        if self.lag is None:
+            self.lag = torch.arange(n, dtype=torch.int32, device=dev)   # bit pattern of uint32
+            self._perm = torch.empty(n, dtype=torch.int32, device=dev)
+            nbytes = lib.pmwd_cell_sort_scratch_bytes(C.byref(desc))
+            self._scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            self._alt = {k: torch.empty_like(v) for k, v in a.items()}
+            self._alt['lag'] = torch.empty_like(self.lag)
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            _lib.check(lib.pmwd_cell_sort_perm(st, C.byref(desc), _lib.ptr(a['pmid']), _lib.ptr(a['disp']),
+                                               _lib.ptr(self._perm), _lib.ptr(self._scratch),
+                                               self._scratch.numel()), 'pmwd_cell_sort_perm')
+            names = list(a) + ['lag']
+            cur = dict(a, lag=self.lag)
+            src = (C.c_void_p * len(names))(*[cur[k].data_ptr() for k in names])
+            dst = (C.c_void_p * len(names))(*[self._alt[k].data_ptr() for k in names])
+            rb = (C.c_int32 * len(names))(*[cur[k].element_size() * (cur[k].shape[1] if cur[k].ndim > 1 else 1)
+                                            for k in names])
+            _lib.check(lib.pmwd_permute_rows(st, n, _lib.ptr(self._perm), len(names), src, dst, rb, 0),
+                       'pmwd_permute_rows')
+        new = {k: self._alt[k] for k in a}
+        new_lag = self._alt['lag']
+        self._alt = dict(a, lag=self.lag)
+        self.arrays, self.lag = new, new_lag
+        self.reorders += 1
+
+    def lagrangian(self, *names):
+        """Arrays restored to Lagrangian order (new tensors; storage untouched)."""
+        a = self.arrays
+        if self.lag is None:
+            out = [a[k].clone() for k in names]
+            return out if len(out) > 1 else out[0]
+        dev = a['disp'].device
+        n = a['disp'].shape[0]
+        outs = [torch.empty_like(a[k]) for k in names]
+        with torch.cuda.device(dev):
+            src = (C.c_void_p * len(names))(*[a[k].data_ptr() for k in names])
+            dst = (C.c_void_p * len(names))(*[o.data_ptr() for o in outs])
+            rb = (C.c_int32 * len(names))(*[a[k].element_size() * a[k].shape[1] for k in names])
+            _lib.check(_lib.lib().pmwd_permute_rows(_lib.stream_ptr(dev), n, _lib.ptr(self.lag), len(names),
+                                                    src, dst, rb, 1), 'pmwd_permute_rows')
+        return outs if len(outs) > 1 else outs[0]
+
+
+def _store_from(ptcl, conf, **extra):
+    p = _owned(ptcl, conf)
+    # pmid is cloned too: the store ping-pongs between two buffer sets when it re-sorts and
+    # must never write into the caller's tensors
+    pmid = p.pmid.clone() if conf.reorder_every > 0 else p.pmid
+    arrays = dict(pmid=pmid, disp=p.disp, vel=p.vel, acc=p.acc)
+    arrays.update(extra)
+    return _Store(conf, arrays)
 
 
 # --------------------------------------------------------------- reference-shaped pieces
@@ -194,11 +297,13 @@ def _nbody_forward(ptcl, cosmo, conf, reverse):
     if reverse:
         a_nbody = a_nbody[::-1]
     with torch.no_grad():
-        ptcl = _owned(ptcl, conf)
-        _force_inplace(ptcl, cosmo, conf)
+        store = _store_from(ptcl, conf)
+        _force_inplace(store.ptcl, cosmo, conf)
         for a_prev, a_next in zip(a_nbody[:-1], a_nbody[1:]):
-            _integrate_inplace(a_prev, a_next, ptcl, cosmo, conf)
-    return ptcl
+            _integrate_inplace(a_prev, a_next, store.ptcl, cosmo, conf)
+            store.maybe_reorder()
+        disp, vel, acc = store.lagrangian('disp', 'vel', 'acc')
+    return Particles(conf, ptcl.pmid, disp, vel=vel, acc=acc, attr=ptcl.attr)
 
 
 # ------------------------------------------------------------------------------- adjoint
@@ -234,12 +339,18 @@ def nbody_adj(ptcl, ptcl_cot, obsvbl_cot, cosmo, conf, reverse=False):
     dev = ptcl.disp.device
     Om = float(cosmo.Omega_m)
     lib = _lib.lib()
+    pmid_in = ptcl.pmid
     with torch.no_grad():
-        ptcl = _owned(ptcl, conf)
-        xi = ptcl_cot.disp.detach().to(conf.float_dtype).clone(memory_format=torch.contiguous_format)
-        pi = ptcl_cot.vel.detach().to(conf.float_dtype).clone(memory_format=torch.contiguous_format)
-        alpha = torch.empty_like(xi)
-        n = xi.numel()
+        store = _store_from(
+            ptcl, conf,
+            xi=ptcl_cot.disp.detach().to(conf.float_dtype).clone(memory_format=torch.contiguous_format),
+            pi=ptcl_cot.vel.detach().to(conf.float_dtype).clone(memory_format=torch.contiguous_format))
+        store.arrays['alpha'] = torch.empty_like(store.arrays['xi'])
+        n = store.arrays['xi'].numel()
+        if conf.reorder_every > 0 and _fast_ok(ptcl, conf) and \
+                float(store.arrays['disp'].abs().max()) >= conf.reorder_min_disp * conf.cell_size:
+            store.active = True
+            store.reorder()       # the adjoint starts from the evolved (clustered) state
         pairs = list(zip(a_nbody[:0:-1], a_nbody[-2::-1]))
         # per kick / drift: float64 dot products kept on the device until the end
         nsplit = len(conf.symp_splits)
@@ -247,15 +358,20 @@ def nbody_adj(ptcl, ptcl_cot, obsvbl_cot, cosmo, conf, reverse=False):
         records = []   # (kind, slot, column, factor, grads)
 
         def kd_adj(K, D, do_kick, do_drift, slot):
+            a = store.arrays
             with torch.cuda.device(dev):
                 _lib.check(lib.pmwd_kick_drift_adj(
-                    _lib.stream_ptr(dev), n, _lib.ptr(ptcl.disp), _lib.ptr(ptcl.vel),
-                    _lib.ptr(ptcl.acc), _lib.ptr(xi), _lib.ptr(pi), _lib.ptr(alpha), K, D,
+                    _lib.stream_ptr(dev), n, _lib.ptr(a['disp']), _lib.ptr(a['vel']),
+                    _lib.ptr(a['acc']), _lib.ptr(a['xi']), _lib.ptr(a['pi']), _lib.ptr(a['alpha']), K, D,
                     int(do_kick), int(do_drift), C.c_void_p(sums[slot].data_ptr())),
                     'pmwd_kick_drift_adj')
 
+        def f_adj():
+            a = store.arrays
+            force_adj_into(a['pmid'], a['disp'], Om, conf, a['pi'], a['acc'], a['alpha'])
+
         # nbody_adj_init (nbody.py:226-236)
-        force_adj_into(ptcl.pmid, ptcl.disp, Om, conf, pi, ptcl.acc, alpha)
+        f_adj()
 
         slot = 0
         for a_prev, a_next in pairs:
@@ -281,8 +397,9 @@ def nbody_adj(ptcl, ptcl_cot, obsvbl_cot, cosmo, conf, reverse=False):
                 kd_adj(fk, fd, k != 0, d != 0, slot)
                 slot += 1
                 if d != 0:
-                    force_adj_into(ptcl.pmid, ptcl.disp, Om, conf, pi, ptcl.acc, alpha)
+                    f_adj()
                     a_acc = a_disp
+            store.maybe_reorder()
 
         sums_h = sums.cpu()
         cosmo_cot = {nme: torch.zeros_like(getattr(cosmo, nme)) for nme in _COSMO_LEAVES
@@ -296,7 +413,9 @@ def nbody_adj(ptcl, ptcl_cot, obsvbl_cot, cosmo, conf, reverse=False):
                 # Omega_m, equal to sum(pi . acc) / Omega_m (gravity.py:54)
                 cosmo_cot['Omega_m'] = cosmo_cot['Omega_m'] - (S / Om) * factor
 
-    ptcl_cot = Particles(conf, ptcl.pmid, xi, vel=pi, acc=alpha)
+        disp, vel, acc, xi, pi, alpha = store.lagrangian('disp', 'vel', 'acc', 'xi', 'pi', 'alpha')
+    ptcl = Particles(conf, pmid_in, disp, vel=vel, acc=acc)
+    ptcl_cot = Particles(conf, pmid_in, xi, vel=pi, acc=alpha)
     return ptcl, ptcl_cot, cosmo_cot
 
 

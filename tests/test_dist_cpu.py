@@ -1,0 +1,72 @@
+"""world_size-2 gloo tests (CPU) of the slab decomposition's host logic: the distributed FFT
+(2-D local transforms + one all-to-all + 1-D transform) against numpy's rfftn/irfftn of the
+gathered field, the neighbour halo reduce / fill, and the particle partition."""
+import os
+import socket
+import subprocess
+import sys
+import textwrap
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = textwrap.dedent('''
+    import sys, numpy as np, torch, torch.distributed as dist
+    sys.path.insert(0, %r)
+    from pmwd_b200.configuration import Configuration
+    from pmwd_b200.dist import SlabComm
+    dist.init_process_group('gloo')
+    r, P = dist.get_rank(), dist.get_world_size()
+    conf = Configuration(1., (8, 4, 6), mesh_shape=2, device='cpu')
+    comm = SlabComm(conf)
+    Mx, My, Mz = conf.mesh_shape
+    assert (comm.mx, comm.my) == (Mx // P, My // P) and comm.x0 == r * comm.mx
+    sl = comm.local_slice()
+    assert sl.stop - sl.start == conf.ptcl_num // P and sl.start == r * conf.ptcl_num // P
+
+    full = np.random.default_rng(0).standard_normal(conf.mesh_shape).astype(np.float32)
+    slab = torch.from_numpy(full[comm.x0:comm.x0 + comm.mx].copy())
+    spec = comm.rfftn(slab)                                # [Mx][my][Mz/2+1]
+    ref = np.fft.rfftn(full.astype(np.float64))
+    got = spec.numpy()
+    np.testing.assert_allclose(got, ref[:, comm.y0:comm.y0 + comm.my], rtol=0, atol=2e-4 * np.abs(ref).max())
+    back = comm.irfftn(spec, My, Mz) / full.size
+    np.testing.assert_allclose(back.numpy(), full[comm.x0:comm.x0 + comm.mx], rtol=0, atol=1e-5)
+
+    # halo reduce: every rank deposits ones into its extended slab -> owned planes get the
+    # neighbours' halo contributions;  halo fill: halos equal the neighbours' owned planes
+    h = 3
+    ext = torch.zeros(comm.mx + 2 * h, My, Mz)
+    ext += (r + 1)
+    own = comm.halo_reduce(ext.clone(), h)
+    left, right = (r - 1) %% P + 1, (r + 1) %% P + 1
+    exp = torch.full((comm.mx, My, Mz), float(r + 1))
+    exp[:h] += left
+    exp[comm.mx - h:] += right
+    assert torch.equal(own, exp)
+    planes = torch.arange(comm.x0, comm.x0 + comm.mx, dtype=torch.float32).reshape(-1, 1, 1).expand(comm.mx, My, Mz)
+    ext3 = torch.zeros(3, comm.mx + 2 * h, My, Mz)
+    ext3[:, h:h + comm.mx] = planes
+    comm.halo_fill(ext3, h)
+    want = (torch.arange(comm.x0 - h, comm.x0 + comm.mx + h) %% Mx).float().reshape(-1, 1, 1).expand(-1, My, Mz)
+    assert torch.equal(ext3[1], want)
+    assert comm.allreduce_max(torch.tensor(float(r))) == P - 1
+    print('rank', r, 'ok')
+''')
+
+
+def _free_port():
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+@pytest.mark.timeout(300)
+def test_slab_host_logic_gloo_world2(tmp_path):
+    script = tmp_path / 'worker.py'
+    script.write_text(WORKER % ROOT)
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+           '--master-addr', '127.0.0.1', '--master-port', str(_free_port()), str(script)]
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES='', OMP_NUM_THREADS='1')
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=280)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count('ok') == 2

@@ -22,7 +22,8 @@ def _confs(shape, mesh_shape=2, spacing=1., **kw):
     pm = _pm()
     return (pm.Configuration(spacing, shape, mesh_shape=mesh_shape, **kw),
             O.Conf(spacing, shape, mesh_shape=mesh_shape,
-                   **{k: v for k, v in kw.items() if k != 'scatter_mode'}))
+                   **{k: v for k, v in kw.items() if k not in ('scatter_mode', 'reorder_every',
+                                                               'reorder_min_disp')}))
 
 
 def _cos(a, b):
@@ -317,6 +318,33 @@ def test_nbody_config1_vs_oracle(mode):
     assert 30 < out.disp.std().item() / ptcl.disp.std().item() < 60
 
 
+@pytest.mark.parametrize('mode', ['atomic', 'deterministic'])
+def test_storage_reorder_is_transparent(mode):
+    """Re-sorting the integrator's particle storage by mesh cell (csrc/reorder.cu) must not
+    change results beyond float32 summation-order noise, and outputs stay in Lagrangian order;
+    forward and adjoint."""
+    base = dict(a_nbody_maxstep=1 / 16, scatter_mode=mode)
+    pm, conf0, oconf, cosmo, ocosmo, ic, ptcl = _ic(32, reorder_every=0, **base)
+    conf1 = conf0.replace(reorder_every=1, reorder_min_disp=0.0)
+    outs = []
+    for conf in (conf0, conf1):
+        d = ptcl.disp.clone().requires_grad_(True)
+        out, _ = pm.nbody(pm.Particles(conf, ptcl.pmid, d, vel=ptcl.vel), None, cosmo, conf)
+        (out.disp ** 2).sum().backward()
+        outs.append((pm.Particles(conf, out.pmid, out.disp.detach(), vel=out.vel.detach()), d.grad))
+    (o0, g0), (o1, g1) = outs
+    assert torch.equal(o0.pmid, ptcl.pmid)                     # caller's arrays untouched
+    assert torch.equal(o0.pmid, o1.pmid)
+    cell = conf0.cell_size
+    err = ((o0.disp - o1.disp).abs() / cell).cpu().numpy()
+    assert _rms(err) <= 1e-4 and np.quantile(err, 0.999) <= 1e-4
+    assert _rms((o0.vel - o1.vel).cpu().numpy()) <= 1e-4 * _rms(o0.vel.cpu().numpy())
+    assert _cos(g0.cpu().numpy(), g1.cpu().numpy()) >= 0.9999
+    if mode == 'deterministic':      # still bitwise reproducible run to run
+        out2, _ = pm.nbody(pm.Particles(conf1, ptcl.pmid, ptcl.disp, vel=ptcl.vel), None, cosmo, conf1)
+        assert torch.equal(out2.disp, o1.disp) and torch.equal(out2.vel, o1.vel)
+
+
 def test_nbody_reversibility():
     """pm_test.py:177-192: forward then reverse integration returns the initial state to
     float32 round-off (RMSD/sigma of the order of the reference's table, adjoint.tex:1534-1541)."""
@@ -335,7 +363,8 @@ def test_nbody_reversibility():
 def test_nbody_step_api_matches_nbody():
     """nbody_init / nbody_step (imported by user scripts, demo_data_time_evo.py:17) give the
     same trajectory as nbody, and never modify their inputs."""
-    pm, conf, oconf, cosmo, ocosmo, ic, ptcl = _ic(16, a_nbody_maxstep=0.25, scatter_mode='deterministic')
+    pm, conf, oconf, cosmo, ocosmo, ic, ptcl = _ic(16, a_nbody_maxstep=0.25, scatter_mode='deterministic',
+                                                    reorder_every=0)
     d0 = ptcl.disp.clone()
     out, _ = pm.nbody(ptcl, None, cosmo, conf)
     a = conf.a_nbody

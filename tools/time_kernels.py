@@ -102,6 +102,12 @@ def run(n, sigma, results):
     alpha = torch.empty_like(pi)
     rec('force_adj', timeit(lambda: force_adj_into(ptcl.pmid, ptcl.disp, 0.3, conf, pi, acc, alpha), reps=3),
         (72 + 30 + 42) * Np + (68 + 24 + 24 + 16 + 8 + 16) * Nm)
+    from pmwd_b200.nbody import _Store
+    store = _Store(conf, dict(pmid=ptcl.pmid, disp=ptcl.disp, vel=ptcl.vel, acc=ptcl.acc))
+    store.reorder()
+    rec('reorder(sort+permute 4 arrays)', timeit(store.reorder, reps=3, warm=1), 2 * 46 * Np)
+    sp = store.ptcl
+    rec('force_fwd_after_sort', timeit(lambda: force_into(sp.pmid, sp.disp, 0.3, conf, sp.acc)), 72 * Np + 68 * Nm)
     step = row['kick_drift']['ms'] + row['force_fwd+kick']['ms']
     row['fwd_step'] = dict(ms=round(step, 3), updates_per_s=round(Np / step * 1e3, 0),
                            frac=round((132 * Np + 68 * Nm) / step / 1e6 / HBM, 3))
