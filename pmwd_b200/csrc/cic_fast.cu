@@ -235,7 +235,8 @@ bool cic_is_fast(const pmwd_cic_desc* d) {
   for (int a = 0; a < 3; ++a) if (d->wrap_shape[a] <= 0 || d->mesh_shape[a] <= 0) return false;
   if (d->offset[1] != 0.0 || d->offset[2] != 0.0) return false;
   if (d->mesh_shape[1] != d->wrap_shape[1] || d->mesh_shape[2] != d->wrap_shape[2]) return false;
-  if (d->mesh_shape[0] > d->wrap_shape[0]) return false;
+  // mesh_shape[0] may exceed wrap_shape[0] (slab + halos wider than the box on 2 ranks): every
+  // global plane then maps to its first local copy, consistently for scatter and gather
   double a1 = (double)(float)d->cell_size;
   double q = floor(d->offset[0] / a1);
   if (d->offset[0] - q * a1 != 0.0) return false;            // whole cells only

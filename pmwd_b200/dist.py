@@ -79,7 +79,9 @@ class SlabComm:
         nzc = s.shape[-1]
         s = s.reshape(mx, P, my, nzc).permute(1, 0, 2, 3).contiguous()   # pack per destination
         s = self._a2a(s).reshape(P * mx, my, nzc)                   # blocks arrive in x order
-        return torch.fft.fft(s, dim=0)                              # 1-D C2C over x
+        # torch returns a strided view for transforms over a leading dim; the kernels take raw
+        # pointers, so materialise the C-order layout
+        return torch.fft.fft(s, dim=0).contiguous()                 # 1-D C2C over x
 
     def irfftn(self, spec, My, Mz):
         """Inverse of :meth:`rfftn` WITHOUT the 1/N (callers fold it into their scale)."""
@@ -354,6 +356,14 @@ def nbody_slab(ptcl, cosmo, conf, comm, reverse=False, force=None):
             store.maybe_reorder(sync_max=comm.allreduce_max)
         disp, vel, acc = store.lagrangian('disp', 'vel', 'acc')
     return Particles(conf, ptcl.pmid, disp, vel=vel, acc=acc)
+
+
+def nbody_adj_slab(ptcl, ptcl_cot, cosmo, conf, comm, reverse=False, force=None):
+    """``nbody_adj`` (pmwd/nbody.py:251-260) on this rank's slab: returns
+    ``(ptcl, ptcl_cot, cosmo_cot)`` with ``cosmo_cot`` already summed over ranks."""
+    from .nbody import nbody_adj
+    force = force or SlabForce(conf, comm)
+    return nbody_adj(ptcl, ptcl_cot, None, cosmo, conf, reverse=reverse, _slab=force)
 
 
 def step_slab(a_prev, a_next, store, cosmo, conf, force):

@@ -324,8 +324,12 @@ def _factor_valgrad(fun, a0, a1, a2, cosmo, conf):
     return float(val.detach()), grads
 
 
-def nbody_adj(ptcl, ptcl_cot, obsvbl_cot, cosmo, conf, reverse=False):
+def nbody_adj(ptcl, ptcl_cot, obsvbl_cot, cosmo, conf, reverse=False, _slab=None):
     """N-body time integration with adjoint equation (``nbody.py:226-260``).
+
+    ``_slab`` (internal): a ``dist.SlabForce`` when the particles are one rank's slab of a
+    multi-GPU run; forces then go through the slab pipeline and the float64 dot products are
+    all-reduced once at the end.
 
     Returns ``(ptcl, ptcl_cot, cosmo_cot)``; ``cosmo_cot`` is a dict leaf-name -> float64
     tensor over the leaves ``nbody`` can touch (all other leaves of the reference's
@@ -346,6 +350,8 @@ def nbody_adj(ptcl, ptcl_cot, obsvbl_cot, cosmo, conf, reverse=False):
             xi=ptcl_cot.disp.detach().to(conf.float_dtype).clone(memory_format=torch.contiguous_format),
             pi=ptcl_cot.vel.detach().to(conf.float_dtype).clone(memory_format=torch.contiguous_format))
         store.arrays['alpha'] = torch.empty_like(store.arrays['xi'])
+        if _slab is not None:
+            store.desc_fn = lambda pmid: _slab._desc(pmid, max(_slab.h_alloc, 1))
         n = store.arrays['xi'].numel()
         if conf.reorder_every > 0 and _fast_ok(ptcl, conf) and \
                 float(store.arrays['disp'].abs().max()) >= conf.reorder_min_disp * conf.cell_size:
@@ -368,7 +374,10 @@ def nbody_adj(ptcl, ptcl_cot, obsvbl_cot, cosmo, conf, reverse=False):
 
         def f_adj():
             a = store.arrays
-            force_adj_into(a['pmid'], a['disp'], Om, conf, a['pi'], a['acc'], a['alpha'])
+            if _slab is not None:
+                _slab.force_adj(a['pmid'], a['disp'], Om, a['pi'], a['acc'], a['alpha'])
+            else:
+                force_adj_into(a['pmid'], a['disp'], Om, conf, a['pi'], a['acc'], a['alpha'])
 
         # nbody_adj_init (nbody.py:226-236)
         f_adj()
@@ -401,6 +410,8 @@ def nbody_adj(ptcl, ptcl_cot, obsvbl_cot, cosmo, conf, reverse=False):
                     a_acc = a_disp
             store.maybe_reorder()
 
+        if _slab is not None:
+            _slab.comm.allreduce_sum_(sums)
         sums_h = sums.cpu()
         cosmo_cot = {nme: torch.zeros_like(getattr(cosmo, nme)) for nme in _COSMO_LEAVES
                      if getattr(cosmo, nme) is not None}

@@ -62,7 +62,19 @@ def main():
     err = ((out.disp - ref.disp[sl]).abs() / conf.cell_size)
     q = float(torch.quantile(err.flatten()[:: max(1, err.numel() // 1000000)], 0.999))
     assert rms(err) < 1e-4 and q < 1e-4, (rms(err), q)
+    # ---- reverse-time adjoint: slab vs single GPU (cos >= 0.9999), cosmology cotangent summed
+    w = torch.randn(ref.disp.shape, device=dev, generator=g)
+    cot = pm.Particles(conf, ref.pmid, w, vel=torch.zeros_like(w))
+    _, pc_ref, cc_ref = pm.nbody_adj(ref, cot, None, cosmo, conf)
+    cot_l = pm.Particles(conf, pm_l, w[sl].contiguous(), vel=torch.zeros_like(w[sl]))
+    _, pc, cc = pd.nbody_adj_slab(pm.Particles(conf, pm_l, out.disp, vel=out.vel), cot_l, cosmo, conf, comm)
+    a_, b_ = pc.disp.double().flatten(), pc_ref.disp[sl].double().flatten()
+    cs = float(a_ @ b_ / torch.sqrt((a_ @ a_) * (b_ @ b_)))
+    assert cs >= 0.9999, cs
+    rel = abs(float(cc['Omega_m']) / float(cc_ref['Omega_m']) - 1)
+    assert rel < 1e-2, rel
     dist.barrier()
+    print(f'rank {rank}/{world} ok: adj cos {cs:.6f} Om_cot rel {rel:.1e}', flush=True)
     print(f'rank {rank}/{world} ok: lpt {ev:.1e} force {e:.1e} alpha {ea:.1e} nbody rms {rms(err):.1e} p999 {q:.1e}',
           flush=True)
     dist.destroy_process_group()

@@ -26,4 +26,4 @@ def test_slab_matches_single_gpu():
            os.path.join(ROOT, 'tests', 'dist_gpu_worker.py')]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=850)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count(' ok: ') == world
+    assert r.stdout.count(' ok: ') == 2 * world
