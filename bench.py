@@ -29,6 +29,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ['NCCL_DEBUG'] = 'WARN'      # keep NCCL's version banner off stdout: ONE JSON line
 
 
 def _peaks():
@@ -331,8 +332,8 @@ def main():
     ap.add_argument('--n', type=int, default=512, help='particles per side per GPU (mesh is 2x)')
     ap.add_argument('--scatter-mode', default='atomic', choices=['atomic', 'deterministic'])
     ap.add_argument('--e2e-steps', type=int, default=4)
-    ap.add_argument('--reorder-every', type=int, default=4)
-    ap.add_argument('--reorder-min-disp', type=float, default=1.5)
+    ap.add_argument('--reorder-every', type=int, default=3)
+    ap.add_argument('--reorder-min-disp', type=float, default=1.0)
     ap.add_argument('--cpu-n', type=int, default=96)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()

@@ -98,6 +98,12 @@ int pmwd_fft_r2c(pmwd_ctx* ctx, void* stream, int rank, const int32_t* shape,
 int pmwd_fft_c2r(pmwd_ctx* ctx, void* stream, int rank, const int32_t* shape,
                  void* in_c64, float* out, float scale);
 
+/* In-place 1-D complex transforms along the leading axis of data[n][inner] (stride = inner):
+ * the x-pass of the slab-decomposed FFT.  Unnormalised in both directions.  The plan for a
+ * given (n, inner) is created (allocating) on first use. */
+int pmwd_fft_c2c_lead(pmwd_ctx* ctx, void* stream, int n, long long inner, void* data_c64,
+                      int inverse);
+
 /* ---- CIC scatter / gather and their VJPs ------------------------------------------ */
 /* _scatter (pmwd/scatter.py:33-83): mesh[ind] += val * frac.  `val` is either a device
  * array float[N][nchan] or NULL, in which case `val_scalar` is broadcast (0-D val).

@@ -65,9 +65,9 @@ class Configuration:
 
     # additions of this implementation (not in the reference)
     scatter_mode: str = 'atomic'          # 'atomic' | 'deterministic' (cell-sorted)
-    reorder_every: int = 4                # re-sort the integrator's particle storage by mesh cell
+    reorder_every: int = 3                # re-sort the integrator's particle storage by mesh cell
                                           # every this many steps (0 = never; see csrc/reorder.cu)
-    reorder_min_disp: float = 1.5         # ... once max |disp| exceeds this many cells
+    reorder_min_disp: float = 1.0         # ... once max |disp| exceeds this many cells
     device: Union[str, torch.device] = 'cuda'
 
     def __post_init__(self):

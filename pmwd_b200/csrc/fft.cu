@@ -25,6 +25,7 @@ struct pmwd_ctx {
   int device = 0;
   std::mutex mu;
   std::map<std::tuple<int, int, int, int>, pmwd::PlanPair> plans;
+  std::map<std::tuple<int, long long, long long>, cufftHandle> xplans;   // strided 1-D C2C
   void* work = nullptr;
   size_t work_bytes = 0;
 };
@@ -105,6 +106,7 @@ extern "C" int pmwd_ctx_destroy(pmwd_ctx* ctx) {
     if (kv.second.r2c) cufftDestroy(kv.second.r2c);
     if (kv.second.c2r) cufftDestroy(kv.second.c2r);
   }
+  for (auto& kv : ctx->xplans) cufftDestroy(kv.second);
   if (ctx->work) cudaFree(ctx->work);
   cudaSetDevice(prev);
   delete ctx;
@@ -171,5 +173,40 @@ extern "C" int pmwd_fft_c2r(pmwd_ctx* ctx, void* stream, int rank, const int32_t
     scale_kernel<<<grid, 256, 0, as_stream(stream)>>>(out, n, scale);
     PMWD_LAUNCH_CHECK();
   }
+  return PMWD_OK;
+}
+
+// 1-D complex transforms along the LEADING axis of a C-order array data[n][inner] (stride =
+// inner, `inner` transforms), in place: the x-pass of the slab-decomposed FFT after the
+// all-to-all (dist.py).  The plan (with its own work area) is created on first use for a given
+// (n, inner) -- that first call allocates; later calls only enqueue.
+extern "C" int pmwd_fft_c2c_lead(pmwd_ctx* ctx, void* stream, int n, long long inner, void* data,
+                                 int inverse) {
+  PMWD_REQUIRE(ctx && data, "null buffer");
+  PMWD_REQUIRE(n > 0 && inner > 0, "bad sizes");
+  cufftHandle plan;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    auto key = std::make_tuple(n, inner, 0LL);
+    auto it = ctx->xplans.find(key);
+    if (it == ctx->xplans.end()) {
+      int prev = 0;
+      PMWD_CUDA_TRY(cudaGetDevice(&prev));
+      PMWD_CUDA_TRY(cudaSetDevice(ctx->device));
+      long long nn[1] = {n};
+      long long embed[1] = {n};
+      size_t work = 0;
+      PMWD_CUFFT_TRY(cufftCreate(&plan));
+      PMWD_CUFFT_TRY(cufftMakePlanMany64(plan, 1, nn, embed, inner, 1, embed, inner, 1, CUFFT_C2C,
+                                         inner, &work));
+      PMWD_CUDA_TRY(cudaSetDevice(prev));
+      ctx->xplans[key] = plan;
+    } else {
+      plan = it->second;
+    }
+  }
+  PMWD_CUFFT_TRY(cufftSetStream(plan, as_stream(stream)));
+  PMWD_CUFFT_TRY(cufftExecC2C(plan, (cufftComplex*)data, (cufftComplex*)data,
+                              inverse ? CUFFT_INVERSE : CUFFT_FORWARD));
   return PMWD_OK;
 }

@@ -13,6 +13,8 @@
 //   pmwd_permute_rows   : dst[i] = src[perm[i]]  (gather)   or  dst[perm[i]] = src[i]  (scatter)
 #include <cub/device/device_radix_sort.cuh>
 
+#include <stdlib.h>
+
 #include "cic.cuh"
 
 namespace pmwd {
@@ -24,6 +26,8 @@ struct SortParams {
   int64_t n;
   int nx, ny, nz;   // periodic wrap shape
   int nx_ext, xoff; // slab: planes held locally and global index of the first one
+  int shift;        // xy footprint of a storage "column" is (1<<shift)^2 cells
+  int nyc;          // ceil(ny >> shift)
   float cell;
 };
 
@@ -42,7 +46,10 @@ sort_keys_kernel(SortParams P, const short* __restrict__ pmid, const float* __re
     int lx = c[0] - P.xoff;           // slab-local plane keeps the key below 2^32 on big meshes
     if (lx < 0) lx += P.nx;
     if (lx >= P.nx_ext) lx = P.nx_ext - 1;
-    keys[p] = (uint32_t)(((int64_t)lx * P.ny + c[1]) * P.nz + c[2]);
+    // columns of (1<<shift)^2 cells in (x, y), ordered by z inside: consecutive particles are
+    // as dense along the contiguous z axis as the Lagrangian lattice was, which is what makes
+    // a warp's 32 stencils share 32-byte sectors
+    keys[p] = (uint32_t)(((int64_t)(lx >> P.shift) * P.nyc + (c[1] >> P.shift)) * P.nz + c[2]);
     vals[p] = (uint32_t)p;
   }
 }
@@ -121,6 +128,12 @@ extern "C" int pmwd_cell_sort_perm(void* stream, const pmwd_cic_desc* d, const v
   P.nx_ext = d->mesh_shape[0];
   P.xoff = slab_xoff(d);
   P.cell = (float)d->cell_size;
+  {
+    const char* e = getenv("PMWD_SORT_SHIFT");
+    P.shift = e ? atoi(e) : 1;
+    if (P.shift < 0 || P.shift > 4) P.shift = 1;
+    P.nyc = (P.ny + (1 << P.shift) - 1) >> P.shift;
+  }
   PMWD_REQUIRE(cic_is_fast(d), "cell sort needs a fast-path (slab) descriptor");
   int64_t ncell = (int64_t)P.nx_ext * P.ny * P.nz;
   PMWD_REQUIRE(ncell <= ((int64_t)1 << 32) && P.n < ((int64_t)1 << 32),

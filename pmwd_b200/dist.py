@@ -32,6 +32,45 @@ from .particles import Particles
 from .scatter import make_desc
 
 
+class _Timers:
+    """Optional per-phase CUDA-event timers (enabled by bench / tools; off by default)."""
+
+    def __init__(self):
+        self.on = False
+        self.recs = []
+
+    class _Ctx:
+        def __init__(self, owner, name):
+            self.o, self.name = owner, name
+
+        def __enter__(self):
+            if self.o.on:
+                self.a = torch.cuda.Event(enable_timing=True)
+                self.b = torch.cuda.Event(enable_timing=True)
+                self.a.record()
+
+        def __exit__(self, *exc):
+            if self.o.on:
+                self.b.record()
+                self.o.recs.append((self.name, self.a, self.b))
+
+    def __call__(self, name):
+        return self._Ctx(self, name)
+
+    def read(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, a, b in self.recs:
+            t = out.setdefault(name, [0.0, 0])
+            t[0] += a.elapsed_time(b)
+            t[1] += 1
+        self.recs = []
+        return out
+
+
+TIMERS = _Timers()
+
+
 class SlabComm:
     """Geometry and collectives of one rank of the slab decomposition."""
 
@@ -69,29 +108,52 @@ class SlabComm:
         dist.all_to_all_single(r, s, group=self.group)
         return recv
 
+    def _fft_x(self, s, inverse):
+        """1-D complex FFT along dim 0 of a contiguous [Mx][my][nzc] array, in place on CUDA
+        (cuFFT strided-batch plan behind ``pmwd_fft_c2c_lead``; torch.fft on CPU for the gloo
+        host-logic tests)."""
+        if not s.is_cuda:
+            return (torch.fft.ifft(s, dim=0, norm='forward') if inverse else torch.fft.fft(s, dim=0)).contiguous()
+        s = s.contiguous()
+        ctx = _lib.Context.get(s.device)
+        with torch.cuda.device(s.device):
+            _lib.check(_lib.lib().pmwd_fft_c2c_lead(ctx.handle, _lib.stream_ptr(s.device), s.shape[0],
+                                                    s.shape[1] * s.shape[2], _lib.ptr(s), int(inverse)),
+                       'pmwd_fft_c2c_lead')
+        return s
+
     def rfftn(self, real, shape=None):
         """x-slab real ``[mx][My][Mz]`` -> y-slab spectrum ``[Mx][my][Mz/2+1]`` (unnormalised,
         = numpy rfftn of the global field, pmwd/pm_util.py:281)."""
         P = self.size
         mx, My, Mz = real.shape
         my = My // P
-        s = torch.fft.rfft2(real)                                   # local 2-D R2C over (y, z)
+        with TIMERS('fft2d_r2c'):
+            s = torch.fft.rfft2(real)                               # local 2-D R2C over (y, z)
         nzc = s.shape[-1]
-        s = s.reshape(mx, P, my, nzc).permute(1, 0, 2, 3).contiguous()   # pack per destination
-        s = self._a2a(s).reshape(P * mx, my, nzc)                   # blocks arrive in x order
-        # torch returns a strided view for transforms over a leading dim; the kernels take raw
-        # pointers, so materialise the C-order layout
-        return torch.fft.fft(s, dim=0).contiguous()                 # 1-D C2C over x
+        with TIMERS('pack'):
+            s = s.reshape(mx, P, my, nzc).permute(1, 0, 2, 3).contiguous()   # pack per destination
+        with TIMERS('all_to_all'):
+            s = self._a2a(s).reshape(P * mx, my, nzc)               # blocks arrive in x order
+        with TIMERS('fft1d_x'):
+            return self._fft_x(s, inverse=False)                    # 1-D C2C over x
 
-    def irfftn(self, spec, My, Mz):
-        """Inverse of :meth:`rfftn` WITHOUT the 1/N (callers fold it into their scale)."""
+    def irfftn(self, spec, My, Mz, out=None):
+        """Inverse of :meth:`rfftn` WITHOUT the 1/N (callers fold it into their scale).
+        ``spec`` is clobbered on CUDA (in-place x-pass)."""
         P = self.size
         Mx, my, nzc = spec.shape
         mx = Mx // P
-        s = torch.fft.ifft(spec, dim=0, norm='forward')             # unnormalised inverse over x
-        s = self._a2a(s.reshape(P, mx, my, nzc))                    # [p] = y-chunk p of my planes
-        s = s.permute(1, 0, 2, 3).reshape(mx, My, nzc)              # unpack
-        return torch.fft.irfft2(s, s=(My, Mz), norm='forward')
+        with TIMERS('fft1d_x'):
+            s = self._fft_x(spec, inverse=True)                     # unnormalised inverse over x (in place)
+        with TIMERS('all_to_all'):
+            s = self._a2a(s.reshape(P, mx, my, nzc))                # [p] = y-chunk p of my planes
+        with TIMERS('pack'):
+            s = s.permute(1, 0, 2, 3).reshape(mx, My, nzc)          # unpack
+        with TIMERS('fft2d_c2r'):
+            if out is not None:
+                return torch.fft.irfft2(s, s=(My, Mz), norm='forward', out=out)
+            return torch.fft.irfft2(s, s=(My, Mz), norm='forward')
 
     # ---- halos ---------------------------------------------------------------------------
     def _exchange(self, to_left, to_right):
@@ -186,31 +248,37 @@ class SlabForce:
         desc = self._desc(pmid, h)
         st = _lib.stream_ptr(dev)
         val = float(np.float32(conf.mesh_size / conf.ptcl_num))       # scatter.py:37-39
-        ext1.zero_()
-        _lib.check(lib.pmwd_scatter_soa(st, C.byref(desc), _lib.ptr(pmid), _lib.ptr(disp), None, val, 1,
-                                        _lib.ptr(ext1), None, None), 'pmwd_scatter_soa')
-        rho = comm.halo_reduce(ext1, h)
+        with TIMERS('scatter'):
+            ext1.zero_()
+            _lib.check(lib.pmwd_scatter_soa(st, C.byref(desc), _lib.ptr(pmid), _lib.ptr(disp), None, val, 1,
+                                            _lib.ptr(ext1), None, None), 'pmwd_scatter_soa')
+        with TIMERS('halo'):
+            rho = comm.halo_reduce(ext1, h)
         spec = comm.rfftn(rho)
         g = [torch.empty_like(spec) for _ in range(3)]
         scale = float(np.float32(1.5 * Om / conf.mesh_size))          # 1.5 Omega_m and irfftn's 1/N
         arr = (C.c_void_p * 3)(*[t.data_ptr() for t in g])
-        _lib.check(lib.pmwd_kspace_force_slab(st, _lib.shape_arr(conf.mesh_shape), comm.y0, comm.my,
-                                              float(conf.cell_size), scale, _lib.ptr(spec), arr),
-                   'pmwd_kspace_force_slab')
+        with TIMERS('kspace'):
+            _lib.check(lib.pmwd_kspace_force_slab(st, _lib.shape_arr(conf.mesh_shape), comm.y0, comm.my,
+                                                  float(conf.cell_size), scale, _lib.ptr(spec), arr),
+                       'pmwd_kspace_force_slab')
         del spec
         for i in range(3):
-            ext3[i, h:h + comm.mx] = comm.irfftn(g[i], My, Mz)
+            comm.irfftn(g[i], My, Mz, out=ext3[i, h:h + comm.mx])
             g[i] = None
-        comm.halo_fill(ext3, h)
+        with TIMERS('halo'):
+            comm.halo_fill(ext3, h)
         return desc, ext3, val
 
     def force(self, pmid, disp, Om, acc, kick_vel=None, kick_factor=0.0):
-        h = self._halo(disp)
+        with TIMERS('halo_width'):
+            h = self._halo(disp)
         desc, F, _ = self._mesh_forces(pmid, disp, Om, h)
-        _lib.check(_lib.lib().pmwd_gather3(
-            _lib.stream_ptr(disp.device), C.byref(desc), _lib.ptr(pmid), _lib.ptr(disp), _lib.ptr(F[0]),
-            _lib.ptr(F[1]), _lib.ptr(F[2]), _lib.ptr(acc), _lib.ptr(kick_vel), float(kick_factor)),
-            'pmwd_gather3')
+        with TIMERS('gather'):
+            _lib.check(_lib.lib().pmwd_gather3(
+                _lib.stream_ptr(disp.device), C.byref(desc), _lib.ptr(pmid), _lib.ptr(disp), _lib.ptr(F[0]),
+                _lib.ptr(F[1]), _lib.ptr(F[2]), _lib.ptr(acc), _lib.ptr(kick_vel), float(kick_factor)),
+                'pmwd_gather3')
 
     def force_adj(self, pmid, disp, Om, pi, acc, alpha):
         conf, comm = self.conf, self.comm
@@ -237,7 +305,7 @@ class SlabForce:
                    'pmwd_kspace_force_adj_slab')
         del S
         rc = torch.empty_like(F[0])
-        rc[h:h + comm.mx] = comm.irfftn(out, My, Mz)
+        comm.irfftn(out, My, Mz, out=rc[h:h + comm.mx])
         comm.halo_fill(rc, h)
         _lib.check(lib.pmwd_force_adj_gather(st, C.byref(desc), _lib.ptr(pmid), _lib.ptr(disp), _lib.ptr(F[0]),
                                              _lib.ptr(F[1]), _lib.ptr(F[2]), _lib.ptr(rc), _lib.ptr(pi), val,
@@ -376,7 +444,8 @@ def step_slab(a_prev, a_next, store, cosmo, conf, force):
     k1 = _f32(kick_factor(a_prev, a_prev, a_mid, cosmo, conf))
     d = _f32(drift_factor(a_mid, a_prev, a_next, cosmo, conf))
     k2 = _f32(kick_factor(a_next, a_mid, a_next, cosmo, conf))
-    _kick_drift(store.ptcl, k1, d, True, True)
+    with TIMERS('kick_drift'):
+        _kick_drift(store.ptcl, k1, d, True, True)
     a = store.arrays
     force.force(a['pmid'], a['disp'], Om, a['acc'], a['vel'], k2)
 
@@ -433,6 +502,7 @@ def run_bench(args):
             step_slab(a[i], a[i + 1], store, cosmo, conf, force); store.maybe_reorder(sync_max=comm.allreduce_max); i += 1
         torch.cuda.synchronize(); dist.barrier()
         sampler = B.ClockSampler(local); sampler.start()
+        TIMERS.on = True
         l0 = _lib.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
@@ -448,6 +518,8 @@ def run_bench(args):
         ms = float(ms)
         launches = _lib.launch_count() - l0
         clocks = sampler.stop()
+        phases = {k: round(v[0] / K, 3) for k, v in TIMERS.read().items()}
+        TIMERS.on = False
     assert torch.isfinite(store.arrays['disp']).all()
     Np = conf.ptcl_num
     if rank == 0:
@@ -459,7 +531,7 @@ def run_bench(args):
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic', 'config': B.workload_config(args, world),
             'steps_per_sec': K / (ms * 1e-3), 'clocks': clocks, 'gpu_launches': launches,
-            'halo_planes': force.h_alloc,
+            'halo_planes': force.h_alloc, 'phase_ms_per_step_rank0': phases,
             'roofline': {'bound': 'hbm', 'unit': 'GB/s', 'peak': peak, 'peak_source': peak_src,
                          'kernel': 'whole step (per GPU)', 'traffic': None,
                          'achieved': (132 * Np + 68 * Nm) / world / (ms / K) / 1e6,
