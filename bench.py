@@ -265,6 +265,40 @@ def run_ours(args):
                 'step_alg_bytes': 132 * Np + 68 * Nm,
                 'step_frac': round((132 * Np + 68 * Nm) / (ms / K) / 1e6 / peak, 4)}
 
+    # ---- reverse-time adjoint (the "fwd+adjoint" half of the metric): the whole nbody_adj
+    # loop from the evolved state (63 adjoint steps + init), CUDA events
+    adjoint = None
+    if not args.no_adjoint:
+        with torch.no_grad():
+            disp, vel = store.lagrangian('disp', 'vel')
+            final = pm.Particles(conf, ic.pmid, disp, vel=vel)
+            g = torch.Generator(device=dev).manual_seed(1)
+            cot = pm.Particles(conf, ic.pmid, torch.randn(disp.shape, device=dev, generator=g),
+                               vel=torch.randn(disp.shape, device=dev, generator=g))
+            del store
+            torch.cuda.empty_cache()
+            _lib.profile_enable(True); _lib.profile_read()
+            torch.cuda.synchronize()
+            e0.record()
+            _, pc, cc = pm.nbody_adj(final, cot, None, cosmo, conf)
+            e1.record()
+            torch.cuda.synchronize()
+            ams = e0.elapsed_time(e1)
+            astages = _lib.profile_read()
+            _lib.profile_enable(False)
+        assert torch.isfinite(pc.disp).all()
+        nadj = nsched
+        adjoint = {'ms_per_step': ams / nadj, 'steps': nadj,
+                   'particle_steps_per_sec': Np * nadj / (ams * 1e-3),
+                   'adjoint_over_forward': (ams / nadj) / (ms / K),
+                   'gradient_particle_steps_per_sec': Np / ((ams / nadj + ms / K) * 1e-3),
+                   'alg_bytes_per_step': 312 * Np + 156 * Nm,
+                   'step_frac': round((312 * Np + 156 * Nm) / (ams / nadj) / 1e6 / peak, 4),
+                   'stage_ms_per_step': {k: round(v[0] / nadj, 3) for k, v in astages.items() if v[1]}}
+        del final, cot, pc
+        store = None
+        torch.cuda.empty_cache()
+
     # ---- e2e: public API with host buffers, copies inside the timed region
     ke = max(1, min(K, args.e2e_steps))
     host = {k: torch.empty(getattr(ic, k).shape, dtype=getattr(ic, k).dtype).pin_memory()
@@ -273,7 +307,7 @@ def run_ours(args):
     p0, _ = pm.nbody_init(a[0], ic, None, cosmo, conf)
     for k in host:
         host[k].copy_(getattr(p0, k))
-    del p0, store
+    del p0
     torch.cuda.empty_cache()
     h2d = sum(t.numel() * t.element_size() for t in host.values())
     d2h = sum(host[k].numel() * host[k].element_size() for k in ('disp', 'vel', 'acc'))
@@ -315,7 +349,7 @@ def run_ours(args):
         'config': workload_config(args, 1),
         'steps_per_sec': K / (ms * 1e-3),
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'storage_reorders': reorders,
-        'roofline': roofline, 'kernels': kernels, 'cpu_baseline': cpu,
+        'roofline': roofline, 'kernels': kernels, 'adjoint': adjoint, 'cpu_baseline': cpu,
         'context': {'h100_pcie_jax_derived_updates_per_s': 6.5e8,
                     'note': 'BASELINE.md derived figure for the same geometry on other hardware; not a published '
                             'number for this metric, hence vs_baseline = null'},
@@ -336,6 +370,7 @@ def main():
     ap.add_argument('--reorder-min-disp', type=float, default=1.0)
     ap.add_argument('--cpu-n', type=int, default=96)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-adjoint', action='store_true')
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -174,6 +174,18 @@ int pmwd_kspace_force_adj_slab(void* stream, const int32_t* shape, int y0, int n
                                double spacing, float scale, const void* const* v_c64,
                                void* out_c64);
 
+/* Fused x-pass (csrc/xpass.cu): on data[nx][ny_local][nz/2+1] already transformed over (y, z),
+ * FFT along x in shared memory + laplace/neg_grad algebra + inverse FFT along x in ONE pass.
+ * forward: rho2d -> g2d[0..2] (the three force spectra, still to be inverse-transformed over
+ * (y, z));  adjoint: v2d[0..2] -> out2d.  `shape` is the GLOBAL mesh shape, nx in
+ * {64..2048} powers of two (pmwd_xpass_supported).  Replaces gravity.py:56-64's
+ * rfftn-x / laplace / neg_grad / irfftn-x chain. */
+int pmwd_xpass_supported(int nx);
+int pmwd_xpass_force(void* stream, const int32_t* shape, int y0, int ny_local, double spacing,
+                     float scale, const void* rho2d_c64, void* const* g2d_c64);
+int pmwd_xpass_force_adj(void* stream, const int32_t* shape, int y0, int ny_local, double spacing,
+                         float scale, const void* const* v2d_c64, void* out2d_c64);
+
 /* ---- fused force: gravity() (pmwd/gravity.py:47-72) -------------------------------- */
 /* Workspace (device bytes) needed by pmwd_force / pmwd_force_adj for this geometry. */
 size_t pmwd_force_workspace_bytes(const pmwd_cic_desc* d, int adjoint, int mode);

@@ -72,6 +72,9 @@ _SIGNATURES = {
     'pmwd_force_adj_gather': (_i, [_vp, _descp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp]),
     'pmwd_kspace_force_slab': (_i, [_vp, _i32p, _i, _i, _d, _f, _vp, C.POINTER(_vp)]),
     'pmwd_kspace_force_adj_slab': (_i, [_vp, _i32p, _i, _i, _d, _f, C.POINTER(_vp), _vp]),
+    'pmwd_xpass_supported': (_i, [_i]),
+    'pmwd_xpass_force': (_i, [_vp, _i32p, _i, _i, _d, _f, _vp, C.POINTER(_vp)]),
+    'pmwd_xpass_force_adj': (_i, [_vp, _i32p, _i, _i, _d, _f, C.POINTER(_vp), _vp]),
     'pmwd_force_workspace_bytes': (_sz, [_descp, _i, _i]),
     'pmwd_force': (_i, [_vp, _vp, _descp, _vp, _vp, _d, _vp, _vp, _f, _i, _vp, _sz]),
     'pmwd_force_adj': (_i, [_vp, _vp, _descp, _vp, _vp, _d, _vp, _vp, _vp, _i, _vp, _sz]),

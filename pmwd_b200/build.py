@@ -17,7 +17,7 @@ BUILD = os.path.join(HERE, 'csrc', 'build')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 # --fmad=false: the kernels promise IEEE mul-then-add in the reference's operation order
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '--fmad=false',
-         '-std=c++17', '-Xcompiler', '-fPIC', '-Xcompiler', '-O2']
+         '-std=c++17', '-Xcompiler', '-fPIC', '-Xcompiler', '-O2'] + os.environ.get('PMWD_NVCC_EXTRA', '').split()
 
 
 def _sources():

@@ -82,6 +82,37 @@ int fft_c2r(pmwd_ctx* ctx, cudaStream_t st, int rank, const int32_t* shape, void
   return PMWD_OK;
 }
 
+static int find_plans2d(pmwd_ctx* ctx, const int32_t* shape, PlanPair* out) {
+  PMWD_REQUIRE(ctx != nullptr && shape, "null context/shape");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  auto it = ctx->plans.find(std::make_tuple(23, shape[0], shape[1], shape[2]));
+  if (it == ctx->plans.end()) {
+    set_error("no 2-D cuFFT plans for this shape: call pmwd_ctx_reserve first");
+    return PMWD_ESTATE;
+  }
+  *out = it->second;
+  return PMWD_OK;
+}
+
+// in[nx][ny][nz] real -> out[nx][ny][nz/2+1]: R2C over (y, z) for every x plane
+int fft2d_r2c(pmwd_ctx* ctx, cudaStream_t st, const int32_t* shape, const float* in, void* out) {
+  PlanPair pp;
+  int rc = find_plans2d(ctx, shape, &pp);
+  if (rc) return rc;
+  PMWD_CUFFT_TRY(cufftSetStream(pp.r2c, st));
+  PMWD_CUFFT_TRY(cufftExecR2C(pp.r2c, const_cast<float*>(in), (cufftComplex*)out));
+  return PMWD_OK;
+}
+
+int fft2d_c2r(pmwd_ctx* ctx, cudaStream_t st, const int32_t* shape, void* in, float* out) {
+  PlanPair pp;
+  int rc = find_plans2d(ctx, shape, &pp);
+  if (rc) return rc;
+  PMWD_CUFFT_TRY(cufftSetStream(pp.c2r, st));
+  PMWD_CUFFT_TRY(cufftExecC2R(pp.c2r, (cufftComplex*)in, out));
+  return PMWD_OK;
+}
+
 }  // namespace pmwd
 
 using namespace pmwd;
@@ -151,6 +182,39 @@ extern "C" int pmwd_ctx_reserve(pmwd_ctx* ctx, int rank, const int32_t* shape) {
     PMWD_CUFFT_TRY(cufftSetWorkArea(pp.c2r, ctx->work));
   }
   ctx->plans[key] = pp;
+  if (rank == 3) {
+    // (y, z) 2-D transforms batched over the x planes: the companions of the fused x-pass
+    // (xpass.cu).  Key: rank tag 23.
+    PlanPair p2;
+    long long n2[2] = {shape[1], shape[2]};
+    long long nzc = shape[2] / 2 + 1;
+    size_t v1 = 0, v2 = 0;
+    PMWD_CUFFT_TRY(cufftCreate(&p2.r2c));
+    PMWD_CUFFT_TRY(cufftSetAutoAllocation(p2.r2c, 0));
+    PMWD_CUFFT_TRY(cufftMakePlanMany64(p2.r2c, 2, n2, nullptr, 1, (long long)shape[1] * shape[2], nullptr, 1,
+                                       (long long)shape[1] * nzc, CUFFT_R2C, shape[0], &v1));
+    PMWD_CUFFT_TRY(cufftCreate(&p2.c2r));
+    PMWD_CUFFT_TRY(cufftSetAutoAllocation(p2.c2r, 0));
+    PMWD_CUFFT_TRY(cufftMakePlanMany64(p2.c2r, 2, n2, nullptr, 1, (long long)shape[1] * nzc, nullptr, 1,
+                                       (long long)shape[1] * shape[2], CUFFT_C2R, shape[0], &v2));
+    p2.work = v1 > v2 ? v1 : v2;
+    if (p2.work > ctx->work_bytes) {
+      PMWD_CUDA_TRY(cudaDeviceSynchronize());
+      if (ctx->work) PMWD_CUDA_TRY(cudaFree(ctx->work));
+      ctx->work = nullptr;
+      PMWD_CUDA_TRY(cudaMalloc(&ctx->work, p2.work));
+      ctx->work_bytes = p2.work;
+      for (auto& kv : ctx->plans) {
+        PMWD_CUFFT_TRY(cufftSetWorkArea(kv.second.r2c, ctx->work));
+        PMWD_CUFFT_TRY(cufftSetWorkArea(kv.second.c2r, ctx->work));
+      }
+    }
+    if (ctx->work) {
+      PMWD_CUFFT_TRY(cufftSetWorkArea(p2.r2c, ctx->work));
+      PMWD_CUFFT_TRY(cufftSetWorkArea(p2.c2r, ctx->work));
+    }
+    ctx->plans[std::make_tuple(23, shape[0], shape[1], shape[2])] = p2;
+  }
   PMWD_CUDA_TRY(cudaSetDevice(prev));
   return PMWD_OK;
 }

@@ -11,6 +11,8 @@
 // Adjoint force additionally:
 //   3-channel scatter of pi -> 3x R2C -> fused k-space transpose (3 reads, 1 write) -> C2R ->
 //   one weight-gradient gather over (F_0, F_1, F_2, rho_cot).
+#include <stdlib.h>
+
 #include "cic.cuh"
 
 struct pmwd_ctx;
@@ -40,6 +42,24 @@ int scatter_det(cudaStream_t st, const pmwd_cic_desc* d, const void* pmid, const
 // fft.cu
 int fft_r2c(pmwd_ctx* ctx, cudaStream_t st, int rank, const int32_t* shape, const float* in, void* out);
 int fft_c2r(pmwd_ctx* ctx, cudaStream_t st, int rank, const int32_t* shape, void* in, float* out);
+int fft2d_r2c(pmwd_ctx* ctx, cudaStream_t st, const int32_t* shape, const float* in, void* out);
+int fft2d_c2r(pmwd_ctx* ctx, cudaStream_t st, const int32_t* shape, void* in, float* out);
+// xpass.cu
+bool xpass_supported(int nx);
+int xpass_run(cudaStream_t st, const int32_t* shape, int y0, int ny_l, double spacing, float scale,
+              const void* const* in, void* const* out, bool adjoint);
+
+// The fused x-pass pipeline (2-D cuFFT over (y,z) + xpass.cu) replaces {3-D cuFFT, k-space
+// kernel, 3-D cuFFT} whenever the mesh's x extent is a supported power of two.
+// PMWD_XPASS=0 selects the plain cuFFT-3D pipeline (kept for A/B measurements and odd sizes).
+static bool use_xpass(const int32_t* shape) {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("PMWD_XPASS");
+    env = (e && e[0] == '0') ? 0 : 1;
+  }
+  return env == 1 && xpass_supported(shape[0]);
+}
 
 static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
@@ -101,22 +121,25 @@ static int force_forward(pmwd_ctx* ctx, cudaStream_t st, const pmwd_cic_desc* d,
       rc = scatter_fast(st, d, pmid, disp, nullptr, val, 1, rho, nullptr, nullptr);
   }
   if (rc) return rc;
+  const bool xp = use_xpass(shape);
   {
     StageTimer t(ST_FFT_R2C, st);
-    rc = fft_r2c(ctx, st, 3, shape, rho, ws + L.rho_k);
+    rc = xp ? fft2d_r2c(ctx, st, shape, rho, ws + L.rho_k) : fft_r2c(ctx, st, 3, shape, rho, ws + L.rho_k);
   }
   if (rc) return rc;
   void* g[3] = {ws + L.g[0], ws + L.g[1], ws + L.g[2]};
   const float scale = (float)(1.5 * Omega_m / (double)nm);
   {
     StageTimer t(ST_KSPACE, st);
-    rc = pmwd_kspace_force(st, 3, shape, d->cell_size, scale, ws + L.rho_k, g);
+    const void* in[3] = {ws + L.rho_k, nullptr, nullptr};
+    rc = xp ? xpass_run(st, shape, 0, shape[1], d->cell_size, scale, in, g, false)
+            : pmwd_kspace_force(st, 3, shape, d->cell_size, scale, ws + L.rho_k, g);
   }
   if (rc) return rc;
   float* F[3] = {(float*)(ws + L.rho_f0), (float*)(ws + L.f1), (float*)(ws + L.f2)};
   for (int a = 0; a < 3; ++a) {
     StageTimer t(ST_FFT_C2R, st);
-    rc = fft_c2r(ctx, st, 3, shape, g[a], F[a]);
+    rc = xp ? fft2d_c2r(ctx, st, shape, g[a], F[a]) : fft_c2r(ctx, st, 3, shape, g[a], F[a]);
     if (rc) return rc;
   }
   return PMWD_OK;
@@ -273,22 +296,26 @@ extern "C" int pmwd_force_adj(pmwd_ctx* ctx, void* stream, const pmwd_cic_desc* 
   }
   if (rc) return rc;
   const void* S[3] = {ws + L.s[0], ws + L.s[1], ws + L.s[2]};
+  const bool xp = use_xpass(shape);
   for (int a = 0; a < 3; ++a) {
     StageTimer t(ST_FFT_R2C, st);
-    rc = fft_r2c(ctx, st, 3, shape, V[a], ws + L.s[a]);
+    rc = xp ? fft2d_r2c(ctx, st, shape, V[a], ws + L.s[a]) : fft_r2c(ctx, st, 3, shape, V[a], ws + L.s[a]);
     if (rc) return rc;
   }
   // rho_cot_k = (1.5 Omega_m / N_m) * sum_i (+i k_i)(-V_i,k / k^2)   [A_i^T = -A_i]
   const float scale = (float)(1.5 * Omega_m / (double)nm);
   {
     StageTimer t(ST_KSPACE_ADJ, st);
-    rc = pmwd_kspace_force_adj(st, 3, shape, d->cell_size, scale, S, ws + L.rho_k);
+    void* out[3] = {ws + L.rho_k, nullptr, nullptr};
+    rc = xp ? xpass_run(st, shape, 0, shape[1], d->cell_size, scale, S, out, true)
+            : pmwd_kspace_force_adj(st, 3, shape, d->cell_size, scale, S, ws + L.rho_k);
   }
   if (rc) return rc;
   float* rho_cot = (float*)(ws + L.g[0]);
   {
     StageTimer t(ST_FFT_C2R, st);
-    rc = fft_c2r(ctx, st, 3, shape, ws + L.rho_k, rho_cot);
+    rc = xp ? fft2d_c2r(ctx, st, shape, ws + L.rho_k, rho_cot)
+            : fft_c2r(ctx, st, 3, shape, ws + L.rho_k, rho_cot);
   }
   if (rc) return rc;
   StageTimer t(ST_GATHER_ADJ, st);

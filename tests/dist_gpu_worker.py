@@ -22,7 +22,7 @@ def main():
     rank, world = dist.get_rank(), dist.get_world_size()
     dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0')))
     n = 32
-    shape = (n * 2, n, n) if world > 1 else (n, n, n)      # non-cubic box: x doubled
+    shape = (n * world, n, n)        # non-cubic box, 2n mesh planes per rank (room for the halos)
     conf = pm.Configuration(1., shape, mesh_shape=2, a_nbody_maxstep=0.1, device=dev, reorder_every=3,
                             reorder_min_disp=0.5)
     comm = pd.SlabComm(conf)

@@ -25,5 +25,6 @@ def test_slab_matches_single_gpu():
            '--master-addr', '127.0.0.1', '--master-port', str(_free_port()),
            os.path.join(ROOT, 'tests', 'dist_gpu_worker.py')]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=850)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    errs = [l for l in (r.stdout + r.stderr).splitlines() if 'rank' in l and ('Error' in l or 'assert' in l)]
+    assert r.returncode == 0, '\n'.join(errs[:20]) + r.stderr[-1500:]
     assert r.stdout.count(' ok: ') == 2 * world

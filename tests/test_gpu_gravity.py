@@ -479,3 +479,55 @@ def test_full_gradient_pipeline():
     got = [theta[nme].grad.item() for nme in names]
     assert _cos(got, fd) >= 0.9999, (got, fd)
     np.testing.assert_allclose(got, fd, rtol=2e-2)
+
+
+@pytest.mark.parametrize('shape', [(64, 8, 10), (128, 6, 9), (256, 4, 6), (512, 4, 4), (1024, 2, 4), (2048, 2, 4)])
+def test_fused_xpass_vs_cufft3d(shape):
+    """csrc/xpass.cu (shared-memory FFT along x fused with the k-space algebra) against the
+    plain pipeline cuFFT-3D -> pmwd_kspace_force(_adj) -> cuFFT-3D, forward and adjoint, incl. the
+    y-slab form used after the distributed all-to-all.  Tolerance: 2e-6 of the field's rms."""
+    import ctypes as C
+    from pmwd_b200 import _lib
+    lib = _lib.lib()
+    nx, ny, nz = shape
+    cell, scale = 0.7, 0.37
+    g = torch.Generator(device='cuda').manual_seed(0)
+    rho = torch.randn(shape, device='cuda', generator=g)
+    st = _lib.stream_ptr()
+    shp = _lib.shape_arr(shape)
+    # reference: full 3-D transforms + the standalone fused k-space kernel
+    spec = torch.fft.rfftn(rho).contiguous()
+    ref_g = [torch.empty_like(spec) for _ in range(3)]
+    arr = (C.c_void_p * 3)(*[t.data_ptr() for t in ref_g])
+    _lib.check(lib.pmwd_kspace_force(st, 3, shp, cell, scale, _lib.ptr(spec), arr), 'ks')
+    ref_F = [torch.fft.irfftn(t, s=shape, norm='forward') for t in ref_g]
+    # fused: 2-D transforms over (y, z) + x-pass
+    s2 = torch.fft.rfft2(rho).contiguous()
+    out = [torch.empty_like(s2) for _ in range(3)]
+    arr = (C.c_void_p * 3)(*[t.data_ptr() for t in out])
+    _lib.check(lib.pmwd_xpass_force(st, shp, 0, ny, cell, scale, _lib.ptr(s2), arr), 'xpass')
+    for a in range(3):
+        F = torch.fft.irfft2(out[a], s=(ny, nz), norm='forward')
+        err = _rms((F - ref_F[a]).cpu().numpy())
+        assert err <= 2e-6 * _rms(ref_F[a].cpu().numpy()) + 1e-12, (a, err, _rms(ref_F[a].cpu().numpy()))
+    # y-slab form: rows y0 .. y0+nyl-1 only
+    y0, nyl = ny // 2, ny - ny // 2
+    s2s = s2[:, y0:y0 + nyl].contiguous()
+    outs = [torch.empty_like(s2s) for _ in range(3)]
+    arr = (C.c_void_p * 3)(*[t.data_ptr() for t in outs])
+    _lib.check(lib.pmwd_xpass_force(st, shp, y0, nyl, cell, scale, _lib.ptr(s2s), arr), 'xpass slab')
+    for a in range(3):
+        assert torch.equal(outs[a], out[a][:, y0:y0 + nyl])
+    # adjoint: three inputs -> one output
+    V = [torch.randn(shape, device='cuda', generator=g) for _ in range(3)]
+    Vk = [torch.fft.rfftn(v).contiguous() for v in V]
+    ref_o = torch.empty_like(spec)
+    arr = (C.c_void_p * 3)(*[t.data_ptr() for t in Vk])
+    _lib.check(lib.pmwd_kspace_force_adj(st, 3, shp, cell, scale, arr, _lib.ptr(ref_o)), 'ks adj')
+    ref_r = torch.fft.irfftn(ref_o, s=shape, norm='forward')
+    V2 = [torch.fft.rfft2(v).contiguous() for v in V]
+    o2 = torch.empty_like(s2)
+    arr = (C.c_void_p * 3)(*[t.data_ptr() for t in V2])
+    _lib.check(lib.pmwd_xpass_force_adj(st, shp, 0, ny, cell, scale, arr, _lib.ptr(o2)), 'xpass adj')
+    r = torch.fft.irfft2(o2, s=(ny, nz), norm='forward')
+    assert _rms((r - ref_r).cpu().numpy()) <= 2e-6 * _rms(ref_r.cpu().numpy())
