@@ -158,13 +158,14 @@ def workload_config(args, ngpu):
 
 
 def rank_grid(n, ngpu):
-    """Weak scaling: per-GPU work fixed; the global box grows along x first, then y, then z."""
+    """Weak scaling: per-GPU work fixed; the global box doubles along z, then y, then x (so
+    that 8 GPUs run the 1024^3-particle / 2048^3-mesh configuration of BASELINE.json)."""
     shape = [n, n, n]
-    g, ax = ngpu, 0
+    g, ax = ngpu, 2
     while g > 1:
         shape[ax % 3] *= 2
         g //= 2
-        ax += 1
+        ax -= 1
     return tuple(shape)
 
 

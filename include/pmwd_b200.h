@@ -104,6 +104,11 @@ int pmwd_fft_c2r(pmwd_ctx* ctx, void* stream, int rank, const int32_t* shape,
 int pmwd_fft_c2c_lead(pmwd_ctx* ctx, void* stream, int n, long long inner, void* data_c64,
                       int inverse);
 
+/* (y, z) 2-D transforms batched over the leading axis of in[n0][n1][n2] (real) <->
+ * out[n0][n1][n2/2+1]; plans come from pmwd_ctx_reserve(ctx, 3, shape).  Unnormalised. */
+int pmwd_fft2d_r2c(pmwd_ctx* ctx, void* stream, const int32_t* shape, const float* in, void* out_c64);
+int pmwd_fft2d_c2r(pmwd_ctx* ctx, void* stream, const int32_t* shape, void* in_c64, float* out);
+
 /* ---- CIC scatter / gather and their VJPs ------------------------------------------ */
 /* _scatter (pmwd/scatter.py:33-83): mesh[ind] += val * frac.  `val` is either a device
  * array float[N][nchan] or NULL, in which case `val_scalar` is broadcast (0-D val).

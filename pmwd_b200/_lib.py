@@ -56,6 +56,8 @@ _SIGNATURES = {
     'pmwd_ctx_reserve': (_i, [_vp, _i, _i32p]),
     'pmwd_fft_r2c': (_i, [_vp, _vp, _i, _i32p, _vp, _vp]),
     'pmwd_fft_c2r': (_i, [_vp, _vp, _i, _i32p, _vp, _vp, _f]),
+    'pmwd_fft2d_r2c': (_i, [_vp, _vp, _i32p, _vp, _vp]),
+    'pmwd_fft2d_c2r': (_i, [_vp, _vp, _i32p, _vp, _vp]),
     'pmwd_fft_c2c_lead': (_i, [_vp, _vp, _i, C.c_longlong, _vp, _i]),
     'pmwd_scatter_scratch_bytes': (_sz, [_descp, _i]),
     'pmwd_scatter': (_i, [_vp, _descp, _vp, _vp, _vp, _f, _vp, _i, _vp, _sz]),

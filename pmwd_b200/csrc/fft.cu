@@ -274,3 +274,18 @@ extern "C" int pmwd_fft_c2c_lead(pmwd_ctx* ctx, void* stream, int n, long long i
                               inverse ? CUFFT_INVERSE : CUFFT_FORWARD));
   return PMWD_OK;
 }
+
+// (y, z) 2-D transforms batched over the leading axis of a [n0][n1][n2] real array (plans are
+// created by pmwd_ctx_reserve(ctx, 3, shape)): the local part of the slab-decomposed FFT and
+// the companions of the fused x-pass.  Unnormalised; C2R clobbers its input.
+extern "C" int pmwd_fft2d_r2c(pmwd_ctx* ctx, void* stream, const int32_t* shape, const float* in,
+                              void* out) {
+  PMWD_REQUIRE(in && out, "null buffer");
+  return fft2d_r2c(ctx, as_stream(stream), shape, in, out);
+}
+
+extern "C" int pmwd_fft2d_c2r(pmwd_ctx* ctx, void* stream, const int32_t* shape, void* in,
+                              float* out) {
+  PMWD_REQUIRE(in && out, "null buffer");
+  return fft2d_c2r(ctx, as_stream(stream), shape, in, out);
+}

@@ -29,13 +29,17 @@ template <int NX>
 struct XCfg {
   // T kz-columns per tile (T*8-byte row segments).  T=8 runs 1024 threads, one CTA per SM;
   // T=4 runs 512 threads, two CTAs per SM (slower: 32-byte rows waste L2/DRAM requests).
-  static constexpr int T = NX >= 2048 ? 4 : PMWD_XT;
-  static constexpr int BIG = (NX >= 2048 || PMWD_XT == 8) ? 1024 : 512;
+  static constexpr int T = PMWD_XT;
+  static constexpr int BIG = PMWD_XT == 8 ? 1024 : 512;
   static constexpr int CTAS = BIG == 1024 ? 1 : 2;
   static constexpr int THREADS = NX * T / 2 >= BIG ? BIG : NX * T / 2;
   static constexpr int EPT = NX * T / THREADS;
   static constexpr int XSTEP = THREADS / T;
   static constexpr int LOG2 = NX == 64 ? 6 : NX == 128 ? 7 : NX == 256 ? 8 : NX == 512 ? 9 : NX == 1024 ? 10 : 11;
+  // q = -i kx pot is parked in registers across the P transform, except for the longest
+  // columns where that would spill: there it is parked in the G_x output array itself
+  // (written, then re-read -- an L2 hit -- transformed and overwritten)
+  static constexpr bool QGLOBAL = false;   // (measured: no gain for 2048; the stages themselves spill)
   static constexpr int N4 = LOG2 / 2;
   static constexpr bool HAS2 = (LOG2 & 1) != 0;
 };
@@ -180,7 +184,8 @@ __global__ void __launch_bounds__(XCfg<NX>::THREADS, XCfg<NX>::CTAS) xfused_forc
     fft_tile<NX, false>(buf, tw);
 
     // ---- pot = -(scale S)/k^2 in place; q = -i kx pot kept in registers
-    float2 q[EPT];
+    constexpr bool QG = XCfg<NX>::QGLOBAL;
+    float2 q[QG ? 1 : EPT];
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
       const int x = x0 + XSTEP * e;
@@ -191,8 +196,13 @@ __global__ void __launch_bounds__(XCfg<NX>::THREADS, XCfg<NX>::CTAS) xfused_forc
       if (ksq != 0.f)
         pot = make_float2(__fdiv_rn(-__fmul_rn(P.scale, s.x), ksq), __fdiv_rn(-__fmul_rn(P.scale, s.y), ksq));
       buf[x * XT + c] = pot;
-      q[e] = xnyq(k0, P.nyq, P.eps) ? make_float2(0.f, 0.f)
-                                    : make_float2(__fmul_rn(k0, pot.y), -__fmul_rn(k0, pot.x));
+      const float2 qq = xnyq(k0, P.nyq, P.eps) ? make_float2(0.f, 0.f)
+                                               : make_float2(__fmul_rn(k0, pot.y), -__fmul_rn(k0, pot.x));
+      if (QG) {
+        if (live) P.out[0][(int64_t)x * plane + col] = qq;
+      } else {
+        q[e] = qq;
+      }
     }
     __syncthreads();
 
@@ -213,7 +223,11 @@ __global__ void __launch_bounds__(XCfg<NX>::THREADS, XCfg<NX>::CTAS) xfused_forc
 
     // ---- G_x = IFFT_x(q)
 #pragma unroll
-    for (int e = 0; e < EPT; ++e) buf[(x0 + XSTEP * e) * XT + c] = q[e];
+    for (int e = 0; e < EPT; ++e) {
+      const int x = x0 + XSTEP * e;
+      if (QG) buf[x * XT + c] = live ? P.out[0][(int64_t)x * plane + col] : make_float2(0.f, 0.f);
+      else buf[x * XT + c] = q[e];
+    }
     __syncthreads();
     fft_tile<NX, true>(buf, tw);
 #pragma unroll

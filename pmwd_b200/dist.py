@@ -122,38 +122,99 @@ class SlabComm:
                        'pmwd_fft_c2c_lead')
         return s
 
-    def rfftn(self, real, shape=None):
-        """x-slab real ``[mx][My][Mz]`` -> y-slab spectrum ``[Mx][my][Mz/2+1]`` (unnormalised,
-        = numpy rfftn of the global field, pmwd/pm_util.py:281)."""
+    def _rfft2(self, real):
+        """Local 2-D R2C over (y, z) of a contiguous [mx][My][Mz] slab (cuFFT plans of the C
+        library on CUDA; torch.fft on CPU for the gloo tests)."""
+        if not real.is_cuda:
+            return torch.fft.rfft2(real)
+        real = real.contiguous()
+        shape = tuple(real.shape)
+        ctx = _lib.Context.get(real.device).reserve(shape)
+        out = torch.empty(shape[:2] + (shape[2] // 2 + 1,), dtype=torch.complex64, device=real.device)
+        with torch.cuda.device(real.device):
+            _lib.check(_lib.lib().pmwd_fft2d_r2c(ctx.handle, _lib.stream_ptr(real.device), _lib.shape_arr(shape),
+                                                 _lib.ptr(real), _lib.ptr(out)), 'pmwd_fft2d_r2c')
+        return out
+
+    def _irfft2(self, s, My, Mz, out=None):
+        """Local 2-D C2R over (y, z), unnormalised; ``s`` (contiguous) is clobbered on CUDA."""
+        if not s.is_cuda:
+            r = torch.fft.irfft2(s, s=(My, Mz), norm='forward')
+            if out is not None:
+                out.copy_(r)
+                return out
+            return r
+        shape = (s.shape[0], My, Mz)
+        ctx = _lib.Context.get(s.device).reserve(shape)
+        if out is None:
+            out = torch.empty(shape, dtype=torch.float32, device=s.device)
+        assert out.is_contiguous() and s.is_contiguous()
+        with torch.cuda.device(s.device):
+            _lib.check(_lib.lib().pmwd_fft2d_c2r(ctx.handle, _lib.stream_ptr(s.device), _lib.shape_arr(shape),
+                                                 _lib.ptr(s), _lib.ptr(out)), 'pmwd_fft2d_c2r')
+        return out
+
+    def rfft2_a2a(self, real):
+        """x-slab real ``[mx][My][Mz]`` -> ``[Mx][my][Mz/2+1]`` transformed over (y, z) only and
+        transposed to y-slabs (the input layout of the fused x-pass, csrc/xpass.cu)."""
         P = self.size
         mx, My, Mz = real.shape
         my = My // P
         with TIMERS('fft2d_r2c'):
-            s = torch.fft.rfft2(real)                               # local 2-D R2C over (y, z)
+            s = self._rfft2(real)                                   # local 2-D R2C over (y, z)
         nzc = s.shape[-1]
         with TIMERS('pack'):
             s = s.reshape(mx, P, my, nzc).permute(1, 0, 2, 3).contiguous()   # pack per destination
         with TIMERS('all_to_all'):
-            s = self._a2a(s).reshape(P * mx, my, nzc)               # blocks arrive in x order
+            return self._a2a(s).reshape(P * mx, my, nzc)            # blocks arrive in x order
+
+    def a2a_irfft2(self, s, My, Mz, out=None):
+        """Inverse of :meth:`rfft2_a2a` without any 1/N: ``[Mx][my][nzc]`` -> real ``[mx][My][Mz]``."""
+        P = self.size
+        Mx, my, nzc = s.shape
+        mx = Mx // P
+        with TIMERS('all_to_all'):
+            s = self._a2a(s.reshape(P, mx, my, nzc))                # [p] = y-chunk p of my planes
+        with TIMERS('pack'):
+            s = s.permute(1, 0, 2, 3).reshape(mx, My, nzc)          # unpack (copies)
+        with TIMERS('fft2d_c2r'):
+            return self._irfft2(s, My, Mz, out=out)
+
+    def a2a_start(self, s):
+        """Start the transpose of :meth:`a2a_irfft2` asynchronously (NCCL stream); returns a
+        token for :meth:`a2a_finish_irfft2`.  Lets the 2-D C2R of one force component overlap
+        the all-to-all of the next."""
+        P = self.size
+        Mx, my, nzc = s.shape
+        send = s.reshape(P, Mx // P, my, nzc).contiguous()
+        recv = torch.empty_like(send)
+        work = dist.all_to_all_single(torch.view_as_real(recv), torch.view_as_real(send),
+                                      group=self.group, async_op=True)
+        return send, recv, work
+
+    def a2a_finish_irfft2(self, token, My, Mz, out=None):
+        send, recv, work = token
+        with TIMERS('all_to_all_wait'):
+            work.wait()
+        P, mx, my, nzc = recv.shape
+        with TIMERS('pack'):
+            s = recv.permute(1, 0, 2, 3).reshape(mx, My, nzc)       # unpack (copies)
+        with TIMERS('fft2d_c2r'):
+            return self._irfft2(s, My, Mz, out=out)
+
+    def rfftn(self, real, shape=None):
+        """x-slab real ``[mx][My][Mz]`` -> y-slab spectrum ``[Mx][my][Mz/2+1]`` (unnormalised,
+        = numpy rfftn of the global field, pmwd/pm_util.py:281)."""
+        s = self.rfft2_a2a(real)
         with TIMERS('fft1d_x'):
             return self._fft_x(s, inverse=False)                    # 1-D C2C over x
 
     def irfftn(self, spec, My, Mz, out=None):
         """Inverse of :meth:`rfftn` WITHOUT the 1/N (callers fold it into their scale).
         ``spec`` is clobbered on CUDA (in-place x-pass)."""
-        P = self.size
-        Mx, my, nzc = spec.shape
-        mx = Mx // P
         with TIMERS('fft1d_x'):
             s = self._fft_x(spec, inverse=True)                     # unnormalised inverse over x (in place)
-        with TIMERS('all_to_all'):
-            s = self._a2a(s.reshape(P, mx, my, nzc))                # [p] = y-chunk p of my planes
-        with TIMERS('pack'):
-            s = s.permute(1, 0, 2, 3).reshape(mx, My, nzc)          # unpack
-        with TIMERS('fft2d_c2r'):
-            if out is not None:
-                return torch.fft.irfft2(s, s=(My, Mz), norm='forward', out=out)
-            return torch.fft.irfft2(s, s=(My, Mz), norm='forward')
+        return self.a2a_irfft2(s, My, Mz, out=out)
 
     # ---- halos ---------------------------------------------------------------------------
     def _exchange(self, to_left, to_right):
@@ -254,18 +315,29 @@ class SlabForce:
                                             _lib.ptr(ext1), None, None), 'pmwd_scatter_soa')
         with TIMERS('halo'):
             rho = comm.halo_reduce(ext1, h)
-        spec = comm.rfftn(rho)
+        fused = bool(lib.pmwd_xpass_supported(Mx)) and os.environ.get('PMWD_XPASS', '1') != '0'
+        spec = comm.rfft2_a2a(rho) if fused else comm.rfftn(rho)
         g = [torch.empty_like(spec) for _ in range(3)]
         scale = float(np.float32(1.5 * Om / conf.mesh_size))          # 1.5 Omega_m and irfftn's 1/N
         arr = (C.c_void_p * 3)(*[t.data_ptr() for t in g])
         with TIMERS('kspace'):
-            _lib.check(lib.pmwd_kspace_force_slab(st, _lib.shape_arr(conf.mesh_shape), comm.y0, comm.my,
-                                                  float(conf.cell_size), scale, _lib.ptr(spec), arr),
-                       'pmwd_kspace_force_slab')
+            fn = lib.pmwd_xpass_force if fused else lib.pmwd_kspace_force_slab
+            _lib.check(fn(st, _lib.shape_arr(conf.mesh_shape), comm.y0, comm.my, float(conf.cell_size), scale,
+                          _lib.ptr(spec), arr), 'pmwd_xpass_force / pmwd_kspace_force_slab')
         del spec
-        for i in range(3):
-            comm.irfftn(g[i], My, Mz, out=ext3[i, h:h + comm.mx])
-            g[i] = None
+        if fused and dist.get_backend(comm.group) == 'nccl':
+            tokens = [comm.a2a_start(g[i]) for i in range(3)]      # comm of i+1 overlaps C2R of i
+            g = None
+            for i in range(3):
+                comm.a2a_finish_irfft2(tokens[i], My, Mz, out=ext3[i, h:h + comm.mx])
+                tokens[i] = None
+        else:
+            for i in range(3):
+                if fused:
+                    comm.a2a_irfft2(g[i], My, Mz, out=ext3[i, h:h + comm.mx])
+                else:
+                    comm.irfftn(g[i], My, Mz, out=ext3[i, h:h + comm.mx])
+                g[i] = None
         with TIMERS('halo'):
             comm.halo_fill(ext3, h)
         return desc, ext3, val
@@ -295,17 +367,21 @@ class SlabForce:
         _lib.check(lib.pmwd_scatter_soa(st, C.byref(desc), _lib.ptr(pmid), _lib.ptr(disp), _lib.ptr(pi), 0.0, 3,
                                         _lib.ptr(V[0]), _lib.ptr(V[1]), _lib.ptr(V[2])), 'pmwd_scatter_soa')
         Vs = comm.halo_reduce(V, h)
-        S = [comm.rfftn(Vs[i].contiguous()) for i in range(3)]
+        fused = bool(lib.pmwd_xpass_supported(Mx)) and os.environ.get('PMWD_XPASS', '1') != '0'
+        S = [(comm.rfft2_a2a if fused else comm.rfftn)(Vs[i].contiguous()) for i in range(3)]
         del V, Vs
         out = torch.empty_like(S[0])
         scale = float(np.float32(1.5 * Om / conf.mesh_size))
         arr = (C.c_void_p * 3)(*[t.data_ptr() for t in S])
-        _lib.check(lib.pmwd_kspace_force_adj_slab(st, _lib.shape_arr(conf.mesh_shape), comm.y0, comm.my,
-                                                  float(conf.cell_size), scale, arr, _lib.ptr(out)),
-                   'pmwd_kspace_force_adj_slab')
+        fn = lib.pmwd_xpass_force_adj if fused else lib.pmwd_kspace_force_adj_slab
+        _lib.check(fn(st, _lib.shape_arr(conf.mesh_shape), comm.y0, comm.my, float(conf.cell_size), scale, arr,
+                      _lib.ptr(out)), 'pmwd_xpass_force_adj / pmwd_kspace_force_adj_slab')
         del S
         rc = torch.empty_like(F[0])
-        comm.irfftn(out, My, Mz, out=rc[h:h + comm.mx])
+        if fused:
+            comm.a2a_irfft2(out, My, Mz, out=rc[h:h + comm.mx])
+        else:
+            comm.irfftn(out, My, Mz, out=rc[h:h + comm.mx])
         comm.halo_fill(rc, h)
         _lib.check(lib.pmwd_force_adj_gather(st, C.byref(desc), _lib.ptr(pmid), _lib.ptr(disp), _lib.ptr(F[0]),
                                              _lib.ptr(F[1]), _lib.ptr(F[2]), _lib.ptr(rc), _lib.ptr(pi), val,
