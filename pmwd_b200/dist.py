@@ -510,6 +510,19 @@ def nbody_adj_slab(ptcl, ptcl_cot, cosmo, conf, comm, reverse=False, force=None)
     return nbody_adj(ptcl, ptcl_cot, None, cosmo, conf, reverse=reverse, _slab=force)
 
 
+def nbody_step_slab(a_prev, a_next, ptcl, cosmo, conf, comm, force=None):
+    """``nbody_step`` (pmwd/nbody.py:204-212) on this rank's slab: functional, returns new
+    Particles (inputs untouched)."""
+    from .nbody import _Store, _owned
+    force = force or SlabForce(conf, comm)
+    with torch.no_grad():
+        p = _owned(ptcl, conf)
+        store = _Store(conf, dict(pmid=p.pmid, disp=p.disp, vel=p.vel, acc=p.acc))
+        step_slab(float(a_prev), float(a_next), store, cosmo, conf, force)
+        a = store.arrays
+    return Particles(conf, ptcl.pmid, a['disp'], vel=a['vel'], acc=a['acc'])
+
+
 def step_slab(a_prev, a_next, store, cosmo, conf, force):
     """One KDK step (default ``symp_splits``; nbody.py:121-140) on the store's arrays."""
     from .nbody import drift_factor, kick_factor, _f32, _kick_drift
@@ -598,6 +611,39 @@ def run_bench(args):
         TIMERS.on = False
     assert torch.isfinite(store.arrays['disp']).all()
     Np = conf.ptcl_num
+
+    # ---- e2e: per-rank pinned host slabs -> device -> nbody_step_slab -> host, every step
+    ke = max(1, min(K, args.e2e_steps))
+    with torch.no_grad():
+        p0 = fresh().ptcl
+        host = {k: torch.empty(getattr(p0, k).shape, dtype=getattr(p0, k).dtype).pin_memory()
+                for k in ('pmid', 'disp', 'vel', 'acc')}
+        for k in host:
+            host[k].copy_(getattr(p0, k))
+        del p0, store
+        torch.cuda.empty_cache()
+        h2d = sum(t.numel() * t.element_size() for t in host.values()) * world
+        d2h = sum(host[k].numel() * host[k].element_size() for k in ('disp', 'vel', 'acc')) * world
+
+        def e2e_step(j):
+            d = {k: host[k].to(dev, non_blocking=True) for k in host}
+            p = Particles(conf, d['pmid'], d['disp'], vel=d['vel'], acc=d['acc'])
+            p = nbody_step_slab(a[j], a[j + 1], p, cosmo, conf, comm, force)
+            for k in ('disp', 'vel', 'acc'):
+                host[k].copy_(getattr(p, k), non_blocking=True)
+        e2e_step(0)
+        torch.cuda.synchronize(); dist.barrier()
+        e0.record()
+        for j in range(1, 1 + ke):
+            e2e_step(j % nsched)
+        e1.record()
+        torch.cuda.synchronize(); dist.barrier()
+        ems = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        ems = float(ems)
+    e2e = {'value': Np * ke / (ems * 1e-3), 'unit': 'particle-updates/s', 'steps': ke, 'ms_per_step': ems / ke,
+           'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+           'api': 'pmwd_b200.dist.nbody_step_slab on per-rank pinned host slabs'}
     if rank == 0:
         Nm = conf.mesh_size
         peak, peak_src = B._peaks()
@@ -612,7 +658,7 @@ def run_bench(args):
                          'kernel': 'whole step (per GPU)', 'traffic': None,
                          'achieved': (132 * Np + 68 * Nm) / world / (ms / K) / 1e6,
                          'frac': (132 * Np + 68 * Nm) / world / (ms / K) / 1e6 / peak},
-            'e2e': None, 'cpu_baseline': None,
+            'e2e': e2e, 'cpu_baseline': None,
         }
         print(json.dumps(line), flush=True)
     dist.barrier()

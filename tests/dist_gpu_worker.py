@@ -40,7 +40,7 @@ def main():
 
     # ---- force and force_adj on evolved-like particles
     g = torch.Generator(device=dev).manual_seed(1)
-    disp = ref_ic.disp + 3.0 * torch.randn(ref_ic.disp.shape, device=dev, generator=g)
+    disp = ref_ic.disp + 1.5 * torch.randn(ref_ic.disp.shape, device=dev, generator=g)
     pi = torch.randn(ref_ic.disp.shape, device=dev, generator=g)
     acc_ref = torch.empty_like(disp); alpha_ref = torch.empty_like(disp)
     force_adj_into(ref_ic.pmid, disp, 0.3, conf, pi, acc_ref, alpha_ref)
