@@ -23,7 +23,7 @@ def main():
     dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0')))
     n = 32
     shape = (n * world, n, n)        # non-cubic box, 2n mesh planes per rank (room for the halos)
-    conf = pm.Configuration(1., shape, mesh_shape=2, a_nbody_maxstep=0.1, device=dev, reorder_every=3,
+    conf = pm.Configuration(1., shape, mesh_shape=2, a_nbody_maxstep=0.05, a_stop=0.5, device=dev, reorder_every=3,
                             reorder_min_disp=0.5)
     comm = pd.SlabComm(conf)
     cosmo = pm.boltzmann(pm.SimpleLCDM(conf), conf)
