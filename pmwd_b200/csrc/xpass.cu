@@ -17,11 +17,16 @@
 // The FFT is a one-buffer Stockham autosort (radix 4 (+2)), 1024 threads per CTA,
 // twiddles from a shared-memory table built in float64.  Works on the slab-decomposed
 // layout too (ny_l rows starting at global row y0).
+#include <cuda_pipeline.h>
+
 #include "common.cuh"
 
 namespace pmwd {
 
 
+#ifndef PMWD_XTHREADS
+#define PMWD_XTHREADS 1024
+#endif
 #ifndef PMWD_XT
 #define PMWD_XT 8     // measured on B200 at 1024^3: T=8 (64-byte rows) 11.5 ms, T=4 (32-byte rows) 23.4 ms
 #endif
@@ -30,7 +35,7 @@ struct XCfg {
   // T kz-columns per tile (T*8-byte row segments).  T=8 runs 1024 threads, one CTA per SM;
   // T=4 runs 512 threads, two CTAs per SM (slower: 32-byte rows waste L2/DRAM requests).
   static constexpr int T = PMWD_XT;
-  static constexpr int BIG = PMWD_XT == 8 ? 1024 : 512;
+  static constexpr int BIG = PMWD_XTHREADS;
   static constexpr int CTAS = BIG == 1024 ? 1 : 2;
   static constexpr int THREADS = NX * T / 2 >= BIG ? BIG : NX * T / 2;
   static constexpr int EPT = NX * T / THREADS;
@@ -39,7 +44,9 @@ struct XCfg {
   // q = -i kx pot is parked in registers across the P transform, except for the longest
   // columns where that would spill: there it is parked in the G_x output array itself
   // (written, then re-read -- an L2 hit -- transformed and overwritten)
-  static constexpr bool QGLOBAL = false;   // (measured: no gain for 2048; the stages themselves spill)
+  static constexpr bool QGLOBAL = (NX * T / THREADS) >= 16;
+  // two tile buffers (cp.async prefetch of the next tile) when they fit in shared memory
+  static constexpr bool DBUF = 2 * NX * T * 8 + NX * 12 <= 200 * 1024;
   static constexpr int N4 = LOG2 / 2;
   static constexpr bool HAS2 = (LOG2 & 1) != 0;
 };
@@ -75,8 +82,7 @@ __device__ __forceinline__ void fft_stage(float2* buf, const float2* tw, const i
   constexpr int t = NX / R;                     // butterflies per column
   constexpr int nb = XT * t;
   constexpr int MAXB = (nb + THREADS - 1) / THREADS;
-  float2 v[MAXB][R];
-  int dst[MAXB];
+  float2 v[MAXB][R];                            // the whole tile lives in registers across the barrier
   const int tstep = NX / (p * R);               // twiddle table stride: angle = 2 pi r k / (p R)
 #pragma unroll
   for (int m = 0; m < MAXB; ++m) {
@@ -84,8 +90,6 @@ __device__ __forceinline__ void fft_stage(float2* buf, const float2* tw, const i
     if (nb % THREADS == 0 || b < nb) {
       const int c = b % XT, i = b / XT;
       const int k = i & (p - 1);
-      const int j = (i - k) * R + k;
-      float2 u[R];
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         float2 x = buf[(i + r * t) * XT + c];
@@ -94,24 +98,24 @@ __device__ __forceinline__ void fft_stage(float2* buf, const float2* tw, const i
           if (INV) w.y = -w.y;
           x = cmul(x, w);
         }
-        u[r] = x;
+        v[m][r] = x;
       }
       if (R == 4) {
-        float2 a0 = make_float2(u[0].x + u[2].x, u[0].y + u[2].y);
-        float2 a1 = make_float2(u[0].x - u[2].x, u[0].y - u[2].y);
-        float2 a2 = make_float2(u[1].x + u[R - 1].x, u[1].y + u[R - 1].y);
-        float2 d = make_float2(u[1].x - u[R - 1].x, u[1].y - u[R - 1].y);
+        const float2 a0 = make_float2(v[m][0].x + v[m][2].x, v[m][0].y + v[m][2].y);
+        const float2 a1 = make_float2(v[m][0].x - v[m][2].x, v[m][0].y - v[m][2].y);
+        const float2 a2 = make_float2(v[m][1].x + v[m][R - 1].x, v[m][1].y + v[m][R - 1].y);
+        const float2 d = make_float2(v[m][1].x - v[m][R - 1].x, v[m][1].y - v[m][R - 1].y);
         // forward: multiply by -i ; inverse: by +i
-        float2 a3 = INV ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);
+        const float2 a3 = INV ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);
         v[m][0] = make_float2(a0.x + a2.x, a0.y + a2.y);
         v[m][1] = make_float2(a1.x + a3.x, a1.y + a3.y);
         v[m][R - 2] = make_float2(a0.x - a2.x, a0.y - a2.y);
         v[m][R - 1] = make_float2(a1.x - a3.x, a1.y - a3.y);
       } else {
-        v[m][0] = make_float2(u[0].x + u[1].x, u[0].y + u[1].y);
-        v[m][1] = make_float2(u[0].x - u[1].x, u[0].y - u[1].y);
+        const float2 s0 = v[m][0], s1 = v[m][1];
+        v[m][0] = make_float2(s0.x + s1.x, s0.y + s1.y);
+        v[m][1] = make_float2(s0.x - s1.x, s0.y - s1.y);
       }
-      dst[m] = j * XT + c;
     }
   }
   __syncthreads();                              // all reads of this stage done
@@ -119,8 +123,11 @@ __device__ __forceinline__ void fft_stage(float2* buf, const float2* tw, const i
   for (int m = 0; m < MAXB; ++m) {
     const int b = threadIdx.x + THREADS * m;
     if (nb % THREADS == 0 || b < nb) {
+      const int c = b % XT, i = b / XT;
+      const int k = i & (p - 1);
+      const int dst = ((i - k) * R + k) * XT + c;
 #pragma unroll
-      for (int r = 0; r < R; ++r) buf[dst[m] + r * p * XT] = v[m][r];
+      for (int r = 0; r < R; ++r) buf[dst + r * p * XT] = v[m][r];
     }
   }
   __syncthreads();
@@ -148,23 +155,50 @@ __device__ __forceinline__ void build_tables(const XParams& P, float2* tw, float
 }
 
 // -------------------------------------------------------------------------- forward force
+// Tile input is double-buffered: the next tile's column data is fetched with cp.async (LDGSTS)
+// into the second buffer while the current tile goes through its three transforms.
+template <int NX>
+__device__ __forceinline__ void prefetch_tile(const XParams& P, float2* dst, int64_t tile, int ztiles,
+                                              int64_t plane) {
+  constexpr int EPT = XCfg<NX>::EPT;
+  constexpr int XT = XCfg<NX>::T;
+  constexpr int XSTEP = XCfg<NX>::XSTEP;
+  const int c = threadIdx.x % XT;
+  const int x0 = threadIdx.x / XT;
+  const int iy = (int)(tile / ztiles);
+  const int kz0 = (int)(tile - (int64_t)iy * ztiles) * XT;
+  const bool live = kz0 + c < P.nzc;
+  const int64_t col = (int64_t)iy * P.nzc + kz0 + c;
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) {
+    const int x = x0 + XSTEP * e;
+    if (live) __pipeline_memcpy_async(dst + x * XT + c, P.in[0] + (int64_t)x * plane + col, sizeof(float2));
+    else dst[x * XT + c] = make_float2(0.f, 0.f);
+  }
+  __pipeline_commit();
+}
+
 template <int NX>
 __global__ void __launch_bounds__(XCfg<NX>::THREADS, XCfg<NX>::CTAS) xfused_force_kernel(XParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2* buf = reinterpret_cast<float2*>(smem_raw);           // [NX][T]
-  float2* tw = buf + NX * XCfg<NX>::T;                          // [NX]
+  constexpr int XT = XCfg<NX>::T;
+  float2* buf = reinterpret_cast<float2*>(smem_raw);           // [NX][T]   current tile
+  constexpr bool DB = XCfg<NX>::DBUF;
+  float2* nxt = DB ? buf + NX * XT : buf;                       // [NX][T]   next tile (prefetch)
+  float2* tw = nxt + NX * XT;                                   // [NX]
   float* kx = reinterpret_cast<float*>(tw + NX);                // [NX]
   build_tables<NX>(P, tw, kx);
-  __syncthreads();
 
   constexpr int EPT = XCfg<NX>::EPT;                            // elements per thread
-  constexpr int XT = XCfg<NX>::T;
   const int ztiles = (P.nzc + XT - 1) / XT;
   const int64_t ntiles = (int64_t)P.ny_l * ztiles;
   const int c = threadIdx.x % XT;
-  const int x0 = threadIdx.x / XT;                              // rows x0 + (XTHREADS/XT) * e
+  const int x0 = threadIdx.x / XT;
   constexpr int XSTEP = XCfg<NX>::XSTEP;
   const int64_t plane = (int64_t)P.ny_l * P.nzc;
+
+  __syncthreads();
+  if (DB && (int64_t)blockIdx.x < ntiles) prefetch_tile<NX>(P, buf, blockIdx.x, ztiles, plane);
 
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int iy = (int)(tile / ztiles);
@@ -174,18 +208,18 @@ __global__ void __launch_bounds__(XCfg<NX>::THREADS, XCfg<NX>::CTAS) xfused_forc
     const float ky = xkval(iy + P.y0, P.ny_g, P.period, false);
     const float kz = xkval(kz0 + c, P.nz_g, P.period, true);
 
-    // ---- load the tile (coalesced 64-byte segments), forward FFT along x
-#pragma unroll
-    for (int e = 0; e < EPT; ++e) {
-      const int x = x0 + XSTEP * e;
-      buf[x * XT + c] = live ? __ldcs(P.in[0] + (int64_t)x * plane + col) : make_float2(0.f, 0.f);
+    // ---- this tile's data has been requested one iteration ago: wait, then start the next one
+    if (!DB) {
+      __syncthreads();                                           // previous tile's stores from buf done
+      prefetch_tile<NX>(P, buf, tile, ztiles, plane);
     }
+    __pipeline_wait_prior(0);
     __syncthreads();
+    if (DB && tile + gridDim.x < ntiles) prefetch_tile<NX>(P, nxt, tile + gridDim.x, ztiles, plane);
     fft_tile<NX, false>(buf, tw);
 
     // ---- pot = -(scale S)/k^2 in place; q = -i kx pot kept in registers
-    constexpr bool QG = XCfg<NX>::QGLOBAL;
-    float2 q[QG ? 1 : EPT];
+    float2 q[EPT];
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
       const int x = x0 + XSTEP * e;
@@ -196,13 +230,8 @@ __global__ void __launch_bounds__(XCfg<NX>::THREADS, XCfg<NX>::CTAS) xfused_forc
       if (ksq != 0.f)
         pot = make_float2(__fdiv_rn(-__fmul_rn(P.scale, s.x), ksq), __fdiv_rn(-__fmul_rn(P.scale, s.y), ksq));
       buf[x * XT + c] = pot;
-      const float2 qq = xnyq(k0, P.nyq, P.eps) ? make_float2(0.f, 0.f)
-                                               : make_float2(__fmul_rn(k0, pot.y), -__fmul_rn(k0, pot.x));
-      if (QG) {
-        if (live) P.out[0][(int64_t)x * plane + col] = qq;
-      } else {
-        q[e] = qq;
-      }
+      q[e] = xnyq(k0, P.nyq, P.eps) ? make_float2(0.f, 0.f)
+                                    : make_float2(__fmul_rn(k0, pot.y), -__fmul_rn(k0, pot.x));
     }
     __syncthreads();
 
@@ -223,11 +252,7 @@ __global__ void __launch_bounds__(XCfg<NX>::THREADS, XCfg<NX>::CTAS) xfused_forc
 
     // ---- G_x = IFFT_x(q)
 #pragma unroll
-    for (int e = 0; e < EPT; ++e) {
-      const int x = x0 + XSTEP * e;
-      if (QG) buf[x * XT + c] = live ? P.out[0][(int64_t)x * plane + col] : make_float2(0.f, 0.f);
-      else buf[x * XT + c] = q[e];
-    }
+    for (int e = 0; e < EPT; ++e) buf[(x0 + XSTEP * e) * XT + c] = q[e];
     __syncthreads();
     fft_tile<NX, true>(buf, tw);
 #pragma unroll
@@ -235,7 +260,8 @@ __global__ void __launch_bounds__(XCfg<NX>::THREADS, XCfg<NX>::CTAS) xfused_forc
       const int x = x0 + XSTEP * e;
       if (live) __stcs(P.out[0] + (int64_t)x * plane + col, buf[x * XT + c]);
     }
-    __syncthreads();
+    // swap the roles of the two tile buffers
+    float2* tmp = buf; buf = nxt; nxt = tmp;
   }
 }
 
@@ -323,7 +349,8 @@ __global__ void __launch_bounds__(XCfg<NX>::THREADS, XCfg<NX>::CTAS) xfused_forc
 template <int NX>
 static int launch_x(cudaStream_t st, const XParams& P, bool adjoint) {
   constexpr int XT = XCfg<NX>::T;
-  size_t smem = (size_t)NX * XT * sizeof(float2) + (size_t)NX * sizeof(float2) + (size_t)NX * sizeof(float);
+  size_t smem = (size_t)NX * XT * sizeof(float2) * ((adjoint || !XCfg<NX>::DBUF) ? 1 : 2) + (size_t)NX * sizeof(float2) +
+                (size_t)NX * sizeof(float);
   const int ztiles = (P.nzc + XT - 1) / XT;
   int64_t ntiles = (int64_t)P.ny_l * ztiles;
   int64_t cap = (int64_t)sm_count() * (XCfg<NX>::THREADS >= 1024 ? 1 : 2);
