@@ -29,7 +29,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ['NCCL_DEBUG'] = 'WARN'      # keep NCCL's version banner off stdout: ONE JSON line
+os.environ.pop('NCCL_DEBUG', None)       # NCCL_DEBUG >= VERSION prints a banner on stdout: ONE JSON line only
 
 
 def _peaks():
@@ -170,6 +170,35 @@ def rank_grid(n, ngpu):
 
 
 # ----------------------------------------------------------------------------- GPU arm
+class _StdoutToStderr:
+    """Route fd 1 to stderr while libraries initialise (NCCL prints a version banner on
+    stdout), so that the only thing on stdout is the ONE JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def restore(self):
+        if self.saved is not None:
+            sys.stdout.flush()
+            os.dup2(self.saved, 1)
+            os.close(self.saved)
+            self.saved = None
+
+    def __exit__(self, *exc):
+        self.restore()
+
+
+def emit(line):
+    """Print the JSON line on the real stdout."""
+    guard = globals().get('_GUARD')
+    if guard is not None:
+        guard.restore()
+    print(json.dumps(line), flush=True)
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -185,6 +214,7 @@ def run_ours(args):
             raise SystemExit('launch with torch.distributed.run for --gpus > 1')
     if world > 1:
         from pmwd_b200 import dist as pdist
+        args._emit = emit
         return pdist.run_bench(args)
 
     torch.cuda.set_device(local)
@@ -355,7 +385,7 @@ def run_ours(args):
                     'note': 'BASELINE.md derived figure for the same geometry on other hardware; not a published '
                             'number for this metric, hence vs_baseline = null'},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -378,7 +408,9 @@ def main():
     if args.impl == 'reference':
         run_reference(args)
     else:
-        run_ours(args)
+        global _GUARD
+        with _StdoutToStderr() as _GUARD:
+            run_ours(args)
 
 
 if __name__ == '__main__':
