@@ -220,6 +220,15 @@ int pmwd_permute_rows(void* stream, int64_t n, const uint32_t* perm, int narr,
                       const void* const* src, void* const* dst, const int32_t* row_bytes,
                       int inverse);
 
+/* Slab-FFT transpose as one kernel over NVLink peer memory: every rank stores the rows of its
+ * local array straight into the peers' receive buffers (peer-mapped device pointers, one per
+ * rank, e.g. from torch symmetric memory) at their final position.
+ * mode 0: src[mx][My][nzc] -> peer q = y/my: dst_q[rank*mx+ix][iy][nzc];
+ * mode 1: src[Mx][my][nzc] -> peer p = x/mx: dst_p[ix][rank*my+iy][nzc].
+ * The caller brackets the call with cross-rank barriers. */
+int pmwd_transpose_p2p(void* stream, int mode, int nranks, int rank, int mx, int my, int nzc,
+                       const void* src_c64, const uint64_t* peer_ptrs);
+
 /* ---- leapfrog updates: pmwd/nbody.py:39-99 ----------------------------------------- */
 /* kick (nbody.py:70-77) then drift (nbody.py:39-46) in one pass over n = N*dim floats:
  * if do_kick: vel += acc * K;  if do_drift: disp += vel * D.  In place. */

@@ -83,6 +83,7 @@ _SIGNATURES = {
     'pmwd_cell_sort_scratch_bytes': (_sz, [_descp]),
     'pmwd_cell_sort_perm': (_i, [_vp, _descp, _vp, _vp, _vp, _vp, _sz]),
     'pmwd_permute_rows': (_i, [_vp, _i64, _vp, _i, C.POINTER(_vp), C.POINTER(_vp), _i32p, _i]),
+    'pmwd_transpose_p2p': (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, C.POINTER(C.c_uint64)]),
     'pmwd_kick_drift': (_i, [_vp, _i64, _vp, _vp, _vp, _f, _f, _i, _i]),
     'pmwd_kick_drift_adj': (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _i, _vp]),
 }

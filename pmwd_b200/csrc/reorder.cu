@@ -186,3 +186,78 @@ extern "C" int pmwd_permute_rows(void* stream, int64_t n, const uint32_t* perm, 
   PMWD_LAUNCH_CHECK();
   return PMWD_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// Slab-FFT transposes as ONE kernel over NVLink peer memory (no pack/unpack copies, no NCCL
+// staging): every rank stores the rows of its local array straight into the peers' receive
+// buffers (symmetric memory, peer-mapped pointers) at their final position.
+//   mode 0 (forward):  src[mx][My][nzc]  ->  peer q = y / my :  dst_q[(rank*mx + ix)][iy][nzc]
+//                      (x-slab after the local 2-D R2C  ->  y-slab [Mx][my][nzc] for the x-pass)
+//   mode 1 (inverse):  src[Mx][my][nzc]  ->  peer p = x / mx :  dst_p[ix][rank*my + iy][nzc]
+//                      (y-slab after the x-pass  ->  x-slab [mx][My][nzc], already unpacked for C2R)
+// One warp per row of nzc complex64 (contiguous on both sides), 8-byte accesses, 4 in flight.
+namespace pmwd {
+
+struct PeerPtrs { float2* p[8]; };
+
+__global__ void __launch_bounds__(256)
+transpose_p2p_kernel(int mode, int nranks, int rank, int mx, int my, int nzc,
+                     const float2* __restrict__ src, PeerPtrs dst) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int My = my * nranks, Mx = mx * nranks;
+  const int64_t rows = mode == 0 ? (int64_t)mx * My : (int64_t)Mx * my;
+  for (int64_t row = warp; row < rows; row += nwarp) {
+    float2* d;
+    if (mode == 0) {
+      const int ix = (int)(row / My), y = (int)(row - (int64_t)ix * My);
+      const int q = y / my, iy = y - q * my;
+      d = dst.p[q] + ((int64_t)(rank * mx + ix) * my + iy) * nzc;
+    } else {
+      const int x = (int)(row / my), iy = (int)(row - (int64_t)x * my);
+      const int p = x / mx, ix = x - p * mx;
+      d = dst.p[p] + ((int64_t)ix * My + rank * my + iy) * nzc;
+    }
+    const float2* s = src + row * nzc;
+    // 16-byte remote stores (NVLink packets) where the destination row is 16-byte aligned from
+    // element `head`; loads stay 8-byte because source and destination rows are skewed
+    const int head = (int)((reinterpret_cast<uintptr_t>(d) >> 3) & 1);     // 1 if d is only 8-byte aligned
+    if (lane == 0 && head) d[0] = __ldcs(s);
+    const int npair = (nzc - head) >> 1;
+    for (int i = lane; i < npair; i += 128) {
+      float2 a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i + 32 * u < npair) {
+          a[u] = __ldcs(s + head + 2 * (i + 32 * u));
+          b[u] = __ldcs(s + head + 2 * (i + 32 * u) + 1);
+        }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i + 32 * u < npair)
+          *reinterpret_cast<float4*>(d + head + 2 * (i + 32 * u)) = make_float4(a[u].x, a[u].y, b[u].x, b[u].y);
+    }
+    const int tail = head + 2 * npair;
+    if (lane == 0 && tail < nzc) d[tail] = __ldcs(s + tail);
+  }
+}
+
+}  // namespace pmwd
+
+extern "C" int pmwd_transpose_p2p(void* stream, int mode, int nranks, int rank, int mx, int my,
+                                  int nzc, const void* src, const uint64_t* peer_ptrs) {
+  PMWD_REQUIRE(src && peer_ptrs, "null buffer");
+  PMWD_REQUIRE(nranks >= 1 && nranks <= 8 && rank >= 0 && rank < nranks, "bad rank / world size");
+  PMWD_REQUIRE(mx > 0 && my > 0 && nzc > 0 && (mode == 0 || mode == 1), "bad sizes");
+  pmwd::PeerPtrs P;
+  for (int i = 0; i < 8; ++i) P.p[i] = i < nranks ? reinterpret_cast<float2*>(peer_ptrs[i]) : nullptr;
+  for (int i = 0; i < nranks; ++i) PMWD_REQUIRE(P.p[i] != nullptr, "null peer pointer");
+  cudaStream_t st = pmwd::as_stream(stream);
+  pmwd::StageTimer timer(pmwd::ST_OTHER, st);
+  int64_t rows = mode == 0 ? (int64_t)mx * my * nranks : (int64_t)mx * nranks * my;
+  int grid = pmwd::grid_for(rows * 32, 256, 8);
+  pmwd::transpose_p2p_kernel<<<grid, 256, 0, st>>>(mode, nranks, rank, mx, my, nzc, (const float2*)src, P);
+  PMWD_LAUNCH_CHECK();
+  return PMWD_OK;
+}

@@ -94,6 +94,67 @@ class SlabComm:
         self.ptcl_num_local = self.pnx * ny * nz
         self.left, self.right = (self.rank - 1) % P, (self.rank + 1) % P
 
+    # ---- symmetric-memory (NVLink peer) buffers for the P2P-store transposes ---------------
+    def setup_p2p(self, dev, nslots=4):
+        """Allocate ``nslots`` spectrum-sized receive buffers in torch symmetric memory and
+        exchange their peer-mapped pointers.  Returns False (and the NCCL all-to-all path stays
+        in use) if symmetric memory is unavailable."""
+        if getattr(self, '_p2p', None) is not None:
+            return bool(self._p2p)
+        self._p2p = []
+        if os.environ.get('PMWD_P2P', '1') == '0' or self.size == 1 or self.size > 8:
+            return False
+        try:
+            import torch.distributed._symmetric_memory as symm
+            Mx, My, Mz = self.conf.mesh_shape
+            numel = Mx * self.my * (Mz // 2 + 1)
+            group = dist.group.WORLD if self.group is None else self.group
+            slots = []
+            for _ in range(nslots):
+                t = symm.empty(numel * 2, dtype=torch.float32, device=dev)
+                hdl = symm.rendezvous(t, group)
+                ptrs = (C.c_uint64 * self.size)(*[int(p) for p in hdl.buffer_ptrs])
+                slots.append((t, hdl, ptrs))
+            self._p2p = slots
+            self._p2p_numel = numel
+        except Exception as e:  # noqa: BLE001
+            import sys
+            print(f'[pmwd_b200.dist] symmetric memory unavailable ({type(e).__name__}: {e}); '
+                  f'using NCCL all-to-all transposes', file=sys.stderr)
+            self._p2p = []
+        return bool(self._p2p)
+
+    def p2p_barrier(self):
+        self._p2p[0][1].barrier(channel=0)
+
+    def _p2p_view(self, slot, shape):
+        t = self._p2p[slot][0]
+        n = shape[0] * shape[1] * shape[2]
+        return torch.view_as_complex(t[:2 * n].view(n, 2)).view(shape)
+
+    def p2p_forward(self, real, slot):
+        """Local 2-D R2C + P2P-store transpose into receive buffer ``slot`` of every peer.
+        The caller brackets a batch of these with :meth:`p2p_barrier`."""
+        P = self.size
+        mx, My, Mz = real.shape
+        with TIMERS('fft2d_r2c'):
+            s = self._rfft2(real)
+        nzc = s.shape[-1]
+        with TIMERS('p2p_transpose'):
+            _lib.check(_lib.lib().pmwd_transpose_p2p(_lib.stream_ptr(real.device), 0, P, self.rank, mx, My // P,
+                                                     nzc, _lib.ptr(s), self._p2p[slot][2]), 'pmwd_transpose_p2p')
+        return self._p2p_view(slot, (P * mx, My // P, nzc))
+
+    def p2p_inverse(self, spec, slot):
+        """P2P-store transpose of a y-slab spectrum ``[Mx][my][nzc]`` into buffer ``slot`` of the
+        owning peers, already in the x-slab layout ``[mx][My][nzc]`` the 2-D C2R reads."""
+        P = self.size
+        Mx, my, nzc = spec.shape
+        with TIMERS('p2p_transpose'):
+            _lib.check(_lib.lib().pmwd_transpose_p2p(_lib.stream_ptr(spec.device), 1, P, self.rank, Mx // P, my,
+                                                     nzc, _lib.ptr(spec), self._p2p[slot][2]), 'pmwd_transpose_p2p')
+        return self._p2p_view(slot, (Mx // P, my * P, nzc))
+
     # ---- particles -----------------------------------------------------------------------
     def local_slice(self):
         """Range of this rank in the reference's (global, C-ordered) particle arrays."""
@@ -316,7 +377,13 @@ class SlabForce:
         with TIMERS('halo'):
             rho = comm.halo_reduce(ext1, h)
         fused = bool(lib.pmwd_xpass_supported(Mx)) and os.environ.get('PMWD_XPASS', '1') != '0'
-        spec = comm.rfft2_a2a(rho) if fused else comm.rfftn(rho)
+        p2p = fused and disp.is_cuda and comm.setup_p2p(dev)
+        if p2p:
+            comm.p2p_barrier()                      # peers are done reading their receive buffers
+            spec = comm.p2p_forward(rho, 0)
+            comm.p2p_barrier()                      # every rank's rows have landed
+        else:
+            spec = comm.rfft2_a2a(rho) if fused else comm.rfftn(rho)
         g = [torch.empty_like(spec) for _ in range(3)]
         scale = float(np.float32(1.5 * Om / conf.mesh_size))          # 1.5 Omega_m and irfftn's 1/N
         arr = (C.c_void_p * 3)(*[t.data_ptr() for t in g])
@@ -325,7 +392,14 @@ class SlabForce:
             _lib.check(fn(st, _lib.shape_arr(conf.mesh_shape), comm.y0, comm.my, float(conf.cell_size), scale,
                           _lib.ptr(spec), arr), 'pmwd_xpass_force / pmwd_kspace_force_slab')
         del spec
-        if fused and dist.get_backend(comm.group) == 'nccl':
+        if p2p:
+            recv = [comm.p2p_inverse(g[i], 1 + i) for i in range(3)]
+            g = None
+            comm.p2p_barrier()
+            for i in range(3):
+                with TIMERS('fft2d_c2r'):
+                    comm._irfft2(recv[i], My, Mz, out=ext3[i, h:h + comm.mx])
+        elif fused and dist.get_backend(comm.group) == 'nccl':
             tokens = [comm.a2a_start(g[i]) for i in range(3)]      # comm of i+1 overlaps C2R of i
             g = None
             for i in range(3):
@@ -368,7 +442,13 @@ class SlabForce:
                                         _lib.ptr(V[0]), _lib.ptr(V[1]), _lib.ptr(V[2])), 'pmwd_scatter_soa')
         Vs = comm.halo_reduce(V, h)
         fused = bool(lib.pmwd_xpass_supported(Mx)) and os.environ.get('PMWD_XPASS', '1') != '0'
-        S = [(comm.rfft2_a2a if fused else comm.rfftn)(Vs[i].contiguous()) for i in range(3)]
+        p2p = fused and comm.setup_p2p(dev)
+        if p2p:
+            comm.p2p_barrier()
+            S = [comm.p2p_forward(Vs[i].contiguous(), i) for i in range(3)]
+            comm.p2p_barrier()
+        else:
+            S = [(comm.rfft2_a2a if fused else comm.rfftn)(Vs[i].contiguous()) for i in range(3)]
         del V, Vs
         out = torch.empty_like(S[0])
         scale = float(np.float32(1.5 * Om / conf.mesh_size))
@@ -378,7 +458,11 @@ class SlabForce:
                       _lib.ptr(out)), 'pmwd_xpass_force_adj / pmwd_kspace_force_adj_slab')
         del S
         rc = torch.empty_like(F[0])
-        if fused:
+        if p2p:
+            r = comm.p2p_inverse(out, 3)
+            comm.p2p_barrier()
+            comm._irfft2(r, My, Mz, out=rc[h:h + comm.mx])
+        elif fused:
             comm.a2a_irfft2(out, My, Mz, out=rc[h:h + comm.mx])
         else:
             comm.irfftn(out, My, Mz, out=rc[h:h + comm.mx])
