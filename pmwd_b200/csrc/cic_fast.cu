@@ -73,21 +73,72 @@ __device__ __forceinline__ void red_add2(float* p, float a, float b) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Warp-aggregated reductions: lanes of a warp whose particles sit in the same base cell (adjacent
+// in the column-ordered storage of a clustered run) first add their 8 x NCH contributions with a
+// log-step shuffle reduction over the peer group (__match_any_sync), then only the group's
+// first lane issues the RED.E.ADD.F32(x2)s.  No peers (early times) costs one match + one vote.
+template <int NV>
+__device__ __forceinline__ bool reduce_peers(unsigned peers, float (&v)[NV]) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  int rel_pos = __popc(peers << (31 - lane) << 1);        // peers with a lower lane id
+  const bool first = rel_pos == 0;
+  peers &= (0xfffffffeu << lane);                          // peers with a higher lane id
+  while (__any_sync(full, peers)) {
+    const int next = __ffs(peers);
+    const int src = next ? next - 1 : lane;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float t = __shfl_sync(full, v[i], src);
+      if (next) v[i] += t;
+    }
+    const int done = rel_pos & 1;
+    peers &= __ballot_sync(full, !done);
+    rel_pos >>= 1;
+  }
+  return first;
+}
+
 template <int NCH>
 __global__ void __launch_bounds__(256)
 scatter_fast_kernel(FastParams P, const short* __restrict__ pmid, const float* __restrict__ disp,
                     const float* __restrict__ val, float val_scalar,
                     float* __restrict__ m0, float* __restrict__ m1, float* __restrict__ m2) {
-  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P.n;
+  // whole warps iterate together (the shuffles below need all 32 lanes)
+  const int64_t n_round = (P.n + 31) & ~(int64_t)31;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n_round;
        p += (int64_t)gridDim.x * blockDim.x) {
+    const bool active = p < P.n;
+    const int64_t pp = active ? p : P.n - 1;
     Stencil3 s;
-    axis_fast(pmid[3 * p + 0], disp[3 * p + 0], P.cell, P.nx, s.ix, s.wx, nullptr);
-    axis_fast(pmid[3 * p + 1], disp[3 * p + 1], P.cell, P.ny, s.iy, s.wy, nullptr);
-    axis_fast(pmid[3 * p + 2], disp[3 * p + 2], P.cell, P.nz, s.iz, s.wz, nullptr);
+    axis_fast(pmid[3 * pp + 0], disp[3 * pp + 0], P.cell, P.nx, s.ix, s.wx, nullptr);
+    axis_fast(pmid[3 * pp + 1], disp[3 * pp + 1], P.cell, P.ny, s.iy, s.wy, nullptr);
+    axis_fast(pmid[3 * pp + 2], disp[3 * pp + 2], P.cell, P.nz, s.iz, s.wz, nullptr);
+    // group key: the (global) base cell; inactive tail lanes get unique keys
+    const unsigned long long key =
+        active ? (unsigned long long)(((int64_t)s.ix[0] * P.ny + s.iy[0]) * P.nz + s.iz[0])
+               : ~0ull - (unsigned long long)(threadIdx.x & 31);
     localize_x(P, s.ix);
-    float v[NCH];
+    // contributions c[(bx*2+by)*2 + bz][ch] = val[ch] * ((wx*wy)*wz)
+    float c[8 * NCH];
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) v[c] = val ? val[NCH * p + c] : val_scalar;
+    for (int bx = 0; bx < 2; ++bx)
+#pragma unroll
+      for (int by = 0; by < 2; ++by) {
+        const float wxy = __fmul_rn(s.wx[bx], s.wy[by]);
+#pragma unroll
+        for (int bz = 0; bz < 2; ++bz) {
+          const float w = __fmul_rn(wxy, s.wz[bz]);
+#pragma unroll
+          for (int ch = 0; ch < NCH; ++ch) {
+            const float v = val ? val[NCH * pp + ch] : val_scalar;
+            c[((bx * 2 + by) * 2 + bz) * NCH + ch] = active ? __fmul_rn(v, w) : 0.f;
+          }
+        }
+      }
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    const bool first = reduce_peers<8 * NCH>(peers, c);
+    if (!first || !active) continue;
     // z-neighbours are adjacent in memory: one 8-byte reduction when the pair is aligned
     const bool pair = (s.iz[1] == s.iz[0] + 1) && ((s.iz[0] & 1) == 0) && ((P.nz & 1) == 0);
 #pragma unroll
@@ -95,14 +146,11 @@ scatter_fast_kernel(FastParams P, const short* __restrict__ pmid, const float* _
       if (s.ix[bx] < 0) continue;
 #pragma unroll
       for (int by = 0; by < 2; ++by) {
-        float wxy = __fmul_rn(s.wx[bx], s.wy[by]);
-        int64_t row = ((int64_t)s.ix[bx] * P.ny + s.iy[by]) * P.nz;
-        float w0 = __fmul_rn(wxy, s.wz[0]);
-        float w1 = __fmul_rn(wxy, s.wz[1]);
+        const int64_t row = ((int64_t)s.ix[bx] * P.ny + s.iy[by]) * P.nz;
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          float* m = c == 0 ? m0 : (c == 1 ? m1 : m2);
-          float a = __fmul_rn(v[c], w0), b = __fmul_rn(v[c], w1);
+        for (int ch = 0; ch < NCH; ++ch) {
+          float* m = ch == 0 ? m0 : (ch == 1 ? m1 : m2);
+          const float a = c[((bx * 2 + by) * 2 + 0) * NCH + ch], b = c[((bx * 2 + by) * 2 + 1) * NCH + ch];
           if (pair) {
             red_add2(m + row + s.iz[0], a, b);
           } else {
