@@ -334,6 +334,11 @@ class SlabForce:
         self._F = None           # force meshes with halos kept for the adjoint gather
         self._h = None
 
+    def _side_stream(self, dev):
+        if getattr(self, '_side', None) is None:
+            self._side = torch.cuda.Stream(device=dev)
+        return self._side
+
     def _halo(self, disp):
         conf, comm = self.conf, self.comm
         m = comm.allreduce_max(disp[:, 0].abs().max())
@@ -393,12 +398,27 @@ class SlabForce:
                           _lib.ptr(spec), arr), 'pmwd_xpass_force / pmwd_kspace_force_slab')
         del spec
         if p2p:
-            recv = [comm.p2p_inverse(g[i], 1 + i) for i in range(3)]
-            g = None
-            comm.p2p_barrier()
+            # transposes on a side stream, one cross-rank barrier per component; the 2-D C2R of
+            # component i (main stream) overlaps the NVLink stores of component i+1
+            main = torch.cuda.current_stream(dev)
+            side = self._side_stream(dev)
+            side.wait_stream(main)
+            landed, recv = [], []
+            with torch.cuda.stream(side):
+                comm.p2p_barrier()                  # peers are done with their receive buffers
+                for i in range(3):
+                    recv.append(comm.p2p_inverse(g[i], 1 + i))
+                    comm.p2p_barrier()              # component i has landed everywhere
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    landed.append(ev)
             for i in range(3):
+                main.wait_event(landed[i])
                 with TIMERS('fft2d_c2r'):
                     comm._irfft2(recv[i], My, Mz, out=ext3[i, h:h + comm.mx])
+            for t in g:
+                t.record_stream(side)
+            g = None
         elif fused and dist.get_backend(comm.group) == 'nccl':
             tokens = [comm.a2a_start(g[i]) for i in range(3)]      # comm of i+1 overlaps C2R of i
             g = None
