@@ -204,7 +204,7 @@ def run_ours(args):
     import torch
     import pmwd_b200 as pm
     from pmwd_b200 import _lib
-    from pmwd_b200.nbody import _integrate_inplace, _force_inplace, _store_from
+    from pmwd_b200.nbody import _Stepper, _store_from
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -233,18 +233,17 @@ def run_ours(args):
     Np, Nm = conf.ptcl_num, conf.mesh_size
 
     def fresh():
-        st = _store_from(ic, conf)
-        _force_inplace(st.ptcl, cosmo, conf)
-        return st
+        sp = _Stepper(_store_from(ic, conf), a, cosmo, conf)
+        sp.init()
+        return sp
 
     W, K = args.warmup, args.steps
     with torch.no_grad():
-        store = fresh()
-        i = 0
+        stepper = fresh()
         for _ in range(W):
-            if i == nsched:
-                store, i = fresh(), 0
-            _integrate_inplace(a[i], a[i + 1], store.ptcl, cosmo, conf); store.maybe_reorder(); i += 1
+            if stepper.i == nsched:
+                stepper = fresh()
+            stepper.step()
         torch.cuda.synchronize()
         sampler = ClockSampler(local); sampler.start()
         _lib.profile_enable(True); _lib.profile_read()
@@ -253,9 +252,9 @@ def run_ours(args):
         torch.cuda.synchronize()
         e0.record()
         for _ in range(K):
-            if i == nsched:
-                store, i = fresh(), 0
-            _integrate_inplace(a[i], a[i + 1], store.ptcl, cosmo, conf); store.maybe_reorder(); i += 1
+            if stepper.i == nsched:
+                stepper = fresh()
+            stepper.step()
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
@@ -263,6 +262,7 @@ def run_ours(args):
         stages = _lib.profile_read()
         _lib.profile_enable(False)
         clocks = sampler.stop()
+    store = stepper.store
     assert torch.isfinite(store.arrays['disp']).all()
     reorders = store.reorders
     value = Np * K / (ms * 1e-3)
@@ -270,7 +270,9 @@ def run_ours(args):
     # ---- per-stage roofline: algorithmic bytes per launch (SURVEY.md 8d / DESIGN.md)
     peak, peak_src = _peaks()
     alg = {'kick_drift': 60 * Np, 'memset': 4 * Nm, 'scatter': 18 * Np + 4 * Nm, 'fft_r2c': 8 * Nm,
-           'kspace_force': 16 * Nm, 'fft_c2r': 8 * Nm, 'gather3': 54 * Np + 12 * Nm}
+           'kspace_force': 16 * Nm, 'fft_c2r': 8 * Nm,
+           # gather + trailing half-kick + next step's half-kick and drift (pmwd_force_kdk)
+           'gather3': 66 * Np + 12 * Nm}
     kernels = {}
     for name, (tms, calls) in stages.items():
         if calls == 0:
@@ -306,7 +308,7 @@ def run_ours(args):
             g = torch.Generator(device=dev).manual_seed(1)
             cot = pm.Particles(conf, ic.pmid, torch.randn(disp.shape, device=dev, generator=g),
                                vel=torch.randn(disp.shape, device=dev, generator=g))
-            del store
+            del store, stepper
             torch.cuda.empty_cache()
             _lib.profile_enable(True); _lib.profile_read()
             torch.cuda.synchronize()

@@ -200,6 +200,13 @@ size_t pmwd_force_workspace_bytes(const pmwd_cic_desc* d, int adjoint, int mode)
 int pmwd_force(pmwd_ctx* ctx, void* stream, const pmwd_cic_desc* d, const void* pmid,
                const float* disp, double Omega_m, float* acc, float* kick_vel,
                float kick_factor, int mode, void* workspace, size_t workspace_bytes);
+/* One whole KDK step (pmwd/nbody.py:121-140, pipelined across steps) in one call: the force at
+ * the incoming disp, this step's trailing half-kick (K2) and the NEXT step's leading half-kick
+ * and drift (K1_next, D_next) all applied in the gather pass.  disp/vel are updated in place;
+ * float32 operation order identical to pmwd_force(+kick) followed by pmwd_kick_drift. */
+int pmwd_force_kdk(pmwd_ctx* ctx, void* stream, const pmwd_cic_desc* d, const void* pmid,
+                   float* disp, double Omega_m, float* acc, float* vel, float K2, float K1_next,
+                   float D_next, int mode, void* workspace, size_t workspace_bytes);
 /* force_adj (pmwd/nbody.py:108-118): acc = gravity(ptcl) and alpha = VJP_disp(gravity)(pi).
  * The Omega_m cotangent is sum(pi . acc) / Omega_m, which pmwd_kick_adj reduces anyway. */
 int pmwd_force_adj(pmwd_ctx* ctx, void* stream, const pmwd_cic_desc* d, const void* pmid,

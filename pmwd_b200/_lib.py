@@ -79,6 +79,7 @@ _SIGNATURES = {
     'pmwd_xpass_force_adj': (_i, [_vp, _i32p, _i, _i, _d, _f, C.POINTER(_vp), _vp]),
     'pmwd_force_workspace_bytes': (_sz, [_descp, _i, _i]),
     'pmwd_force': (_i, [_vp, _vp, _descp, _vp, _vp, _d, _vp, _vp, _f, _i, _vp, _sz]),
+    'pmwd_force_kdk': (_i, [_vp, _vp, _descp, _vp, _vp, _d, _vp, _vp, _f, _f, _f, _i, _vp, _sz]),
     'pmwd_force_adj': (_i, [_vp, _vp, _descp, _vp, _vp, _d, _vp, _vp, _vp, _i, _vp, _sz]),
     'pmwd_cell_sort_scratch_bytes': (_sz, [_descp]),
     'pmwd_cell_sort_perm': (_i, [_vp, _descp, _vp, _vp, _vp, _vp, _sz]),

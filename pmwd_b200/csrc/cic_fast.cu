@@ -164,12 +164,15 @@ scatter_fast_kernel(FastParams P, const short* __restrict__ pmid, const float* _
 }
 
 // ---------------------------------------------------------------------------------------
-template <bool KICK>
+// KICK: 0 = acc only; 1 = + trailing half-kick vel += acc*K; 2 = additionally the NEXT step's
+// leading half-kick and drift (vel += acc*K1n; disp += vel*Dn): the whole per-particle update of
+// a KDK step in the gather pass, same float32 operation sequence as the separate kernels.
+template <int KICK>
 __global__ void __launch_bounds__(256)
-gather3_kernel(FastParams P, const short* __restrict__ pmid, const float* __restrict__ disp,
+gather3_kernel(FastParams P, const short* __restrict__ pmid, const float* disp,
                const float* __restrict__ f0, const float* __restrict__ f1,
                const float* __restrict__ f2, float* __restrict__ acc, float* __restrict__ vel,
-               float K) {
+               float K, float K1n, float Dn, float* disp_rw) {
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P.n;
        p += (int64_t)gridDim.x * blockDim.x) {
     Stencil3 s;
@@ -193,9 +196,20 @@ gather3_kernel(FastParams P, const short* __restrict__ pmid, const float* __rest
     acc[3 * p + 1] = a1;
     acc[3 * p + 2] = a2;
     if (KICK) {
-      vel[3 * p + 0] = __fadd_rn(vel[3 * p + 0], __fmul_rn(a0, K));
-      vel[3 * p + 1] = __fadd_rn(vel[3 * p + 1], __fmul_rn(a1, K));
-      vel[3 * p + 2] = __fadd_rn(vel[3 * p + 2], __fmul_rn(a2, K));
+      float v0 = __fadd_rn(vel[3 * p + 0], __fmul_rn(a0, K));
+      float v1 = __fadd_rn(vel[3 * p + 1], __fmul_rn(a1, K));
+      float v2 = __fadd_rn(vel[3 * p + 2], __fmul_rn(a2, K));
+      if (KICK == 2) {
+        v0 = __fadd_rn(v0, __fmul_rn(a0, K1n));
+        v1 = __fadd_rn(v1, __fmul_rn(a1, K1n));
+        v2 = __fadd_rn(v2, __fmul_rn(a2, K1n));
+        disp_rw[3 * p + 0] = __fadd_rn(disp[3 * p + 0], __fmul_rn(v0, Dn));
+        disp_rw[3 * p + 1] = __fadd_rn(disp[3 * p + 1], __fmul_rn(v1, Dn));
+        disp_rw[3 * p + 2] = __fadd_rn(disp[3 * p + 2], __fmul_rn(v2, Dn));
+      }
+      vel[3 * p + 0] = v0;
+      vel[3 * p + 1] = v1;
+      vel[3 * p + 2] = v2;
     }
   }
 }
@@ -317,17 +331,20 @@ int scatter_fast(cudaStream_t st, const pmwd_cic_desc* d, const void* pmid, cons
 
 int gather3_fast(cudaStream_t st, const pmwd_cic_desc* d, const void* pmid, const float* disp,
                  const float* f0, const float* f1, const float* f2, float* acc, float* vel,
-                 float K) {
+                 float K, const float* next_kd, float* disp_rw) {
   FastParams P;
   int rc = fast_params(d, &P);
   if (rc) return rc;
   if (P.n == 0) return PMWD_OK;
   const int block = 256;
   int grid = grid_for(P.n, block, 8);
-  if (vel)
-    gather3_kernel<true><<<grid, block, 0, st>>>(P, (const short*)pmid, disp, f0, f1, f2, acc, vel, K);
+  if (vel && next_kd && disp_rw)
+    gather3_kernel<2><<<grid, block, 0, st>>>(P, (const short*)pmid, disp, f0, f1, f2, acc, vel, K,
+                                              next_kd[0], next_kd[1], disp_rw);
+  else if (vel)
+    gather3_kernel<1><<<grid, block, 0, st>>>(P, (const short*)pmid, disp, f0, f1, f2, acc, vel, K, 0.f, 0.f, nullptr);
   else
-    gather3_kernel<false><<<grid, block, 0, st>>>(P, (const short*)pmid, disp, f0, f1, f2, acc, nullptr, 0.f);
+    gather3_kernel<0><<<grid, block, 0, st>>>(P, (const short*)pmid, disp, f0, f1, f2, acc, nullptr, 0.f, 0.f, 0.f, nullptr);
   PMWD_LAUNCH_CHECK();
   return PMWD_OK;
 }

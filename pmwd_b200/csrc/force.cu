@@ -30,7 +30,8 @@ bool cic_is_full_mesh(const pmwd_cic_desc* d);
 int scatter_fast(cudaStream_t st, const pmwd_cic_desc* d, const void* pmid, const float* disp,
                  const float* val, float val_scalar, int nch, float* m0, float* m1, float* m2);
 int gather3_fast(cudaStream_t st, const pmwd_cic_desc* d, const void* pmid, const float* disp,
-                 const float* f0, const float* f1, const float* f2, float* acc, float* vel, float K);
+                 const float* f0, const float* f1, const float* f2, float* acc, float* vel, float K,
+                 const float* next_kd, float* disp_rw);
 int force_adj_gather(cudaStream_t st, const pmwd_cic_desc* d, const void* pmid, const float* disp,
                      const float* f0, const float* f1, const float* f2, const float* rho_cot,
                      const float* pi, float val, float* alpha);
@@ -210,7 +211,7 @@ extern "C" int pmwd_gather3(void* stream, const pmwd_cic_desc* d, const void* pm
                             float* acc, float* kick_vel, float kick_factor) {
   PMWD_REQUIRE(d && f0 && f1 && f2 && (d->ptcl_num == 0 || (pmid && disp && acc)), "null buffer");
   StageTimer t(ST_GATHER, as_stream(stream));
-  return gather3_fast(as_stream(stream), d, pmid, disp, f0, f1, f2, acc, kick_vel, kick_factor);
+  return gather3_fast(as_stream(stream), d, pmid, disp, f0, f1, f2, acc, kick_vel, kick_factor, nullptr, nullptr);
 }
 
 extern "C" int pmwd_force_adj_gather(void* stream, const pmwd_cic_desc* d, const void* pmid,
@@ -249,7 +250,37 @@ extern "C" int pmwd_force(pmwd_ctx* ctx, void* stream, const pmwd_cic_desc* d, c
   if (rc) return rc;
   StageTimer t(ST_GATHER, st);
   return gather3_fast(st, d, pmid, disp, (float*)(ws + L.rho_f0), (float*)(ws + L.f1),
-                      (float*)(ws + L.f2), acc, kick_vel, kick_factor);
+                      (float*)(ws + L.f2), acc, kick_vel, kick_factor, nullptr, nullptr);
+}
+
+// One whole KDK step's particle update behind the force (pmwd/nbody.py:121-140 pipelined):
+//   acc = gravity(disp); vel += acc*K2;   [this step's trailing half-kick]
+//   vel += acc*K1_next; disp += vel*D_next  [the NEXT step's leading half-kick and drift]
+// in the gather pass, so that a step is exactly one pmwd_force_kdk call.  Same float32
+// operation sequence as pmwd_force(+kick) followed by pmwd_kick_drift.  `disp` is updated in
+// place AFTER the force has been evaluated at its incoming value.
+extern "C" int pmwd_force_kdk(pmwd_ctx* ctx, void* stream, const pmwd_cic_desc* d, const void* pmid,
+                              float* disp, double Omega_m, float* acc, float* vel, float K2,
+                              float K1_next, float D_next, int mode, void* workspace,
+                              size_t workspace_bytes) {
+  int rc = check_force_args(d);
+  if (rc) return rc;
+  PMWD_REQUIRE(ctx && pmid && disp && acc && vel && workspace, "null buffer");
+  PMWD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+  ForceLayout L;
+  force_layout(d, 0, mode, &L);
+  if (workspace_bytes < L.total) {
+    set_error("pmwd_force_kdk needs %zu workspace bytes, got %zu", L.total, workspace_bytes);
+    return PMWD_ENOMEM;
+  }
+  cudaStream_t st = as_stream(stream);
+  char* ws = (char*)workspace;
+  rc = force_forward(ctx, st, d, pmid, disp, Omega_m, mode, ws, L, nullptr);
+  if (rc) return rc;
+  const float next_kd[2] = {K1_next, D_next};
+  StageTimer t(ST_GATHER, st);
+  return gather3_fast(st, d, pmid, disp, (float*)(ws + L.rho_f0), (float*)(ws + L.f1),
+                      (float*)(ws + L.f2), acc, vel, K2, next_kd, disp);
 }
 
 extern "C" int pmwd_force_adj(pmwd_ctx* ctx, void* stream, const pmwd_cic_desc* d,
@@ -276,7 +307,7 @@ extern "C" int pmwd_force_adj(pmwd_ctx* ctx, void* stream, const pmwd_cic_desc* 
   float* F[3] = {(float*)(ws + L.rho_f0), (float*)(ws + L.f1), (float*)(ws + L.f2)};
   {
     StageTimer t(ST_GATHER, st);
-    rc = gather3_fast(st, d, pmid, disp, F[0], F[1], F[2], acc, nullptr, 0.f);
+    rc = gather3_fast(st, d, pmid, disp, F[0], F[1], F[2], acc, nullptr, 0.f, nullptr, nullptr);
   }
   if (rc) return rc;
 

@@ -156,6 +156,23 @@ def force_into(pmid, disp, Omega_m, conf, acc, kick_vel=None, kick_factor=0.0):
             _lib.ptr(ws), ws.numel()), 'pmwd_force')
 
 
+def force_kdk_into(pmid, disp, Omega_m, conf, acc, vel, K2, K1_next, D_next):
+    """Enqueue ``pmwd_force_kdk``: force at ``disp``, trailing half-kick ``K2``, then the next
+    step's leading half-kick ``K1_next`` and drift ``D_next`` -- one call per KDK step."""
+    dev = disp.device
+    desc = _force_desc(pmid, conf)
+    mode = _mode(conf)
+    lib = _lib.lib()
+    nbytes = lib.pmwd_force_workspace_bytes(C.byref(desc), 0, mode)
+    ws = _workspace(dev, nbytes)
+    ctx = _lib.Context.get(dev).reserve(conf.mesh_shape)
+    with torch.cuda.device(dev):
+        _lib.check(lib.pmwd_force_kdk(
+            ctx.handle, _lib.stream_ptr(dev), C.byref(desc), _lib.ptr(pmid), _lib.ptr(disp),
+            float(Omega_m), _lib.ptr(acc), _lib.ptr(vel), float(K2), float(K1_next), float(D_next), mode,
+            _lib.ptr(ws), ws.numel()), 'pmwd_force_kdk')
+
+
 def force_adj_into(pmid, disp, Omega_m, conf, pi, acc, alpha):
     """Enqueue ``pmwd_force_adj``: ``acc <- gravity``, ``alpha <- VJP_disp(gravity)(pi)``."""
     dev = disp.device

@@ -16,7 +16,7 @@ import torch
 from . import _lib
 from .boltzmann import growth
 from .cosmology import E2, H_deriv
-from .gravity import gravity, force_into, force_adj_into, _force_desc
+from .gravity import gravity, force_into, force_adj_into, force_kdk_into, _force_desc
 from .particles import Particles
 
 
@@ -292,16 +292,72 @@ def nbody_step(a_prev, a_next, ptcl, obsvbl, cosmo, conf):
     return ptcl, obsvbl
 
 
+class _Stepper:
+    """Pipelined KDK stepping over a schedule of scale factors on a ``_Store``: with the default
+    splitting on the 3-D fast path every step is ONE ``pmwd_force_kdk`` call (force + trailing
+    half-kick + the next step's leading half-kick and drift in the gather pass); the very first
+    step's leading kick+drift is a separate ``pmwd_kick_drift`` pass.  Arithmetic per particle
+    is the same float32 sequence as ``integrate`` (``nbody.py:121-140``).  Other configurations
+    fall back to ``_integrate_inplace`` step by step."""
+
+    def __init__(self, store, a_list, cosmo, conf):
+        self.store, self.a, self.cosmo, self.conf = store, list(a_list), cosmo, conf
+        self.i = 0
+        self.fused = (tuple(tuple(x) for x in conf.symp_splits) == ((0, 0.5), (1, 0.5))
+                      and _fast_ok(store.ptcl, conf))
+        self._factors = {}
+        self.pre = False          # the current step's leading kick+drift has already been applied
+
+    def factors(self, i):
+        f = self._factors.get(i)
+        if f is None:
+            a0, a1 = self.a[i], self.a[i + 1]
+            am = a0 * 0.5 + a1 * 0.5
+            f = (_f32(kick_factor(a0, a0, am, self.cosmo, self.conf)),
+                 _f32(drift_factor(am, a0, a1, self.cosmo, self.conf)),
+                 _f32(kick_factor(a1, am, a1, self.cosmo, self.conf)))
+            self._factors[i] = f
+        return f
+
+    @property
+    def nsteps(self):
+        return len(self.a) - 1
+
+    def init(self):
+        _force_inplace(self.store.ptcl, self.cosmo, self.conf)
+
+    def step(self):
+        i = self.i
+        st = self.store
+        if not self.fused:
+            _integrate_inplace(self.a[i], self.a[i + 1], st.ptcl, self.cosmo, self.conf)
+        else:
+            k1, d, k2 = self.factors(i)
+            if not self.pre:
+                _kick_drift(st.ptcl, k1, d, True, True)
+            a = st.arrays
+            Om = float(self.cosmo.Omega_m)
+            if i + 1 < self.nsteps:
+                k1n, dn, _ = self.factors(i + 1)
+                force_kdk_into(a['pmid'], a['disp'], Om, self.conf, a['acc'], a['vel'], k2, k1n, dn)
+                self.pre = True
+            else:
+                force_into(a['pmid'], a['disp'], Om, self.conf, a['acc'], a['vel'], k2)
+                self.pre = False
+        self.i += 1
+        st.maybe_reorder()
+
+
 def _nbody_forward(ptcl, cosmo, conf, reverse):
     a_nbody = conf.a_nbody.tolist()
     if reverse:
         a_nbody = a_nbody[::-1]
     with torch.no_grad():
         store = _store_from(ptcl, conf)
-        _force_inplace(store.ptcl, cosmo, conf)
-        for a_prev, a_next in zip(a_nbody[:-1], a_nbody[1:]):
-            _integrate_inplace(a_prev, a_next, store.ptcl, cosmo, conf)
-            store.maybe_reorder()
+        stepper = _Stepper(store, a_nbody, cosmo, conf)
+        stepper.init()
+        for _ in range(stepper.nsteps):
+            stepper.step()
         disp, vel, acc = store.lagrangian('disp', 'vel', 'acc')
     return Particles(conf, ptcl.pmid, disp, vel=vel, acc=acc, attr=ptcl.attr)
 
