@@ -166,6 +166,9 @@ int pmwd_scatter_soa(void* stream, const pmwd_cic_desc* d, const void* pmid, con
 int pmwd_gather3(void* stream, const pmwd_cic_desc* d, const void* pmid, const float* disp,
                  const float* f0, const float* f1, const float* f2, float* acc, float* kick_vel,
                  float kick_factor);
+int pmwd_gather3_kdk(void* stream, const pmwd_cic_desc* d, const void* pmid, float* disp,
+                     const float* f0, const float* f1, const float* f2, float* acc, float* vel,
+                     float K2, float K1_next, float D_next);   /* gather3 + pipelined kick/drift, cf. pmwd_force_kdk */
 /* alpha = disp cotangent of gravity from the three force meshes and rho_cot
  * (gather.py:106-110 x3 + scatter.py:112-116). */
 int pmwd_force_adj_gather(void* stream, const pmwd_cic_desc* d, const void* pmid,

@@ -71,6 +71,7 @@ _SIGNATURES = {
     'pmwd_strain': (_i, [_vp, _i, _i32p, _d, _i, _i, _vp, _vp]),
     'pmwd_scatter_soa': (_i, [_vp, _descp, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp]),
     'pmwd_gather3': (_i, [_vp, _descp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f]),
+    'pmwd_gather3_kdk': (_i, [_vp, _descp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f]),
     'pmwd_force_adj_gather': (_i, [_vp, _descp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp]),
     'pmwd_kspace_force_slab': (_i, [_vp, _i32p, _i, _i, _d, _f, _vp, C.POINTER(_vp)]),
     'pmwd_kspace_force_adj_slab': (_i, [_vp, _i32p, _i, _i, _d, _f, C.POINTER(_vp), _vp]),

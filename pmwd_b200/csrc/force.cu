@@ -214,6 +214,17 @@ extern "C" int pmwd_gather3(void* stream, const pmwd_cic_desc* d, const void* pm
   return gather3_fast(as_stream(stream), d, pmid, disp, f0, f1, f2, acc, kick_vel, kick_factor, nullptr, nullptr);
 }
 
+// pmwd_gather3 + this step's trailing half-kick + the next step's leading half-kick and drift
+// (see pmwd_force_kdk); disp is updated in place.
+extern "C" int pmwd_gather3_kdk(void* stream, const pmwd_cic_desc* d, const void* pmid, float* disp,
+                                const float* f0, const float* f1, const float* f2, float* acc,
+                                float* vel, float K2, float K1_next, float D_next) {
+  PMWD_REQUIRE(d && f0 && f1 && f2 && (d->ptcl_num == 0 || (pmid && disp && acc && vel)), "null buffer");
+  StageTimer t(ST_GATHER, as_stream(stream));
+  const float next_kd[2] = {K1_next, D_next};
+  return gather3_fast(as_stream(stream), d, pmid, disp, f0, f1, f2, acc, vel, K2, next_kd, disp);
+}
+
 extern "C" int pmwd_force_adj_gather(void* stream, const pmwd_cic_desc* d, const void* pmid,
                                      const float* disp, const float* f0, const float* f1,
                                      const float* f2, const float* rho_cot, const float* pi,

@@ -436,15 +436,23 @@ class SlabForce:
             comm.halo_fill(ext3, h)
         return desc, ext3, val
 
-    def force(self, pmid, disp, Om, acc, kick_vel=None, kick_factor=0.0):
+    def force(self, pmid, disp, Om, acc, kick_vel=None, kick_factor=0.0, next_kd=None):
+        """``next_kd = (K1_next, D_next)``: also apply the next step's leading half-kick and
+        drift in the gather pass (pipelined KDK, cf. ``pmwd_force_kdk``)."""
         with TIMERS('halo_width'):
             h = self._halo(disp)
         desc, F, _ = self._mesh_forces(pmid, disp, Om, h)
         with TIMERS('gather'):
-            _lib.check(_lib.lib().pmwd_gather3(
-                _lib.stream_ptr(disp.device), C.byref(desc), _lib.ptr(pmid), _lib.ptr(disp), _lib.ptr(F[0]),
-                _lib.ptr(F[1]), _lib.ptr(F[2]), _lib.ptr(acc), _lib.ptr(kick_vel), float(kick_factor)),
-                'pmwd_gather3')
+            st = _lib.stream_ptr(disp.device)
+            if next_kd is not None:
+                _lib.check(_lib.lib().pmwd_gather3_kdk(
+                    st, C.byref(desc), _lib.ptr(pmid), _lib.ptr(disp), _lib.ptr(F[0]), _lib.ptr(F[1]),
+                    _lib.ptr(F[2]), _lib.ptr(acc), _lib.ptr(kick_vel), float(kick_factor), float(next_kd[0]),
+                    float(next_kd[1])), 'pmwd_gather3_kdk')
+            else:
+                _lib.check(_lib.lib().pmwd_gather3(
+                    st, C.byref(desc), _lib.ptr(pmid), _lib.ptr(disp), _lib.ptr(F[0]), _lib.ptr(F[1]),
+                    _lib.ptr(F[2]), _lib.ptr(acc), _lib.ptr(kick_vel), float(kick_factor)), 'pmwd_gather3')
 
     def force_adj(self, pmid, disp, Om, pi, acc, alpha):
         conf, comm = self.conf, self.comm
@@ -596,14 +604,52 @@ def nbody_slab(ptcl, cosmo, conf, comm, reverse=False, force=None):
     with torch.no_grad():
         p = _owned(ptcl, conf)
         store = _Store(conf, dict(pmid=p.pmid.clone(), disp=p.disp, vel=p.vel, acc=p.acc))
-        store.desc_fn = lambda pmid: force._desc(pmid, max(force.h_alloc, 1))
-        a = store.arrays
-        force.force(a['pmid'], a['disp'], Om, a['acc'])
-        for a_prev, a_next in zip(a_nbody[:-1], a_nbody[1:]):
-            step_slab(a_prev, a_next, store, cosmo, conf, force)
-            store.maybe_reorder(sync_max=comm.allreduce_max)
+        stepper = SlabStepper(store, a_nbody, cosmo, conf, comm, force)
+        stepper.init()
+        for _ in range(stepper.nsteps):
+            stepper.step()
         disp, vel, acc = store.lagrangian('disp', 'vel', 'acc')
     return Particles(conf, ptcl.pmid, disp, vel=vel, acc=acc)
+
+
+class SlabStepper:
+    """Pipelined KDK stepping on one rank's slab (cf. ``nbody._Stepper``): one force per step
+    with the kick/drift of both adjacent half-steps applied in its gather pass."""
+
+    def __init__(self, store, a_list, cosmo, conf, comm, force):
+        from .nbody import _Stepper
+        self.inner = _Stepper(store, a_list, cosmo, conf)     # factor cache only
+        self.store, self.cosmo, self.conf, self.comm, self.force = store, cosmo, conf, comm, force
+        if tuple(tuple(x) for x in conf.symp_splits) != ((0, 0.5), (1, 0.5)):
+            raise NotImplementedError('the slab integrator implements the default KDK splitting')
+        self.i = 0
+        self.pre = False
+        store.desc_fn = lambda pmid: force._desc(pmid, max(force.h_alloc, 1))
+
+    @property
+    def nsteps(self):
+        return self.inner.nsteps
+
+    def init(self):
+        a = self.store.arrays
+        self.force.force(a['pmid'], a['disp'], float(self.cosmo.Omega_m), a['acc'])
+
+    def step(self):
+        from .nbody import _kick_drift
+        i = self.i
+        k1, d, k2 = self.inner.factors(i)
+        if not self.pre:
+            with TIMERS('kick_drift'):
+                _kick_drift(self.store.ptcl, k1, d, True, True)
+        a = self.store.arrays
+        nxt = None
+        if i + 1 < self.nsteps:
+            k1n, dn, _ = self.inner.factors(i + 1)
+            nxt = (k1n, dn)
+        self.force.force(a['pmid'], a['disp'], float(self.cosmo.Omega_m), a['acc'], a['vel'], k2, next_kd=nxt)
+        self.pre = nxt is not None
+        self.i += 1
+        self.store.maybe_reorder(sync_max=self.comm.allreduce_max)
 
 
 def nbody_adj_slab(ptcl, ptcl_cot, cosmo, conf, comm, reverse=False, force=None):
@@ -681,18 +727,17 @@ def run_bench(args):
     def fresh():
         p = _owned(ic, conf)
         st = _Store(conf, dict(pmid=p.pmid.clone(), disp=p.disp, vel=p.vel, acc=p.acc))
-        st.desc_fn = lambda pmid: force._desc(pmid, max(force.h_alloc, 1))
-        ar = st.arrays
-        force.force(ar['pmid'], ar['disp'], Om, ar['acc'])
-        return st
+        sp = SlabStepper(st, a, cosmo, conf, comm, force)
+        sp.init()
+        return sp
 
     W, K = args.warmup, args.steps
     with torch.no_grad():
-        store, i = fresh(), 0
+        stepper = fresh()
         for _ in range(W):
-            if i == nsched:
-                store, i = fresh(), 0
-            step_slab(a[i], a[i + 1], store, cosmo, conf, force); store.maybe_reorder(sync_max=comm.allreduce_max); i += 1
+            if stepper.i == nsched:
+                stepper = fresh()
+            stepper.step()
         torch.cuda.synchronize(); dist.barrier()
         sampler = B.ClockSampler(local); sampler.start()
         TIMERS.on = True
@@ -701,9 +746,9 @@ def run_bench(args):
         torch.cuda.synchronize()
         e0.record()
         for _ in range(K):
-            if i == nsched:
-                store, i = fresh(), 0
-            step_slab(a[i], a[i + 1], store, cosmo, conf, force); store.maybe_reorder(sync_max=comm.allreduce_max); i += 1
+            if stepper.i == nsched:
+                stepper = fresh()
+            stepper.step()
         e1.record()
         torch.cuda.synchronize(); dist.barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -713,18 +758,19 @@ def run_bench(args):
         clocks = sampler.stop()
         phases = {k: round(v[0] / K, 3) for k, v in TIMERS.read().items()}
         TIMERS.on = False
+    store = stepper.store
     assert torch.isfinite(store.arrays['disp']).all()
     Np = conf.ptcl_num
 
     # ---- e2e: per-rank pinned host slabs -> device -> nbody_step_slab -> host, every step
     ke = max(1, min(K, args.e2e_steps))
     with torch.no_grad():
-        p0 = fresh().ptcl
+        p0 = fresh().store.ptcl
         host = {k: torch.empty(getattr(p0, k).shape, dtype=getattr(p0, k).dtype).pin_memory()
                 for k in ('pmid', 'disp', 'vel', 'acc')}
         for k in host:
             host[k].copy_(getattr(p0, k))
-        del p0, store
+        del p0, store, stepper
         torch.cuda.empty_cache()
         h2d = sum(t.numel() * t.element_size() for t in host.values()) * world
         d2h = sum(host[k].numel() * host[k].element_size() for k in ('disp', 'vel', 'acc')) * world
