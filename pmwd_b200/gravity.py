@@ -65,7 +65,8 @@ def laplace(kvec, src, cosmo=None):
     shape = _real_shape_of(kvec, src)
     if shape is not None and src.is_cuda and src.dtype == torch.complex64:
         return _Laplace.apply(src, shape, kvec.spacing if kvec.spacing is not None else 2 * torch.pi)
-    # untagged wavevectors: plain elementwise evaluation on the array's own device
+    # untagged wavevectors (not produced by fftfreq): plain elementwise evaluation on the GPU
+    _lib.require_cuda(src)
     k2 = sum(k ** 2 for k in kvec)
     safe = torch.where(k2 != 0, k2, torch.ones_like(k2))
     return torch.where(k2 != 0, -src / safe, torch.zeros_like(src))
@@ -98,6 +99,7 @@ def neg_grad(k, pot, spacing):
         expect = tuple(shape[:-1]) + (shape[-1] // 2 + 1,)
         if tuple(pot.shape) == expect and kspacing == spacing:
             return _NegGrad.apply(pot, shape, spacing, axis, 1)
+    _lib.require_cuda(pot)     # untagged k: elementwise on the GPU; there is no CPU path
     nyquist = torch.pi / spacing
     eps = nyquist * torch.finfo(k.dtype).eps
     neg_ik = torch.where((k.abs() - nyquist).abs() <= eps, torch.zeros_like(k), k) * (-1j)
@@ -210,6 +212,7 @@ def _gravity_general(ptcl, cosmo, conf):
 
 def gravity(a, ptcl, cosmo, conf):
     """Gravitational accelerations of particles in [H_0^2] (``pmwd/gravity.py:47-72``)."""
+    _lib.require_cuda(ptcl.pmid, ptcl.disp)
     if conf.dim == 3 and ptcl.pmid.dtype == torch.int16 and ptcl.disp.is_cuda:
         return _Gravity.apply(ptcl.disp, cosmo.Omega_m, ptcl.pmid, conf)
     return _gravity_general(ptcl, cosmo, conf)

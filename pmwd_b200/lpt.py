@@ -39,6 +39,7 @@ def _strain(kvec, i, j, pot, conf):
     if pot.is_cuda and pot.dtype == torch.complex64 and getattr(kvec, 'shape', None) is not None:
         strain = _Strain.apply(pot, kvec.shape, conf.ptcl_spacing, i, j)
     else:
+        _lib.require_cuda(pot)     # untagged kvec: elementwise on the GPU; there is no CPU path
         k_i, k_j = kvec[i], kvec[j]
         nyquist = torch.pi / conf.ptcl_spacing
         eps = nyquist * torch.finfo(conf.float_dtype).eps
@@ -87,6 +88,7 @@ def lpt(modes, cosmo, conf):
     if conf.lpt_order not in (0, 1, 2, 3):
         raise ValueError(f'lpt_order={conf.lpt_order} not supported')
 
+    _lib.require_cuda(modes)
     dev = modes.device
     modes = modes / conf.ptcl_cell_vol
     kvec = fftfreq(conf.ptcl_grid_shape, conf.ptcl_spacing, dtype=conf.float_dtype, device=dev)

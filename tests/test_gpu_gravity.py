@@ -220,31 +220,6 @@ def test_kick_drift_adj_vs_numpy():
     np.testing.assert_allclose(sums.cpu().numpy(), [s_pa, s_xv], rtol=1e-12)
 
 
-def test_step_factors_vs_oracle():
-    """nbody.py:12-36 in float64: torch host code vs the NumPy/scipy oracle, and the
-    autograd factor gradients vs the oracle's finite differences."""
-    pm = _pm()
-    from pmwd_b200.nbody import kick_factor, drift_factor, _factor_valgrad
-    conf, oconf = _confs((4, 4, 4))
-    cosmo = pm.boltzmann(pm.SimpleLCDM(conf), conf)
-    ocosmo = O.boltzmann(O.SimpleLCDM(oconf), oconf)
-    ocosmo_same = ocosmo.replace(growth=cosmo.growth.numpy())      # identical table
-    a = oconf.a_nbody
-    for i in (0, 10, 40, 62):
-        a0, a1 = a[i], a[i + 1]
-        am = 0.5 * (a0 + a1)
-        for fun, ofun, args in ((kick_factor, O.kick_factor, (a0, a0, am)),
-                                (drift_factor, O.drift_factor, (am, a0, a1)),
-                                (kick_factor, O.kick_factor, (a1, am, a1))):
-            val, grads = _factor_valgrad(fun, *args, cosmo, conf)
-            np.testing.assert_allclose(val, ofun(*args, ocosmo_same, oconf), rtol=1e-12)
-            # independent ODE solvers (Dopri5 @1.5e-8 vs DOP853 @1e-11); factors difference the table
-            np.testing.assert_allclose(val, ofun(*args, ocosmo, oconf), rtol=1e-5)
-            _, og = O.factor_grads(ofun, *args, ocosmo_same, oconf)
-            np.testing.assert_allclose(grads['Omega_m'].item(), og['Omega_m'], rtol=2e-5, atol=1e-9)
-            np.testing.assert_allclose(grads['growth'].numpy(), og['growth'], rtol=1e-5, atol=1e-9)
-
-
 # ------------------------------------------------------------------------------- LPT
 @pytest.mark.parametrize('order', [1, 2])
 def test_lpt_vs_oracle(order):

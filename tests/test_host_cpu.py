@@ -1,0 +1,123 @@
+"""CPU tests of the host-side (float64, torch) code that feeds the kernels: configuration
+validation, particle grid construction, growth / transfer tables and the kick/drift factors with
+their cosmology gradients, against the NumPy/scipy oracle.  No GPU, no kernels."""
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+import pmwd_b200 as pm
+from pmwd_b200._lib import PmwdError
+
+
+def _confs(shape=(4, 4, 4), **kw):
+    return (pm.Configuration(1., shape, mesh_shape=2, device='cpu', **kw),
+            O.Conf(1., shape, mesh_shape=2, **kw))
+
+
+def test_configuration_validation_and_properties():
+    """configuration.py:148-196 (errors) and :198-320 (derived properties)."""
+    conf, oconf = _confs((4, 6, 8))
+    assert conf.mesh_shape == oconf.mesh_shape == (8, 12, 16)
+    assert conf.cell_size == oconf.cell_size and conf.ptcl_num == oconf.ptcl_num
+    assert conf.a_nbody_num == oconf.a_nbody_num == 63
+    np.testing.assert_array_equal(conf.a_nbody.numpy(), oconf.a_nbody)
+    np.testing.assert_array_equal(conf.growth_a.numpy(), oconf.growth_a)
+    np.testing.assert_allclose(conf.transfer_k.numpy(), oconf.transfer_k, rtol=0)
+    with pytest.raises(ValueError):
+        pm.Configuration(1., (4, 4, 4), mesh_shape=(8, 8), device='cpu')
+    with pytest.raises(ValueError):
+        pm.Configuration(1., (4, 4, 4), mesh_shape=(2, 2, 2), device='cpu')
+    with pytest.raises(ValueError):
+        pm.Configuration(1., (4, 4, 4), mesh_shape=(8, 8, 12), device='cpu')
+    with pytest.raises(ValueError):
+        pm.Configuration(1., (4, 4, 4), symp_splits=((0, 0.5), (1, 0.4)), device='cpu')
+    with pytest.raises(ValueError):
+        pm.Configuration(1., (4, 4, 4), float_dtype=torch.float64, device='cpu')
+    c2 = conf.replace(a_nbody_maxstep=0.1)
+    assert c2.a_nbody_num == 10 and conf.a_nbody_num == 63       # frozen, replace() copies
+
+
+def test_gen_grid_and_from_pos_match_oracle():
+    """particles.py:81-144: same pmid / disp as the oracle, incl. a non-integer mesh ratio."""
+    for shape, mesh in (((4, 4, 4), 2), ((4, 6, 8), 1.5)):
+        conf = pm.Configuration(1.3, shape, mesh_shape=mesh, device='cpu')
+        oconf = O.Conf(1.3, shape, mesh_shape=mesh)
+        p = pm.Particles.gen_grid(conf, vel=True)
+        opmid, odisp, _, _ = O.gen_grid(oconf)
+        assert p.pmid.dtype == torch.int16
+        np.testing.assert_array_equal(p.pmid.numpy(), opmid)
+        np.testing.assert_array_equal(p.disp.numpy(), odisp)
+        assert torch.all(p.vel == 0) and p.acc is None
+        pos = p.pos()
+        q = pm.Particles.from_pos(conf, pos)
+        np.testing.assert_allclose(q.pos().numpy(), pos.numpy(), atol=1e-6)
+
+
+def test_growth_and_transfer_tables_vs_oracle():
+    """boltzmann.py:32-229: Dopri5 @ sqrt(eps) (as the reference) vs scipy DOP853 @ 1e-11."""
+    conf, oconf = _confs()
+    cosmo = pm.boltzmann(pm.SimpleLCDM(conf), conf)
+    oc = O.boltzmann(O.SimpleLCDM(oconf), oconf)
+    assert np.abs(cosmo.growth.numpy() - oc.growth).max() < 1e-7
+    np.testing.assert_allclose(cosmo.transfer.numpy(), oc.transfer, rtol=1e-12)
+    k = np.array([0., 1e-3, 0.05, 0.7, 3.], dtype=np.float32)
+    np.testing.assert_allclose(pm.linear_power(torch.from_numpy(k), None, cosmo, conf).numpy(),
+                               O.linear_power(k, None, oc, oconf), rtol=2e-6)
+    for a in (1 / 64, 0.3, 1.0):
+        np.testing.assert_allclose(float(pm.E2(a, cosmo)), O.E2(a, oc), rtol=1e-14)
+        np.testing.assert_allclose(float(pm.H_deriv(a, cosmo)), O.H_deriv(a, oc), rtol=1e-12)
+        np.testing.assert_allclose(float(pm.Omega_m_a(a, cosmo)), O.Omega_m_a(a, oc), rtol=1e-14)
+
+
+def test_step_factors_and_gradients_vs_oracle():
+    """nbody.py:12-36 in float64: torch host code vs the NumPy/scipy oracle, and the autograd
+    factor gradients (replacing jax.value_and_grad, nbody.py:51-52,82-83) vs the oracle's
+    finite differences."""
+    from pmwd_b200.nbody import kick_factor, drift_factor, _factor_valgrad
+    conf, oconf = _confs()
+    cosmo = pm.boltzmann(pm.SimpleLCDM(conf), conf)
+    ocosmo = O.boltzmann(O.SimpleLCDM(oconf), oconf)
+    same = ocosmo.replace(growth=cosmo.growth.numpy())            # identical table
+    a = oconf.a_nbody
+    for i in (0, 10, 40, 62):
+        a0, a1 = a[i], a[i + 1]
+        am = 0.5 * (a0 + a1)
+        for fun, ofun, args in ((kick_factor, O.kick_factor, (a0, a0, am)),
+                                (drift_factor, O.drift_factor, (am, a0, a1)),
+                                (kick_factor, O.kick_factor, (a1, am, a1))):
+            val, grads = _factor_valgrad(fun, *args, cosmo, conf)
+            np.testing.assert_allclose(val, ofun(*args, same, oconf), rtol=1e-12)
+            np.testing.assert_allclose(val, ofun(*args, ocosmo, oconf), rtol=1e-5)
+            _, og = O.factor_grads(ofun, *args, same, oconf)
+            np.testing.assert_allclose(grads['Omega_m'].item(), og['Omega_m'], rtol=2e-5, atol=1e-9)
+            np.testing.assert_allclose(grads['growth'].numpy(), og['growth'], rtol=1e-5, atol=1e-9)
+
+
+def test_growth_table_gradient_vs_finite_difference():
+    """d(growth table)/d(Omega_m) by autograd through the Runge-Kutta steps vs central
+    differences of the oracle's independent ODE solve."""
+    conf, oconf = _confs()
+    Om = torch.tensor(0.3, dtype=torch.float64, requires_grad=True)
+    cosmo = pm.boltzmann(pm.SimpleLCDM(conf, Omega_m=Om), conf)
+    w = torch.from_numpy(np.random.default_rng(0).standard_normal(cosmo.growth.shape))
+    (g,) = torch.autograd.grad((cosmo.growth * w).sum(), Om)
+    h = 1e-5
+    gp = O.boltzmann(O.SimpleLCDM(oconf, Omega_m=0.3 + h), oconf).growth
+    gm = O.boltzmann(O.SimpleLCDM(oconf, Omega_m=0.3 - h), oconf).growth
+    fd = ((gp - gm) / (2 * h) * w.numpy()).sum()
+    np.testing.assert_allclose(g.item(), fd, rtol=1e-4)
+
+
+def test_no_cpu_path_for_kernels():
+    """CPU tensors are rejected by every kernel-backed API (there is no CPU fallback)."""
+    conf, _ = _confs()
+    ptcl = pm.Particles.gen_grid(conf, vel=True)
+    cosmo = pm.SimpleLCDM(conf)
+    for call in (lambda: pm.scatter(ptcl, conf),
+                 lambda: pm.gather(ptcl, conf, torch.zeros(conf.mesh_shape)),
+                 lambda: pm.gravity(1., ptcl, cosmo, conf),
+                 lambda: pm.nbody(ptcl, None, cosmo, conf),
+                 lambda: pm.lpt(torch.zeros((4, 4, 3), dtype=torch.complex64), cosmo, conf)):
+        with pytest.raises(PmwdError):
+            call()
