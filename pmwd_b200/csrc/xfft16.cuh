@@ -1,0 +1,174 @@
+// Register-resident FFT along x for the fused x-pass (xpass16.cu): NX = 16 * 16 * R3 with
+// R3 in {1, 2, 4}, i.e. NX in {256, 512, 1024}.
+//
+// A tile is T = 8 adjacent kz columns (64-byte row segments).  Thread (j, c), j in [0, NX/16),
+// c in [0, T), OWNS the 16 points  x = j + (NX/16) e,  e = 0..15  of column c, in registers,
+// before and after every transform (so loads, the k-space algebra and stores never touch shared
+// memory).  A transform is a Stockham autosort with radices 16, 16, R3:
+//     stage 1: 16-point DFT in registers               -> exchange through shared memory
+//     stage 2: twiddle, 16-point DFT in registers      -> exchange through shared memory
+//     stage 3: twiddle, 16/R3 R3-point DFTs in registers (in place: outputs are owned again)
+// Two exchanges (4 barriers) per transform instead of the 10 shared-memory passes of a radix-4
+// Stockham.  The exchange buffer rows are padded, phys(x) = x + (x >> 4), which makes every
+// access pattern below conflict-free for 64-bit words (half-warp = two rows of opposite parity).
+//
+// The phase functions are __host__ __device__ so that tests/host/xfft16_emul.cc can run the
+// index arithmetic thread by thread on the CPU against a naive DFT.
+#pragma once
+#include <vector_types.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define PMWD_HD __host__ __device__ __forceinline__
+#else
+#define PMWD_HD inline
+#endif
+
+namespace pmwd {
+namespace r16 {
+
+constexpr int T = 8;
+
+template <int NX>
+struct Cfg {
+  static_assert(NX == 256 || NX == 512 || NX == 1024, "NX = 256 * R3, R3 in {1,2,4}");
+  static constexpr int J = NX / 16;          // threads per column; x stride between owned points
+  static constexpr int R3 = NX / 256;        // radix of the last stage
+  static constexpr int M3 = 16 / R3;         // last-stage butterflies per thread
+  static constexpr int THREADS = J * T;
+  static constexpr int ROWS = NX + NX / 16;  // padded rows of the exchange buffer
+  static constexpr int ESTRIDE = (J + J / 16) * T;   // exchange-buffer distance between owned points
+};
+
+PMWD_HD float2 mk2(float x, float y) {
+  float2 r;
+  r.x = x;
+  r.y = y;
+  return r;
+}
+
+PMWD_HD float fma_(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+  return __fmaf_rn(a, b, c);
+#else
+  return fmaf(a, b, c);
+#endif
+}
+
+// a * (wx + i wy)
+PMWD_HD float2 cmulw(float2 a, float wx, float wy) {
+  return mk2(fma_(a.x, wx, -(a.y * wy)), fma_(a.x, wy, a.y * wx));
+}
+
+// 4-point DFT, natural order in and out; forward kernel exp(-2 pi i nk/4), inverse exp(+...)
+template <bool INV>
+PMWD_HD void dft4(float2& a0, float2& a1, float2& a2, float2& a3) {
+  const float2 s02 = mk2(a0.x + a2.x, a0.y + a2.y), d02 = mk2(a0.x - a2.x, a0.y - a2.y);
+  const float2 s13 = mk2(a1.x + a3.x, a1.y + a3.y), d13 = mk2(a1.x - a3.x, a1.y - a3.y);
+  // forward: -i d13 = (d13.y, -d13.x); inverse: +i d13 = (-d13.y, d13.x)
+  const float2 r = INV ? mk2(-d13.y, d13.x) : mk2(d13.y, -d13.x);
+  a0 = mk2(s02.x + s13.x, s02.y + s13.y);
+  a1 = mk2(d02.x + r.x, d02.y + r.y);
+  a2 = mk2(s02.x - s13.x, s02.y - s13.y);
+  a3 = mk2(d02.x - r.x, d02.y - r.y);
+}
+
+template <bool INV>
+PMWD_HD void dft2(float2& a0, float2& a1) {
+  const float2 s = mk2(a0.x + a1.x, a0.y + a1.y), d = mk2(a0.x - a1.x, a0.y - a1.y);
+  a0 = s;
+  a1 = d;
+}
+
+// 16-point DFT in registers, natural order in and out (n = 4 n1 + n2, k = k1 + 4 k2):
+//   B[n2][k1] = sum_n1 v[4 n1 + n2] w4^(n1 k1);  B *= w16^(n2 k1);  V[k1 + 4 k2] = sum_n2 B[n2][k1] w4^(n2 k2)
+template <bool INV>
+PMWD_HD void dft16(float2 (&v)[16]) {
+  constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, C2 = 0.70710678118654752f;
+  constexpr float sg = INV ? 1.f : -1.f;     // sign of the imaginary part of the twiddles
+#pragma unroll
+  for (int n2 = 0; n2 < 4; ++n2) dft4<INV>(v[n2], v[4 + n2], v[8 + n2], v[12 + n2]);
+  // now v[4 k1 + n2] = B[n2][k1]; twiddle w16^(n2 k1) = cos(pi m / 8) + i sg sin(pi m / 8), m = n2 k1
+  v[4 * 1 + 1] = cmulw(v[4 * 1 + 1], C1, sg * S1);     // m = 1
+  v[4 * 1 + 2] = cmulw(v[4 * 1 + 2], C2, sg * C2);     // m = 2
+  v[4 * 1 + 3] = cmulw(v[4 * 1 + 3], S1, sg * C1);     // m = 3
+  v[4 * 2 + 1] = cmulw(v[4 * 2 + 1], C2, sg * C2);     // m = 2
+  v[4 * 2 + 2] = INV ? mk2(-v[4 * 2 + 2].y, v[4 * 2 + 2].x) : mk2(v[4 * 2 + 2].y, -v[4 * 2 + 2].x);   // m = 4
+  v[4 * 2 + 3] = cmulw(v[4 * 2 + 3], -C2, sg * C2);    // m = 6
+  v[4 * 3 + 1] = cmulw(v[4 * 3 + 1], S1, sg * C1);     // m = 3
+  v[4 * 3 + 2] = cmulw(v[4 * 3 + 2], -C2, sg * C2);    // m = 6
+  v[4 * 3 + 3] = cmulw(v[4 * 3 + 3], -C1, -sg * S1);   // m = 9
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1) dft4<INV>(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
+  // v[4 k1 + k2] holds V[k1 + 4 k2]: transpose the 4x4 register file into natural order
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = a + 1; b < 4; ++b) {
+      const float2 t = v[4 * a + b];
+      v[4 * a + b] = v[4 * b + a];
+      v[4 * b + a] = t;
+    }
+}
+
+// ---- exchange buffer addressing (float2 index); rows padded: phys(x) = x + (x >> 4)
+template <int NX>
+PMWD_HD int ex_own(int j, int c) {            // owned point e lives at ex_own + e * ESTRIDE
+  return (j + (j >> 4)) * T + c;
+}
+template <int NX>
+PMWD_HD void ex_read(const float2* ex, int j, int c, float2 (&v)[16]) {
+  const float2* p = ex + ex_own<NX>(j, c);
+#pragma unroll
+  for (int e = 0; e < 16; ++e) v[e] = p[e * Cfg<NX>::ESTRIDE];
+}
+// stage 1 (radix 16, p = 1): output s of butterfly j goes to x = 16 j + s, phys = 17 j + s
+template <int NX>
+PMWD_HD void ex_write1(float2* ex, int j, int c, const float2 (&v)[16]) {
+  float2* p = ex + (17 * j) * T + c;
+#pragma unroll
+  for (int s = 0; s < 16; ++s) p[s * T] = v[s];
+}
+// stage 2 (radix 16, p = 16): k = j & 15, output s goes to x = 16 (j - k) + k + 16 s,
+// phys = 17 (j - k) + k + 17 s
+template <int NX>
+PMWD_HD void ex_write2(float2* ex, int j, int c, const float2 (&v)[16]) {
+  const int k = j & 15;
+  float2* p = ex + (17 * (j - k) + k) * T + c;
+#pragma unroll
+  for (int s = 0; s < 16; ++s) p[s * 17 * T] = v[s];
+}
+
+// tw[n] = exp(-2 pi i n / NX); stage 2 input r is multiplied by exp(-+2 pi i r k / 256)
+template <int NX, bool INV>
+PMWD_HD void twiddle2(float2 (&v)[16], const float2* tw, int j) {
+  const int k = j & 15;
+#pragma unroll
+  for (int r = 1; r < 16; ++r) {
+    const float2 w = tw[r * k * (NX / 256)];
+    v[r] = cmulw(v[r], w.x, INV ? -w.y : w.y);
+  }
+}
+
+// stage 3 (radix R3, p = 256): butterfly i = j + J m takes the owned points e = m + M3 r
+// (x = i + 256 r), twiddle exp(-+2 pi i r i / NX), and is in place
+template <int NX, bool INV>
+PMWD_HD void stage3(float2 (&v)[16], const float2* tw, int j) {
+  constexpr int R3 = Cfg<NX>::R3, M3 = Cfg<NX>::M3, J = Cfg<NX>::J;
+  if constexpr (R3 > 1) {
+#pragma unroll
+  for (int m = 0; m < M3; ++m) {
+    const int i = j + J * m;
+#pragma unroll
+    for (int r = 1; r < R3; ++r) {
+      const float2 w = tw[r * i];
+      v[m + M3 * r] = cmulw(v[m + M3 * r], w.x, INV ? -w.y : w.y);
+    }
+    if constexpr (R3 == 4) dft4<INV>(v[m], v[m + M3], v[m + 2 * M3], v[m + 3 * M3]);
+    if constexpr (R3 == 2) dft2<INV>(v[m], v[m + M3]);
+  }
+  }
+}
+
+}  // namespace r16
+}  // namespace pmwd

@@ -18,8 +18,10 @@
 // twiddles from a shared-memory table built in float64.  Works on the slab-decomposed
 // layout too (ny_l rows starting at global row y0).
 #include <cuda_pipeline.h>
+#include <stdlib.h>
 
 #include "common.cuh"
+#include "xpass.cuh"
 
 namespace pmwd {
 
@@ -51,23 +53,6 @@ struct XCfg {
   static constexpr bool HAS2 = (LOG2 & 1) != 0;
 };
 
-struct XParams {
-  int nx, ny_l, nzc;            // array extents
-  int ny_g, nz_g;               // global (real-space) sizes of axes 1, 2
-  int y0;                       // global index of local row 0
-  double period;                // 2 pi / spacing
-  float nyq, eps, scale;
-  const float2* in[3];
-  float2* out[3];
-};
-
-__device__ __forceinline__ float xkval(int i, int n, double period, bool last) {
-  int f = last ? i : (i < (n + 1) / 2 ? i : i - n);
-  return (float)(((double)f / (double)n) * period);
-}
-__device__ __forceinline__ bool xnyq(float k, float nyq, float eps) {
-  return fabsf(__fsub_rn(fabsf(k), nyq)) <= eps;
-}
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
@@ -387,6 +372,13 @@ int xpass_run(cudaStream_t st, const int32_t* shape, int y0, int ny_l, double sp
   const int nin = adjoint ? 3 : 1, nout = adjoint ? 1 : 3;
   for (int a = 0; a < nin; ++a) { PMWD_REQUIRE(in[a], "null input"); P.in[a] = (const float2*)in[a]; }
   for (int a = 0; a < nout; ++a) { PMWD_REQUIRE(out[a], "null output"); P.out[a] = (float2*)out[a]; }
+  // nx in {256, 512, 1024}: register-resident radix-16 transforms (xpass16.cu);
+  // PMWD_XPASS16=0 keeps the radix-4 shared-memory kernels below for comparison
+  static const bool use16 = [] {
+    const char* e = getenv("PMWD_XPASS16");
+    return !(e && e[0] == '0');
+  }();
+  if (use16 && xpass16_supported(shape[0])) return xpass16_launch(st, P, adjoint);
   switch (shape[0]) {
     case 64: return launch_x<64>(st, P, adjoint);
     case 128: return launch_x<128>(st, P, adjoint);

@@ -456,9 +456,11 @@ def test_full_gradient_pipeline():
     np.testing.assert_allclose(got, fd, rtol=2e-2)
 
 
-@pytest.mark.parametrize('shape', [(64, 8, 10), (128, 6, 9), (256, 4, 6), (512, 4, 4), (1024, 2, 4), (2048, 2, 4)])
+# the last three shapes have more tiles than resident CTAs (persistent loop + cp.async prefetch)
+@pytest.mark.parametrize('shape', [(64, 8, 10), (128, 6, 9), (256, 4, 6), (512, 4, 4), (1024, 2, 4), (2048, 2, 4),
+                                   (256, 80, 130), (512, 40, 130), (1024, 24, 130)])
 def test_fused_xpass_vs_cufft3d(shape):
-    """csrc/xpass.cu (shared-memory FFT along x fused with the k-space algebra) against the
+    """csrc/xpass.cu / xpass16.cu (on-chip FFT along x fused with the k-space algebra) against the
     plain pipeline cuFFT-3D -> pmwd_kspace_force(_adj) -> cuFFT-3D, forward and adjoint, incl. the
     y-slab form used after the distributed all-to-all.  Tolerance: 2e-6 of the field's rms."""
     import ctypes as C
