@@ -1,7 +1,8 @@
 // Register-resident FFT along x for the fused x-pass (xpass16.cu): NX = 16 * 16 * R3 with
 // R3 in {1, 2, 4}, i.e. NX in {256, 512, 1024}.
 //
-// A tile is T = 8 adjacent kz columns (64-byte row segments).  Thread (j, c), j in [0, NX/16),
+// One column per thread (first half of this file; the two-columns-per-thread form that
+// xpass16.cu uses is at the end): a tile is T = 8 adjacent columns.  Thread (j, c), j in [0, NX/16),
 // c in [0, T), OWNS the 16 points  x = j + (NX/16) e,  e = 0..15  of column c, in registers,
 // before and after every transform (so loads, the k-space algebra and stores never touch shared
 // memory).  A transform is a Stockham autosort with radices 16, 16, R3:
@@ -167,6 +168,79 @@ PMWD_HD void stage3(float2 (&v)[16], const float2* tw, int j) {
     if constexpr (R3 == 4) dft4<INV>(v[m], v[m + M3], v[m + 2 * M3], v[m + 3 * M3]);
     if constexpr (R3 == 2) dft2<INV>(v[m], v[m + M3]);
   }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Two adjacent columns per thread (a = column 2 cp, b = column 2 cp + 1): global accesses and the
+// exchange use 16-byte words (a, b), rows of TP = 8 pairs = 128 bytes.  A quarter-warp (8 lanes,
+// same j) reads or writes one whole 128-byte row, so every pattern is conflict-free without
+// padding.  The twiddles are loaded once for both columns.
+constexpr int TP = 8;
+
+PMWD_HD float4 pack4(float2 a, float2 b) {
+  float4 q;
+  q.x = a.x; q.y = a.y; q.z = b.x; q.w = b.y;
+  return q;
+}
+
+template <int NX>
+PMWD_HD void ex4_read(const float4* ex, int j, int cp, float2 (&a)[16], float2 (&b)[16]) {
+  const float4* p = ex + j * TP + cp;
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    const float4 q = p[e * Cfg<NX>::J * TP];
+    a[e] = mk2(q.x, q.y);
+    b[e] = mk2(q.z, q.w);
+  }
+}
+template <int NX>
+PMWD_HD void ex4_write1(float4* ex, int j, int cp, const float2 (&a)[16], const float2 (&b)[16]) {
+  float4* p = ex + (16 * j) * TP + cp;
+#pragma unroll
+  for (int s = 0; s < 16; ++s) p[s * TP] = pack4(a[s], b[s]);
+}
+template <int NX>
+PMWD_HD void ex4_write2(float4* ex, int j, int cp, const float2 (&a)[16], const float2 (&b)[16]) {
+  const int k = j & 15;
+  float4* p = ex + (16 * (j - k) + k) * TP + cp;
+#pragma unroll
+  for (int s = 0; s < 16; ++s) p[s * 16 * TP] = pack4(a[s], b[s]);
+}
+template <int NX, bool INV>
+PMWD_HD void twiddle2x2(float2 (&a)[16], float2 (&b)[16], const float2* tw, int j) {
+  const int k = j & 15;
+#pragma unroll
+  for (int r = 1; r < 16; ++r) {
+    const float2 w = tw[r * k * (NX / 256)];
+    const float wy = INV ? -w.y : w.y;
+    a[r] = cmulw(a[r], w.x, wy);
+    b[r] = cmulw(b[r], w.x, wy);
+  }
+}
+template <int NX, bool INV>
+PMWD_HD void stage3x2(float2 (&a)[16], float2 (&b)[16], const float2* tw, int j) {
+  constexpr int R3 = Cfg<NX>::R3, M3 = Cfg<NX>::M3, J = Cfg<NX>::J;
+  if constexpr (R3 > 1) {
+#pragma unroll
+    for (int m = 0; m < M3; ++m) {
+      const int i = j + J * m;
+#pragma unroll
+      for (int r = 1; r < R3; ++r) {
+        const float2 w = tw[r * i];
+        const float wy = INV ? -w.y : w.y;
+        a[m + M3 * r] = cmulw(a[m + M3 * r], w.x, wy);
+        b[m + M3 * r] = cmulw(b[m + M3 * r], w.x, wy);
+      }
+      if constexpr (R3 == 4) {
+        dft4<INV>(a[m], a[m + M3], a[m + 2 * M3], a[m + 3 * M3]);
+        dft4<INV>(b[m], b[m + M3], b[m + 2 * M3], b[m + 3 * M3]);
+      }
+      if constexpr (R3 == 2) {
+        dft2<INV>(a[m], a[m + M3]);
+        dft2<INV>(b[m], b[m + M3]);
+      }
+    }
   }
 }
 

@@ -378,7 +378,7 @@ int xpass_run(cudaStream_t st, const int32_t* shape, int y0, int ny_l, double sp
     const char* e = getenv("PMWD_XPASS16");
     return !(e && e[0] == '0');
   }();
-  if (use16 && xpass16_supported(shape[0])) return xpass16_launch(st, P, adjoint);
+  if (use16 && xpass16_supported(P, adjoint)) return xpass16_launch(st, P, adjoint);
   switch (shape[0]) {
     case 64: return launch_x<64>(st, P, adjoint);
     case 128: return launch_x<128>(st, P, adjoint);

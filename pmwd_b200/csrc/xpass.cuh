@@ -23,7 +23,7 @@ __device__ __forceinline__ bool xnyq(float k, float nyq, float eps) {
   return fabsf(__fsub_rn(fabsf(k), nyq)) <= eps;
 }
 // xpass16.cu
-bool xpass16_supported(int nx);
+bool xpass16_supported(const XParams& P, bool adjoint);
 int xpass16_launch(cudaStream_t st, const XParams& P, bool adjoint);
 
 }  // namespace pmwd

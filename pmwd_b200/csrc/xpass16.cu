@@ -2,15 +2,26 @@
 // (same math and interface as xpass.cu, see its header; gravity: pmwd/gravity.py:9-16,37-44,56-64,
 // its VJP: pmwd/nbody.py:108-118).
 //
-// The transforms along x keep 16 points per thread in registers (xfft16.cuh): radix 16 x 16 x R3
-// with two shared-memory exchanges per transform.  Global loads, the k-space algebra and the
-// stores work on the registers directly, because a thread owns the same 16 points before and
-// after every transform.  Two thread-private staging arrays in shared memory (slot e of thread t
-// at [e * THREADS + t], never shared between threads, so they need no barrier) hold
-//   forward:  A = next tile's spectrum (cp.async prefetch),  B = q = -i kx pot while P is transformed
-//   adjoint:  A = V_y, then FFT_x(V_x);  B = V_z, then next tile's V_x (cp.async prefetch)
-// Shared memory at nx = 1024: 68 KB exchange + 2 x 64 KB staging + 12 KB tables = 208 KB, one
-// 512-thread CTA per SM with up to 128 registers per thread.
+// Memory pattern first.  The x stride of data[nx][ny_l][nzc] is a whole plane (4.2 MB at 1024^3),
+// so a column tile is read and written as one short row segment per x.  Measured on B200
+// (tools/lab/xpattern.cu, 1 read + 3 write streams at 1024^3): 64-byte segments cap at 2.26 TB/s,
+// 128-byte segments issued as 16-byte words reach 3.9 TB/s.  So:
+//   * the (y, kz) plane is treated as a flat list of ny_l * nzc independent columns, tiled in
+//     runs of 16 columns = 128 bytes that are 128-byte ALIGNED in memory whatever nzc is
+//     (nzc = nz/2 + 1 is odd, per-row tiling would misalign every other row);
+//   * a thread owns TWO adjacent columns (one float4 per x) and 16 points of each, in registers:
+//     x = j + (nx/16) e, e = 0..15, before and after every transform (xfft16.cuh), so the loads,
+//     the k-space algebra and the stores work on registers, as 16-byte accesses;
+//   * the transforms are radix 16 x 16 x R3 with two shared-memory exchanges each; the two
+//     columns of a thread go through a one-column exchange buffer one after the other, which
+//     leaves room for
+//   * a tile-sized staging array in shared memory (thread-private 16-byte slots, no barrier
+//     needed).  It parks the one tile-sized temporary (q = -i kx pot while P is transformed;
+//     FFT_x(V_x) in the adjoint) and, once that has been read back, receives the NEXT tile's
+//     input by cp.async under the tile's last transform.  (Parking q in the G_x array instead
+//     cost 27 % of the kernel: the L2 re-read queued behind the tile's own 256 KB of stores.)
+// Shared memory at nx = 1024: 68 KB exchange + 128 KB staging + 12 KB tables; one 512-thread CTA
+// per SM with up to 128 registers per thread.
 #include <cuda_pipeline.h>
 
 #include "xfft16.cuh"
@@ -19,62 +30,73 @@
 namespace pmwd {
 
 using r16::Cfg;
+using r16::TP;
 
 template <int NX>
 struct K16 {
-  static constexpr int THREADS = Cfg<NX>::THREADS;
+  static constexpr int THREADS = Cfg<NX>::J * TP;
   static constexpr int CTAS = NX == 1024 ? 1 : NX == 512 ? 2 : 4;
-  static constexpr size_t SMEM = (size_t)Cfg<NX>::ROWS * r16::T * sizeof(float2) +
-                                 2 * (size_t)NX * r16::T * sizeof(float2) + (size_t)NX * sizeof(float2) +
-                                 (size_t)NX * sizeof(float);
+  static constexpr size_t EX = (size_t)Cfg<NX>::ROWS * TP * sizeof(float2);     // one-column exchange (padded rows)
+  static constexpr size_t STG = (size_t)NX * TP * sizeof(float4);              // [16][THREADS] staging slots
+  static constexpr size_t SMEM = EX + STG + (size_t)NX * sizeof(float2) + (size_t)NX * sizeof(float);
 };
 
+// Both columns of a thread through the one-column exchange buffer, a then b; the register
+// arithmetic of one column sits between the barriers of the other column's exchange.
 template <int NX, bool INV>
-__device__ __forceinline__ void fft16(float2 (&v)[16], float2* ex, const float2* tw, int j, int c) {
-  r16::dft16<INV>(v);
+__device__ __forceinline__ void fft16x2(float2 (&a)[16], float2 (&b)[16], float2* ex, const float2* tw, int j, int cp) {
+  r16::dft16<INV>(a);
   __syncthreads();                       // every earlier read of the exchange buffer is done
-  r16::ex_write1<NX>(ex, j, c, v);
+  r16::ex_write1<NX>(ex, j, cp, a);
+  r16::dft16<INV>(b);
   __syncthreads();
-  r16::ex_read<NX>(ex, j, c, v);
-  r16::twiddle2<NX, INV>(v, tw, j);
-  r16::dft16<INV>(v);
+  r16::ex_read<NX>(ex, j, cp, a);
   __syncthreads();
-  r16::ex_write2<NX>(ex, j, c, v);
+  r16::ex_write1<NX>(ex, j, cp, b);
+  r16::twiddle2<NX, INV>(a, tw, j);
+  r16::dft16<INV>(a);
   __syncthreads();
-  r16::ex_read<NX>(ex, j, c, v);
-  r16::stage3<NX, INV>(v, tw, j);
+  r16::ex_read<NX>(ex, j, cp, b);
+  __syncthreads();
+  r16::ex_write2<NX>(ex, j, cp, a);
+  r16::twiddle2<NX, INV>(b, tw, j);
+  r16::dft16<INV>(b);
+  __syncthreads();
+  r16::ex_read<NX>(ex, j, cp, a);
+  __syncthreads();
+  r16::ex_write2<NX>(ex, j, cp, b);
+  r16::stage3<NX, INV>(a, tw, j);
+  __syncthreads();
+  r16::ex_read<NX>(ex, j, cp, b);
+  r16::stage3<NX, INV>(b, tw, j);
 }
 
-struct Tile {
-  int iy, kz0;
-  bool live;
-  int64_t col;
-};
-
-__device__ __forceinline__ Tile tile_of(const XParams& P, int64_t tile, int ztiles, int c) {
-  Tile t;
-  t.iy = (int)(tile / ztiles);
-  t.kz0 = (int)(tile - (int64_t)t.iy * ztiles) * r16::T;
-  t.live = t.kz0 + c < P.nzc;
-  t.col = (int64_t)t.iy * P.nzc + t.kz0 + c;
-  return t;
-}
-
-// cp.async this thread's 16 points of `src` for tile t into its private staging slots
+// cp.async this thread's 16 float4 words (two columns x 16 points) of `src` into its staging slots
 template <int NX>
-__device__ __forceinline__ void stage_in(float2* st, const float2* src, const Tile& t, int j, int64_t plane) {
-  if (t.live) {
-    const float2* g = src + (int64_t)j * plane + t.col;
+__device__ __forceinline__ void stage_in(float4* mine, const float2* src, int64_t g0, int64_t plane, bool live) {
+  if (live) {
 #pragma unroll
     for (int e = 0; e < 16; ++e)
-      __pipeline_memcpy_async(st + e * Cfg<NX>::THREADS + threadIdx.x, g + (int64_t)(Cfg<NX>::J * e) * plane,
-                              sizeof(float2));
+      __pipeline_memcpy_async(mine + e * K16<NX>::THREADS, src + g0 + (int64_t)(Cfg<NX>::J * e) * plane, sizeof(float4));
   }
+}
+
+// wavenumbers of flat column m = iy * nzc + kz (m < ny_l * nzc fits 32 bits)
+struct ColK {
+  float ky, kz;
+};
+__device__ __forceinline__ ColK col_k(const XParams& P, unsigned m) {
+  const unsigned iy = m / (unsigned)P.nzc;
+  const unsigned iz = m - iy * (unsigned)P.nzc;
+  ColK k;
+  k.ky = xkval((int)iy + P.y0, P.ny_g, P.period, false);
+  k.kz = xkval((int)iz, P.nz_g, P.period, true);
+  return k;
 }
 
 template <int NX>
 __device__ __forceinline__ void build_tables16(const XParams& P, float2* tw, float* kx) {
-  for (int n = threadIdx.x; n < NX; n += Cfg<NX>::THREADS) {
+  for (int n = threadIdx.x; n < NX; n += K16<NX>::THREADS) {
     double s, c;
     sincospi(-2.0 * (double)n / (double)NX, &s, &c);
     tw[n] = make_float2((float)c, (float)s);
@@ -82,80 +104,107 @@ __device__ __forceinline__ void build_tables16(const XParams& P, float2* tw, flo
   }
 }
 
+__device__ __forceinline__ float ksq_of(float k0, float ky, float kz) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(k0, k0), __fmul_rn(ky, ky)), __fmul_rn(kz, kz));
+}
+// -scale / k^2 (0 at k = 0): one reciprocal per mode; the transforms around it are accurate to
+// ~1e-7 relative anyway, so the correctly rounded quotient of the standalone k-space kernel
+// (kspace.cu, bit-exact with the oracle) would buy nothing here
+__device__ __forceinline__ float green_of(float ksq, float scale) {
+  return ksq != 0.f ? -scale * __frcp_rn(ksq) : 0.f;
+}
+// -i k p, zero on a Nyquist plane
+__device__ __forceinline__ float2 neg_ik(float k, bool zero, float2 p) {
+  return zero ? make_float2(0.f, 0.f) : make_float2(__fmul_rn(k, p.y), -__fmul_rn(k, p.x));
+}
+
+// Schedule of one tile (both kernels): the staging slots hold this tile's input (prefetched
+// during the previous tile's last transform), then the parked temporary, then -- as soon as
+// that has been read back -- the next tile's input, streaming in under the last transform.
+// No global load ever has to be waited for behind the tile's own stores.
+
 // -------------------------------------------------------------------------- forward force
 template <int NX>
 __global__ void __launch_bounds__(K16<NX>::THREADS, K16<NX>::CTAS) xr16_force_kernel(XParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int XT = r16::T, THREADS = Cfg<NX>::THREADS, J = Cfg<NX>::J;
-  float2* ex = reinterpret_cast<float2*>(smem_raw);              // [ROWS][T]  exchange buffer
-  float2* stA = ex + Cfg<NX>::ROWS * XT;                          // [16][THREADS]  next tile's input
-  float2* stB = stA + NX * XT;                                    // [16][THREADS]  q
-  float2* tw = stB + NX * XT;                                     // [NX]
+  constexpr int J = Cfg<NX>::J, THREADS = K16<NX>::THREADS;
+  float2* ex = reinterpret_cast<float2*>(smem_raw);               // [ROWS][TP]  one-column exchange buffer
+  float4* stg = reinterpret_cast<float4*>(smem_raw + K16<NX>::EX); // [16][THREADS]  staging slots
+  float2* tw = reinterpret_cast<float2*>(stg + NX * TP);          // [NX]
   float* kx = reinterpret_cast<float*>(tw + NX);                  // [NX]
   build_tables16<NX>(P, tw, kx);
 
-  const int ztiles = (P.nzc + XT - 1) / XT;
-  const int64_t ntiles = (int64_t)P.ny_l * ztiles;
-  const int c = threadIdx.x % XT;
-  const int j = threadIdx.x / XT;
-  const int64_t plane = (int64_t)P.ny_l * P.nzc;
-  float2* mineA = stA + threadIdx.x;
-  float2* mineB = stB + threadIdx.x;
+  const int64_t plane = (int64_t)P.ny_l * P.nzc;                  // columns; even (checked by the host)
+  const int64_t ntiles = (plane + 2 * TP - 1) / (2 * TP);
+  const int cp = threadIdx.x % TP;
+  const int j = threadIdx.x / TP;
+  float4* mine = stg + threadIdx.x;
 
-  if ((int64_t)blockIdx.x < ntiles) stage_in<NX>(stA, P.in[0], tile_of(P, blockIdx.x, ztiles, c), j, plane);
-  __pipeline_commit();
+  {
+    const int64_t m = (int64_t)blockIdx.x * (2 * TP) + 2 * cp;
+    stage_in<NX>(mine, P.in[0], (int64_t)j * plane + m, plane, m < plane);
+    __pipeline_commit();
+  }
   __syncthreads();                                                // tables
 
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const Tile t = tile_of(P, tile, ztiles, c);
-    const float ky = xkval(t.iy + P.y0, P.ny_g, P.period, false);
-    const float kz = xkval(t.kz0 + c, P.nz_g, P.period, true);
+    const int64_t m = tile * (2 * TP) + 2 * cp;                   // this thread's columns m, m + 1
+    const bool live = m < plane;
+    const ColK ka = col_k(P, live ? (unsigned)m : 0u), kb = col_k(P, live ? (unsigned)m + 1u : 0u);
+    const int64_t g0 = (int64_t)j * plane + m;                    // float2 index of (x = j, column m)
 
-    float2 v[16];
+    float2 a[16], b[16];
     __pipeline_wait_prior(0);
 #pragma unroll
-    for (int e = 0; e < 16; ++e) v[e] = t.live ? mineA[e * THREADS] : make_float2(0.f, 0.f);
-    if (tile + gridDim.x < ntiles) stage_in<NX>(stA, P.in[0], tile_of(P, tile + gridDim.x, ztiles, c), j, plane);
-    __pipeline_commit();
+    for (int e = 0; e < 16; ++e) {
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live) q = mine[e * THREADS];
+      a[e] = make_float2(q.x, q.y);
+      b[e] = make_float2(q.z, q.w);
+    }
+    fft16x2<NX, false>(a, b, ex, tw, j, cp);
 
-    fft16<NX, false>(v, ex, tw, j, c);
-
-    // ---- pot = -(scale S)/k^2 stays in registers; q = -i kx pot is parked in staging B
+    // ---- pot = -(scale S)/k^2 stays in registers; q = -i kx pot is parked in the staging slots
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
       const float k0 = kx[j + J * e];
-      const float ksq = __fadd_rn(__fadd_rn(__fmul_rn(k0, k0), __fmul_rn(ky, ky)), __fmul_rn(kz, kz));
-      const float2 s = v[e];
-      float2 pot = make_float2(0.f, 0.f);
-      if (ksq != 0.f)
-        pot = make_float2(__fdiv_rn(-__fmul_rn(P.scale, s.x), ksq), __fdiv_rn(-__fmul_rn(P.scale, s.y), ksq));
-      v[e] = pot;
-      mineB[e * THREADS] = xnyq(k0, P.nyq, P.eps) ? make_float2(0.f, 0.f)
-                                                 : make_float2(__fmul_rn(k0, pot.y), -__fmul_rn(k0, pot.x));
+      const bool zx = xnyq(k0, P.nyq, P.eps);
+      const float ga = green_of(ksq_of(k0, ka.ky, ka.kz), P.scale), gb = green_of(ksq_of(k0, kb.ky, kb.kz), P.scale);
+      a[e] = make_float2(a[e].x * ga, a[e].y * ga);
+      b[e] = make_float2(b[e].x * gb, b[e].y * gb);
+      mine[e * THREADS] = r16::pack4(neg_ik(k0, zx, a[e]), neg_ik(k0, zx, b[e]));
     }
 
     // ---- P = IFFT_x(pot): G_y = -i ky P, G_z = -i kz P
-    fft16<NX, true>(v, ex, tw, j, c);
-    if (t.live) {
-      const bool zy = xnyq(ky, P.nyq, P.eps), zz = xnyq(kz, P.nyq, P.eps);
-      const int64_t g0 = (int64_t)j * plane + t.col;
+    fft16x2<NX, true>(a, b, ex, tw, j, cp);
+    if (live) {
+      const bool zya = xnyq(ka.ky, P.nyq, P.eps), zza = xnyq(ka.kz, P.nyq, P.eps);
+      const bool zyb = xnyq(kb.ky, P.nyq, P.eps), zzb = xnyq(kb.kz, P.nyq, P.eps);
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
         const int64_t g = g0 + (int64_t)(J * e) * plane;
-        const float2 p = v[e];
-        __stcs(P.out[1] + g, zy ? make_float2(0.f, 0.f) : make_float2(__fmul_rn(ky, p.y), -__fmul_rn(ky, p.x)));
-        __stcs(P.out[2] + g, zz ? make_float2(0.f, 0.f) : make_float2(__fmul_rn(kz, p.y), -__fmul_rn(kz, p.x)));
+        __stcs(reinterpret_cast<float4*>(P.out[1] + g), r16::pack4(neg_ik(ka.ky, zya, a[e]), neg_ik(kb.ky, zyb, b[e])));
+        __stcs(reinterpret_cast<float4*>(P.out[2] + g), r16::pack4(neg_ik(ka.kz, zza, a[e]), neg_ik(kb.kz, zzb, b[e])));
       }
     }
 
-    // ---- G_x = IFFT_x(q)
+    // ---- G_x = IFFT_x(q); the next tile's spectrum streams into the freed slots meanwhile
 #pragma unroll
-    for (int e = 0; e < 16; ++e) v[e] = mineB[e * THREADS];
-    fft16<NX, true>(v, ex, tw, j, c);
-    if (t.live) {
-      const int64_t g0 = (int64_t)j * plane + t.col;
+    for (int e = 0; e < 16; ++e) {
+      const float4 q = mine[e * THREADS];
+      a[e] = make_float2(q.x, q.y);
+      b[e] = make_float2(q.z, q.w);
+    }
+    {
+      const int64_t mn = m + (int64_t)gridDim.x * (2 * TP);       // same columns of this CTA's next tile
+      stage_in<NX>(mine, P.in[0], (int64_t)j * plane + mn, plane, mn < plane);
+      __pipeline_commit();
+    }
+    fft16x2<NX, true>(a, b, ex, tw, j, cp);
+    if (live) {
 #pragma unroll
-      for (int e = 0; e < 16; ++e) __stcs(P.out[0] + g0 + (int64_t)(J * e) * plane, v[e]);
+      for (int e = 0; e < 16; ++e)
+        __stcs(reinterpret_cast<float4*>(P.out[0] + g0 + (int64_t)(J * e) * plane), r16::pack4(a[e], b[e]));
     }
   }
   __pipeline_wait_prior(0);
@@ -165,76 +214,82 @@ __global__ void __launch_bounds__(K16<NX>::THREADS, K16<NX>::CTAS) xr16_force_ke
 template <int NX>
 __global__ void __launch_bounds__(K16<NX>::THREADS, K16<NX>::CTAS) xr16_force_adj_kernel(XParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int XT = r16::T, THREADS = Cfg<NX>::THREADS, J = Cfg<NX>::J;
+  constexpr int J = Cfg<NX>::J, THREADS = K16<NX>::THREADS;
   float2* ex = reinterpret_cast<float2*>(smem_raw);
-  float2* stA = ex + Cfg<NX>::ROWS * XT;                          // V_y, then FFT_x(V_x)
-  float2* stB = stA + NX * XT;                                    // V_z, then the next tile's V_x
-  float2* tw = stB + NX * XT;
+  float4* stg = reinterpret_cast<float4*>(smem_raw + K16<NX>::EX); // V_x, then FFT_x(V_x), then the next tile's V_x
+  float2* tw = reinterpret_cast<float2*>(stg + NX * TP);
   float* kx = reinterpret_cast<float*>(tw + NX);
   build_tables16<NX>(P, tw, kx);
 
-  const int ztiles = (P.nzc + XT - 1) / XT;
-  const int64_t ntiles = (int64_t)P.ny_l * ztiles;
-  const int c = threadIdx.x % XT;
-  const int j = threadIdx.x / XT;
   const int64_t plane = (int64_t)P.ny_l * P.nzc;
-  float2* mineA = stA + threadIdx.x;
-  float2* mineB = stB + threadIdx.x;
+  const int64_t ntiles = (plane + 2 * TP - 1) / (2 * TP);
+  const int cp = threadIdx.x % TP;
+  const int j = threadIdx.x / TP;
+  float4* mine = stg + threadIdx.x;
 
-  if ((int64_t)blockIdx.x < ntiles) stage_in<NX>(stB, P.in[0], tile_of(P, blockIdx.x, ztiles, c), j, plane);
-  __pipeline_commit();
+  {
+    const int64_t m = (int64_t)blockIdx.x * (2 * TP) + 2 * cp;
+    stage_in<NX>(mine, P.in[0], (int64_t)j * plane + m, plane, m < plane);
+    __pipeline_commit();
+  }
   __syncthreads();                                                // tables
 
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const Tile t = tile_of(P, tile, ztiles, c);
-    const float ky = xkval(t.iy + P.y0, P.ny_g, P.period, false);
-    const float kz = xkval(t.kz0 + c, P.nz_g, P.period, true);
-    const float kym = xnyq(ky, P.nyq, P.eps) ? 0.f : ky;
-    const float kzm = xnyq(kz, P.nyq, P.eps) ? 0.f : kz;
+    const int64_t m = tile * (2 * TP) + 2 * cp;
+    const bool live = m < plane;
+    const ColK ka = col_k(P, live ? (unsigned)m : 0u), kb = col_k(P, live ? (unsigned)m + 1u : 0u);
+    const float kyma = xnyq(ka.ky, P.nyq, P.eps) ? 0.f : ka.ky, kzma = xnyq(ka.kz, P.nyq, P.eps) ? 0.f : ka.kz;
+    const float kymb = xnyq(kb.ky, P.nyq, P.eps) ? 0.f : kb.ky, kzmb = xnyq(kb.kz, P.nyq, P.eps) ? 0.f : kb.kz;
+    const int64_t g0 = (int64_t)j * plane + m;
 
-    // ---- FFT_x(V_x) while V_y, V_z stream into the staging arrays
-    float2 v[16];
-    __pipeline_wait_prior(0);
-#pragma unroll
-    for (int e = 0; e < 16; ++e) v[e] = t.live ? mineB[e * THREADS] : make_float2(0.f, 0.f);
-    stage_in<NX>(stA, P.in[1], t, j, plane);
-    stage_in<NX>(stB, P.in[2], t, j, plane);
-    __pipeline_commit();
-    fft16<NX, false>(v, ex, tw, j, c);
-
-    // ---- W = i ky V_y + i kz V_z (ky, kz constant along x); FFT_x(V_x) is parked in staging A
+    // ---- FFT_x(V_x), parked in the staging slots
+    float2 a[16], b[16];
     __pipeline_wait_prior(0);
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
-      float2 w = make_float2(0.f, 0.f);
-      if (t.live) {
-        const float2 vy = mineA[e * THREADS], vz = mineB[e * THREADS];
-        w = make_float2(-(kym * vy.y) - kzm * vz.y, kym * vy.x + kzm * vz.x);
-      }
-      mineA[e * THREADS] = v[e];
-      v[e] = w;
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live) q = mine[e * THREADS];
+      a[e] = make_float2(q.x, q.y);
+      b[e] = make_float2(q.z, q.w);
     }
-    if (tile + gridDim.x < ntiles) stage_in<NX>(stB, P.in[0], tile_of(P, tile + gridDim.x, ztiles, c), j, plane);
-    __pipeline_commit();
-    fft16<NX, false>(v, ex, tw, j, c);
+    fft16x2<NX, false>(a, b, ex, tw, j, cp);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) mine[e * THREADS] = r16::pack4(a[e], b[e]);
 
-    // ---- S = (FFT(W) + i kx FFT(V_x)) * (-scale / k^2)
+    // ---- W = i ky V_y + i kz V_z (ky, kz constant along x), FFT_x(W)
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      float4 vy = make_float4(0.f, 0.f, 0.f, 0.f), vz = vy;
+      if (live) {
+        const int64_t g = g0 + (int64_t)(J * e) * plane;
+        vy = __ldcs(reinterpret_cast<const float4*>(P.in[1] + g));
+        vz = __ldcs(reinterpret_cast<const float4*>(P.in[2] + g));
+      }
+      a[e] = make_float2(-(kyma * vy.y) - kzma * vz.y, kyma * vy.x + kzma * vz.x);
+      b[e] = make_float2(-(kymb * vy.w) - kzmb * vz.w, kymb * vy.z + kzmb * vz.z);
+    }
+    fft16x2<NX, false>(a, b, ex, tw, j, cp);
+
+    // ---- S = (FFT(W) + i kx FFT(V_x)) * (-scale / k^2); then the next tile's V_x streams in
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
       const float k0 = kx[j + J * e];
       const float k0m = xnyq(k0, P.nyq, P.eps) ? 0.f : k0;
-      const float ksq = __fadd_rn(__fadd_rn(__fmul_rn(k0, k0), __fmul_rn(ky, ky)), __fmul_rn(kz, kz));
-      const float2 w = v[e], sx = mineA[e * THREADS];
-      const float2 tt = make_float2(w.x - k0m * sx.y, w.y + k0m * sx.x);
-      float2 s = make_float2(0.f, 0.f);
-      if (ksq != 0.f) s = make_float2(__fdiv_rn(-(P.scale * tt.x), ksq), __fdiv_rn(-(P.scale * tt.y), ksq));
-      v[e] = s;
+      const float4 sx = mine[e * THREADS];
+      const float ga = green_of(ksq_of(k0, ka.ky, ka.kz), P.scale), gb = green_of(ksq_of(k0, kb.ky, kb.kz), P.scale);
+      a[e] = make_float2((a[e].x - k0m * sx.y) * ga, (a[e].y + k0m * sx.x) * ga);
+      b[e] = make_float2((b[e].x - k0m * sx.w) * gb, (b[e].y + k0m * sx.z) * gb);
     }
-    fft16<NX, true>(v, ex, tw, j, c);
-    if (t.live) {
-      const int64_t g0 = (int64_t)j * plane + t.col;
+    {
+      const int64_t mn = m + (int64_t)gridDim.x * (2 * TP);
+      stage_in<NX>(mine, P.in[0], (int64_t)j * plane + mn, plane, mn < plane);
+      __pipeline_commit();
+    }
+    fft16x2<NX, true>(a, b, ex, tw, j, cp);
+    if (live) {
 #pragma unroll
-      for (int e = 0; e < 16; ++e) __stcs(P.out[0] + g0 + (int64_t)(J * e) * plane, v[e]);
+      for (int e = 0; e < 16; ++e)
+        __stcs(reinterpret_cast<float4*>(P.out[0] + g0 + (int64_t)(J * e) * plane), r16::pack4(a[e], b[e]));
     }
   }
   __pipeline_wait_prior(0);
@@ -242,8 +297,8 @@ __global__ void __launch_bounds__(K16<NX>::THREADS, K16<NX>::CTAS) xr16_force_ad
 
 template <int NX>
 static int launch16(cudaStream_t st, const XParams& P, bool adjoint) {
-  const int ztiles = (P.nzc + r16::T - 1) / r16::T;
-  const int64_t ntiles = (int64_t)P.ny_l * ztiles;
+  const int64_t plane = (int64_t)P.ny_l * P.nzc;
+  const int64_t ntiles = (plane + 2 * TP - 1) / (2 * TP);
   const int64_t cap = (int64_t)sm_count() * K16<NX>::CTAS;
   const int grid = (int)(ntiles < cap ? ntiles : cap);
   const int smem = (int)K16<NX>::SMEM;
@@ -258,7 +313,17 @@ static int launch16(cudaStream_t st, const XParams& P, bool adjoint) {
   return PMWD_OK;
 }
 
-bool xpass16_supported(int nx) { return nx == 256 || nx == 512 || nx == 1024; }
+// 16-byte accesses need an even number of columns per x plane and 16-byte aligned arrays
+bool xpass16_supported(const XParams& P, bool adjoint) {
+  if (!(P.nx == 256 || P.nx == 512 || P.nx == 1024)) return false;
+  if ((((int64_t)P.ny_l * P.nzc) & 1) != 0) return false;
+  const int nin = adjoint ? 3 : 1, nout = adjoint ? 1 : 3;
+  for (int i = 0; i < nin; ++i)
+    if ((uintptr_t)P.in[i] % 16 != 0) return false;
+  for (int i = 0; i < nout; ++i)
+    if ((uintptr_t)P.out[i] % 16 != 0) return false;
+  return true;
+}
 
 int xpass16_launch(cudaStream_t st, const XParams& P, bool adjoint) {
   switch (P.nx) {

@@ -80,6 +80,52 @@ static double run() {
   return std::sqrt(err2 / ref2);
 }
 
+// two columns per thread, 16-byte exchange words (the form xpass16.cu uses)
+template <int NX, bool INV>
+static double run2() {
+  using C = Cfg<NX>;
+  const int NT = C::J * TP, NC = 2 * TP;
+  std::vector<float2> tw(NX);
+  for (int n = 0; n < NX; ++n) {
+    const double a = -2.0 * M_PI * n / NX;
+    tw[n] = mk2((float)std::cos(a), (float)std::sin(a));
+  }
+  std::vector<std::complex<double>> in((size_t)NX * NC);
+  for (auto& z : in) z = {drand48() - 0.5, drand48() - 0.5};
+  std::vector<float2[16]> ra(NT), rb(NT);
+  for (int t = 0; t < NT; ++t) {
+    const int cp = t % TP, j = t / TP;
+    for (int e = 0; e < 16; ++e) {
+      const auto za = in[(size_t)(j + C::J * e) * NC + 2 * cp], zb = in[(size_t)(j + C::J * e) * NC + 2 * cp + 1];
+      ra[t][e] = mk2((float)za.real(), (float)za.imag());
+      rb[t][e] = mk2((float)zb.real(), (float)zb.imag());
+    }
+  }
+  float4 poison; poison.x = poison.y = poison.z = poison.w = NAN;
+  std::vector<float4> ex((size_t)NX * TP, poison);
+  for (int t = 0; t < NT; ++t) { dft16<INV>(ra[t]); dft16<INV>(rb[t]); }
+  for (int t = 0; t < NT; ++t) ex4_write1<NX>(ex.data(), t / TP, t % TP, ra[t], rb[t]);
+  for (int t = 0; t < NT; ++t) { ex4_read<NX>(ex.data(), t / TP, t % TP, ra[t], rb[t]); twiddle2x2<NX, INV>(ra[t], rb[t], tw.data(), t / TP); }
+  std::fill(ex.begin(), ex.end(), poison);
+  for (int t = 0; t < NT; ++t) { dft16<INV>(ra[t]); dft16<INV>(rb[t]); }
+  for (int t = 0; t < NT; ++t) ex4_write2<NX>(ex.data(), t / TP, t % TP, ra[t], rb[t]);
+  for (int t = 0; t < NT; ++t) { ex4_read<NX>(ex.data(), t / TP, t % TP, ra[t], rb[t]); stage3x2<NX, INV>(ra[t], rb[t], tw.data(), t / TP); }
+  double err2 = 0, ref2 = 0;
+  for (int c = 0; c < NC; ++c)
+    for (int k = 0; k < NX; ++k) {
+      std::complex<double> acc = 0;
+      for (int n = 0; n < NX; ++n) {
+        const double a = (INV ? 2.0 : -2.0) * M_PI * (double)((long)n * k % NX) / NX;
+        acc += in[(size_t)n * NC + c] * std::complex<double>(std::cos(a), std::sin(a));
+      }
+      const int j = k % C::J, e = k / C::J, t = j * TP + c / 2;
+      const float2 g = (c & 1) ? rb[t][e] : ra[t][e];
+      err2 += std::norm(acc - std::complex<double>(g.x, g.y));
+      ref2 += std::norm(acc);
+    }
+  return std::sqrt(err2 / ref2);
+}
+
 // bank-conflict model for 64-bit shared accesses: a half-warp (16 lanes) is one wavefront if
 // its 16 words fall in 16 distinct 8-byte bank pairs (word index mod 16)
 template <int NX>
@@ -111,6 +157,10 @@ int main() {
   e = run<512, true>(); std::printf("NX=512 inv rel err %.3g\n", e); worst = std::fmax(worst, e);
   e = run<1024, false>(); std::printf("NX=1024 fwd rel err %.3g\n", e); worst = std::fmax(worst, e);
   e = run<1024, true>(); std::printf("NX=1024 inv rel err %.3g\n", e); worst = std::fmax(worst, e);
+  e = run2<256, false>(); std::printf("NX=256 x2 fwd rel err %.3g\n", e); worst = std::fmax(worst, e);
+  e = run2<512, true>(); std::printf("NX=512 x2 inv rel err %.3g\n", e); worst = std::fmax(worst, e);
+  e = run2<1024, false>(); std::printf("NX=1024 x2 fwd rel err %.3g\n", e); worst = std::fmax(worst, e);
+  e = run2<1024, true>(); std::printf("NX=1024 x2 inv rel err %.3g\n", e); worst = std::fmax(worst, e);
   const int bc = conflicts<256>() + conflicts<512>() + conflicts<1024>();
   std::printf("bank conflicts (64-bit half-warp model): %d\n", bc);
   if (!(worst < 1e-6) || bc != 0) { std::printf("FAIL\n"); return 1; }

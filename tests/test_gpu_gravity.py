@@ -493,8 +493,14 @@ def test_fused_xpass_vs_cufft3d(shape):
     outs = [torch.empty_like(s2s) for _ in range(3)]
     arr = (C.c_void_p * 3)(*[t.data_ptr() for t in outs])
     _lib.check(lib.pmwd_xpass_force(st, shp, y0, nyl, cell, scale, _lib.ptr(s2s), arr), 'xpass slab')
+    nzc = nz // 2 + 1
+    same_kernel = nx not in (256, 512, 1024) or (nyl * nzc) % 2 == (ny * nzc) % 2
     for a in range(3):
-        assert torch.equal(outs[a], out[a][:, y0:y0 + nyl])
+        if same_kernel:     # per-column arithmetic does not depend on the slab
+            assert torch.equal(outs[a], out[a][:, y0:y0 + nyl])
+        else:               # odd column count: the slab falls back to the radix-4 kernel
+            d = (outs[a] - out[a][:, y0:y0 + nyl]).abs().max().item()
+            assert d <= 1e-5 * out[a].abs().max().item()
     # adjoint: three inputs -> one output
     V = [torch.randn(shape, device='cuda', generator=g) for _ in range(3)]
     Vk = [torch.fft.rfftn(v).contiguous() for v in V]
