@@ -188,7 +188,7 @@ int pmwd_kspace_force_adj_slab(void* stream, const int32_t* shape, int y0, int n
  * (y, z));  adjoint: v2d[0..2] -> out2d.  `shape` is the GLOBAL mesh shape, nx in
  * {64..2048} powers of two (pmwd_xpass_supported).  Replaces gravity.py:56-64's
  * rfftn-x / laplace / neg_grad / irfftn-x chain. */
-/* The output arrays must not overlap the inputs (out2d_c64 / g2d_c64[0] also serve as tile scratch). */
+/* The output arrays must not overlap the inputs. */
 int pmwd_xpass_supported(int nx);
 int pmwd_xpass_force(void* stream, const int32_t* shape, int y0, int ny_local, double spacing,
                      float scale, const void* rho2d_c64, void* const* g2d_c64);

@@ -9,7 +9,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base dem
     -k regex:'pmwd|fft|Radix|radix' -c 2500 --csv --log-file gpurun_out/launches_${TAG}.csv $BENCH \
     > gpurun_out/launches_${TAG}.bench.log 2>&1
 # full captures of the top hand-written kernels, late in the run (-s skips earlier launches)
-for K in xfused_force_kernel scatter_fast_kernel gather3_kernel kick_drift_kernel; do
+# (the x-pass kernel is data independent: capture it alone, `ncu --set full ... python tools/time_xpass.py 1024`)
+for K in scatter_fast_kernel gather3_kernel kick_drift_kernel; do
   ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
       -k regex:$K -s 45 -c 1 -o gpurun_out/prof_${K}_${TAG} -f $BENCH --steps 47 \
       > gpurun_out/prof_${K}_${TAG}.log 2>&1
