@@ -15,8 +15,9 @@ Gaussian field (seed 0), so with the defaults (W=3, K=60) the timed region is th
              outputs are inside the timed region, every step.
 `roofline`   dominant hand-written kernel: algorithmic bytes / CUDA-event time, vs the measured
              HBM copy bandwidth (MEASURED_PEAKS.json).  `kernels` lists every stage.
-`cpu_baseline`  the NumPy oracle (a port of the reference algorithm) on the host cores, on a
-             bounded sample of the same workload.
+`cpu_baseline`  the oracle's compiled port of the reference algorithm (oracle/cpm.c: C + OpenMP
+             CIC / k-space / kick-drift loops, scipy pocketfft FFTs, all host cores) on a bounded
+             sample of the same workload; the NumPy oracle if the C library cannot be built.
 `--impl reference`  times that CPU implementation as the reference arm.
 """
 import argparse
@@ -92,30 +93,48 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU oracle arm
+def cpu_port():
+    """The CPU implementation that is timed: (step functions, description, threads used)."""
+    import oracle as O
+    try:
+        from oracle import cpm
+        cpm.lib()
+        thr = cpm.max_threads()
+        return (cpm.nbody_init, cpm.nbody_step,
+                f'C + OpenMP port of pmwd (oracle/cpm.c: scatter with atomic adds, 3-mesh gather, k-space, '
+                f'kick/drift on {thr} threads; FFTs scipy pocketfft on all cores)', thr)
+    except Exception as e:     # no gcc / libgomp on this box: fall back to the NumPy oracle, and say so
+        print(f'[bench] oracle/cpm.c unavailable ({e}); timing the NumPy oracle', file=sys.stderr)
+        return (O.nbody_init, O.nbody_step,
+                'NumPy oracle port of pmwd (FFTs on all cores via scipy pocketfft, CIC loops '
+                'single-threaded NumPy)', 1)
+
+
 def cpu_steps(n, steps, warmup):
-    """Time `steps` forward KDK steps of the NumPy oracle at n^3 particles / (2n)^3 mesh."""
+    """Time `steps` forward KDK steps of the CPU port at n^3 particles / (2n)^3 mesh."""
     import numpy as np
     import oracle as O
+    init, step, desc, thr = cpu_port()
     conf = O.Conf(1., (n, n, n), mesh_shape=2)
     cosmo = O.boltzmann(O.SimpleLCDM(conf), conf)
     modes = O.linear_modes(O.white_noise(0, conf), cosmo, conf)
     ptcl = O.lpt(modes, cosmo, conf)
     a = conf.a_nbody
-    ptcl = O.nbody_init(a[0], ptcl, cosmo, conf)
+    ptcl = init(a[0], ptcl, cosmo, conf)
     i = 0
     for _ in range(warmup):
-        ptcl = O.nbody_step(a[i], a[i + 1], ptcl, cosmo, conf); i += 1
+        ptcl = step(a[i], a[i + 1], ptcl, cosmo, conf); i += 1
     t0 = time.perf_counter()
     for _ in range(steps):
-        ptcl = O.nbody_step(a[i % 63], a[i % 63 + 1], ptcl, cosmo, conf); i += 1
+        ptcl = step(a[i % 63], a[i % 63 + 1], ptcl, cosmo, conf); i += 1
     dt = time.perf_counter() - t0
     assert np.isfinite(ptcl['disp']).all()
-    return conf.ptcl_num * steps / dt, dt / steps
+    return conf.ptcl_num * steps / dt, dt / steps, desc, thr
 
 
 def pick_cpu_sample(steps, warmup, budget_s=150.):
-    cost = {128: 17.0, 64: 2.0, 32: 0.3}       # measured s/step of the NumPy oracle (8 cores)
-    for n in (128, 64, 32):
+    cost = {256: 3.6, 128: 0.9, 64: 0.2, 32: 0.05}   # measured s/step of the C port (8 cores)
+    for n in (256, 128, 64, 32):
         if (steps + warmup) * cost[n] <= budget_s:
             return n
     return 32
@@ -126,10 +145,10 @@ def run_reference(args):
     if rank != 0:
         return
     n = pick_cpu_sample(args.steps, args.warmup)
-    cores = os.cpu_count()
-    value, spstep = cpu_steps(n, args.steps, args.warmup)
-    sample = (f'{n}^3 particles / {2 * n}^3 mesh (bounded sample of the {args.n}^3/{2 * args.n}^3 workload), '
-              f'NumPy oracle port of pmwd; FFTs on {cores} threads (scipy pocketfft), CIC loops single-threaded')
+    value, spstep, desc, cores = cpu_steps(n, args.steps, args.warmup)
+    cores = max(cores, os.cpu_count() or 1)      # pocketfft runs on every core
+    sample = (f'{n}^3 particles / {2 * n}^3 mesh (bounded sample of the {args.n}^3/{2 * args.n}^3 workload); '
+              + desc)
     line = {
         'impl': 'reference', 'metric': 'particle_updates_per_sec', 'value': value,
         'unit': 'particle-updates/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
@@ -369,11 +388,10 @@ def run_ours(args):
     cpu = None
     if not args.no_cpu_baseline:
         ncpu = args.cpu_n
-        v, sp = cpu_steps(ncpu, 2, 1)
-        cpu = {'value': v, 'unit': 'particle-updates/s', 'cores': os.cpu_count(), 'kind': 'port',
-               'sample': f'{ncpu}^3 particles / {2 * ncpu}^3 mesh, 2 forward KDK steps after 1 warm-up, '
-                         f'{sp:.2f} s/step; NumPy oracle port of pmwd (FFTs on all cores via scipy '
-                         f'pocketfft, CIC loops single-threaded NumPy)'}
+        v, sp, desc, thr = cpu_steps(ncpu, 3, 1)
+        cpu = {'value': v, 'unit': 'particle-updates/s', 'cores': max(thr, os.cpu_count() or 1), 'kind': 'port',
+               'sample': f'{ncpu}^3 particles / {2 * ncpu}^3 mesh, 3 forward KDK steps after 1 warm-up, '
+                         f'{sp:.2f} s/step; ' + desc}
 
     line = {
         'metric': 'particle_updates_per_sec', 'value': value, 'unit': 'particle-updates/s',
@@ -401,7 +419,7 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=4)
     ap.add_argument('--reorder-every', type=int, default=3)
     ap.add_argument('--reorder-min-disp', type=float, default=1.0)
-    ap.add_argument('--cpu-n', type=int, default=96)
+    ap.add_argument('--cpu-n', type=int, default=256)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-adjoint', action='store_true')
     args = ap.parse_args()

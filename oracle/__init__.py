@@ -23,6 +23,12 @@ The reference is pure JAX and cannot be imported in this image (no ``jax``, no
   pin them ourselves with closed-form plane-wave tests, the EdS growth solution
   and the 3-digit soft known-answers of ``docs/examples/quickstart.ipynb``
   (sigma_disp after LPT), with tolerances stated in the tests.
+
+Compiled twin
+-------------
+``oracle/cpm.c`` (+ ``oracle/cpm.py``) restates one forward KDK step in C with OpenMP, bit-identical
+to the NumPy functions here when run on one thread (``tests/test_oracle_c.py``); it is what
+``bench.py`` times as the CPU baseline.  Same rule: test and bench infrastructure only.
 """
 
 from .conf import Conf

@@ -131,6 +131,50 @@ def test_gravity_vs_oracle(n, disp_std, mode):
     assert _rms(acc - ref64) <= 3 * _rms(ref32 - ref64) + 1e-7 * scale
 
 
+def test_gravity_config2_full_size_vs_compiled_oracle():
+    """BASELINE config 2 at its full size (256^3 particles / 512^3 mesh): the CUDA force against
+    the oracle's compiled twin (oracle/cpm.c, bit-identical to the NumPy oracle on one thread,
+    summation order of the scatter aside; float32 noise floor vs float64 measured at 2.6e-7).
+    Tolerance: acc rel-RMS error <= 1e-5, the same as at the small sizes."""
+    from oracle import cpm
+    pm = _pm()
+    n = 256
+    conf, oconf = _confs((n, n, n))
+    cosmo = pm.SimpleLCDM(conf)
+    pmid, disp, _, _ = O.gen_grid(oconf)
+    pmid = np.ascontiguousarray(pmid)
+    rng = np.random.default_rng(1)
+    disp = (disp + 4.0 * rng.standard_normal(disp.shape, dtype=np.float32)).astype(np.float32)
+    ptcl = pm.Particles(conf, torch.from_numpy(pmid).cuda(), torch.from_numpy(disp).cuda())
+    acc = pm.gravity(1., ptcl, cosmo, conf).cpu().numpy()
+    ref = cpm.gravity(pmid, disp, 0.3, oconf)
+    scale = _rms(ref)
+    assert _rms(acc - ref) <= 1e-5 * scale
+    assert np.abs(acc - ref).max() <= 1e-3 * scale
+
+
+def test_gravity_config3_momentum_conservation():
+    """The north-star size (512^3 particles / 1024^3 mesh) through a size-independent property:
+    scatter and gather share their weights and the mesh force operator is antisymmetric, so the
+    accelerations sum to zero (4e-10 of their rms in the float32 oracle at 128^3)."""
+    pm = _pm()
+    n = 512
+    conf = pm.Configuration(1., (n, n, n), mesh_shape=2)
+    cosmo = pm.SimpleLCDM(conf)
+    ptcl = pm.Particles.gen_grid(conf)
+    g = torch.Generator(device='cuda').manual_seed(0)
+    ptcl = ptcl.replace(disp=ptcl.disp + 4.0 * torch.randn(ptcl.disp.shape, device='cuda', generator=g))
+    acc = pm.gravity(1., ptcl, cosmo, conf)
+    assert torch.isfinite(acc).all()
+    rms = acc.double().square().mean().sqrt().item()
+    assert rms > 0
+    assert acc.double().mean(dim=0).abs().max().item() <= 1e-6 * rms
+    del acc
+    from pmwd_b200.gravity import release_workspaces
+    release_workspaces()
+    torch.cuda.empty_cache()
+
+
 @pytest.mark.parametrize('mode', ['atomic', 'deterministic'])
 def test_gravity_vjp_vs_oracle(mode):
     """pmwd_force_adj vs the oracle's chain of the reference VJP rules (cos >= 0.9999,
