@@ -154,6 +154,14 @@ int pmwd_kspace_force_adj(void* stream, int rank, const int32_t* shape, double s
 int pmwd_strain(void* stream, int rank, const int32_t* shape, double spacing, int i, int j,
                 const void* pot_c64, void* out_c64);
 
+/* powspec binning (spec_util.py:50-147): one pass over a half spectrum, float64 sums per np.digitize
+ * bin accumulated (+=) into out_f64[4][nedges + 1] = {sum k N, sum Re P N, sum Im P N, sum N}, where
+ * P = |f|^2 or f conj(g) (g_c64 may be NULL), optionally times prod_a sinc(k_a)^-deconv, N the Hermitian
+ * multiplicity, k in cycles per grid unit; edges_f64: nedges (<= 512) ascending device float64. */
+int pmwd_powspec_bin(void* stream, const int32_t* shape, const void* f_c64, const void* g_c64,
+                     int has_deconv, double deconv, const double* edges_f64, int nedges, int right,
+                     double* out_f64);
+
 /* ---- slab-decomposed (multi-GPU) building blocks ------------------------------------- */
 /* The reference's own (offset, mesh shape) semantics describe a slab: a mesh array holding
  * d->mesh_shape[0] x-planes starting at global plane d->offset[0] / cell_size of the periodic

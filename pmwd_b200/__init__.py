@@ -12,5 +12,7 @@ from .modes import white_noise, linear_modes
 from .lpt import lpt
 from .nbody import nbody, nbody_init, nbody_step, nbody_adj
 from .pm_util import fftfreq, fftfwd, fftinv
+from .spec_util import powspec
+from . import _lib
 
 __version__ = '0.1.0'

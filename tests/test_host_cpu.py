@@ -118,6 +118,7 @@ def test_no_cpu_path_for_kernels():
                  lambda: pm.gather(ptcl, conf, torch.zeros(conf.mesh_shape)),
                  lambda: pm.gravity(1., ptcl, cosmo, conf),
                  lambda: pm.nbody(ptcl, None, cosmo, conf),
-                 lambda: pm.lpt(torch.zeros((4, 4, 3), dtype=torch.complex64), cosmo, conf)):
+                 lambda: pm.lpt(torch.zeros((4, 4, 3), dtype=torch.complex64), cosmo, conf),
+                 lambda: pm.powspec(torch.zeros(conf.mesh_shape), 1.0)):
         with pytest.raises(PmwdError):
             call()
