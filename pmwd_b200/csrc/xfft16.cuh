@@ -1,5 +1,6 @@
 // Register-resident FFT along x for the fused x-pass (xpass16.cu): NX = 16 * 16 * R3 with
-// R3 in {1, 2, 4}, i.e. NX in {256, 512, 1024}.
+// R3 in {1, 2, 4}, i.e. NX in {256, 512, 1024}, by one CTA; R3 = 8 (NX = 2048) by a cluster of two
+// CTAs that exchange through distributed shared memory (last section of this file).
 //
 // One column per thread (first half of this file; the two-columns-per-thread form that
 // xpass16.cu uses is at the end): a tile is T = 8 adjacent columns.  Thread (j, c), j in [0, NX/16),
@@ -32,7 +33,7 @@ constexpr int T = 8;
 
 template <int NX>
 struct Cfg {
-  static_assert(NX == 256 || NX == 512 || NX == 1024, "NX = 256 * R3, R3 in {1,2,4}");
+  static_assert(NX == 256 || NX == 512 || NX == 1024 || NX == 2048, "NX = 256 * R3, R3 in {1,2,4,8}");
   static constexpr int J = NX / 16;          // threads per column; x stride between owned points
   static constexpr int R3 = NX / 256;        // radix of the last stage
   static constexpr int M3 = 16 / R3;         // last-stage butterflies per thread
@@ -79,6 +80,28 @@ PMWD_HD void dft2(float2& a0, float2& a1) {
   const float2 s = mk2(a0.x + a1.x, a0.y + a1.y), d = mk2(a0.x - a1.x, a0.y - a1.y);
   a0 = s;
   a1 = d;
+}
+
+// 8-point DFT, natural order in and out: even / odd 4-point DFTs, then X[k], X[k+4] = E[k] +- w8^k O[k]
+template <bool INV>
+PMWD_HD void dft8(float2& a0, float2& a1, float2& a2, float2& a3, float2& a4, float2& a5, float2& a6, float2& a7) {
+  constexpr float C2 = 0.70710678118654752f;
+  constexpr float sg = INV ? 1.f : -1.f;
+  dft4<INV>(a0, a2, a4, a6);                 // E[0..3] in a0, a2, a4, a6
+  dft4<INV>(a1, a3, a5, a7);                 // O[0..3] in a1, a3, a5, a7
+  const float2 o0 = a1;
+  const float2 o1 = cmulw(a3, C2, sg * C2);                                        // w8^1
+  const float2 o2 = INV ? mk2(-a5.y, a5.x) : mk2(a5.y, -a5.x);                      // w8^2 = -+i
+  const float2 o3 = cmulw(a7, -C2, sg * C2);                                       // w8^3
+  const float2 e0 = a0, e1 = a2, e2 = a4, e3 = a6;
+  a0 = mk2(e0.x + o0.x, e0.y + o0.y);
+  a1 = mk2(e1.x + o1.x, e1.y + o1.y);
+  a2 = mk2(e2.x + o2.x, e2.y + o2.y);
+  a3 = mk2(e3.x + o3.x, e3.y + o3.y);
+  a4 = mk2(e0.x - o0.x, e0.y - o0.y);
+  a5 = mk2(e1.x - o1.x, e1.y - o1.y);
+  a6 = mk2(e2.x - o2.x, e2.y - o2.y);
+  a7 = mk2(e3.x - o3.x, e3.y - o3.y);
 }
 
 // 16-point DFT in registers, natural order in and out (n = 4 n1 + n2, k = k1 + 4 k2):
@@ -165,6 +188,9 @@ PMWD_HD void stage3(float2 (&v)[16], const float2* tw, int j) {
       const float2 w = tw[r * i];
       v[m + M3 * r] = cmulw(v[m + M3 * r], w.x, INV ? -w.y : w.y);
     }
+    if constexpr (R3 == 8)
+      dft8<INV>(v[m], v[m + M3], v[m + 2 * M3], v[m + 3 * M3], v[m + 4 * M3], v[m + 5 * M3], v[m + 6 * M3],
+                v[m + 7 * M3]);
     if constexpr (R3 == 4) dft4<INV>(v[m], v[m + M3], v[m + 2 * M3], v[m + 3 * M3]);
     if constexpr (R3 == 2) dft2<INV>(v[m], v[m + M3]);
   }
@@ -242,6 +268,41 @@ PMWD_HD void stage3x2(float2 (&a)[16], float2 (&b)[16], const float2* tw, int j)
       }
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// NX = 2048 on a cluster of two CTAs (512 threads each).  Global butterfly index j in [0, 128),
+// CTA rank r owns j in [64 r, 64 r + 64) (local jl = j & 63) and the same 16 points per column as
+// above, x = j + 128 e.  The one-column exchange buffer of 2048 rows is split by bit 6 of x:
+// CTA (x >> 6) & 1 holds row x at local row xl = ((x >> 7) << 6) | (x & 63), padded as before
+// (phys = xl + (xl >> 4), 1088 rows = the NX = 1024 buffer).  Every READ is then local and has
+// exactly the NX = 1024 pattern (x = j + 128 e  ->  xl = jl + 64 e), so ex_read<1024>(ex, jl, ...)
+// serves; only the WRITES of the two exchanges go to either CTA:
+//   stage 1: x = 16 j + s          -> owner (j >> 2) & 1 (a whole warp, 4 consecutive j, writes to ONE CTA),
+//            xl = 64 (j >> 3) + 16 (j & 3) + s,  phys = xl + 4 (j >> 3) + (j & 3)
+//   stage 2: x = 256 (j >> 4) + k + 16 s, k = j & 15  -> owner (s >> 2) & 1,
+//            xl = 64 (2 (j >> 4) + (s >> 3)) + 16 (s & 3) + k,  phys = xl + 4 (2 (j >> 4) + (s >> 3)) + (s & 3)
+// Both keep the half-warp pattern "two rows of opposite parity" (conflict-free).
+PMWD_HD int c2k_owner1(int j) { return (j >> 2) & 1; }
+PMWD_HD int c2k_addr1(int j, int s, int c) {
+  const int xl = 64 * (j >> 3) + 16 * (j & 3) + s;
+  return (xl + 4 * (j >> 3) + (j & 3)) * T + c;
+}
+PMWD_HD int c2k_owner2(int s) { return (s >> 2) & 1; }
+PMWD_HD int c2k_addr2(int j, int s, int c) {
+  const int hi = 2 * (j >> 4) + (s >> 3);
+  const int xl = 64 * hi + 16 * (s & 3) + (j & 15);
+  return (xl + 4 * hi + (s & 3)) * T + c;
+}
+// ex[0], ex[1]: the two CTAs' buffers as seen from the calling thread
+PMWD_HD void c2k_write1(float2* const ex[2], int j, int c, const float2 (&v)[16]) {
+  float2* p = ex[c2k_owner1(j)];
+#pragma unroll
+  for (int s = 0; s < 16; ++s) p[c2k_addr1(j, s, c)] = v[s];
+}
+PMWD_HD void c2k_write2(float2* const ex[2], int j, int c, const float2 (&v)[16]) {
+#pragma unroll
+  for (int s = 0; s < 16; ++s) ex[c2k_owner2(s)][c2k_addr2(j, s, c)] = v[s];
 }
 
 }  // namespace r16

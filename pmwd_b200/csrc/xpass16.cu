@@ -22,7 +22,17 @@
 //     cost 27 % of the kernel: the L2 re-read queued behind the tile's own 256 KB of stores.)
 // Shared memory at nx = 1024: 68 KB exchange + 128 KB staging + 12 KB tables; one 512-thread CTA
 // per SM with up to 128 registers per thread.
+//
+// nx = 2048 (the 8-GPU mesh) does not fit one CTA's registers: the same kernels run on a CLUSTER of
+// two CTAs (cudaLaunchKernelEx, cluster dimension 2), 1024 threads per tile, each CTA keeping half
+// of the butterflies.  The exchange buffer is split between the two CTAs' shared memories so that
+// every read is local and the writes go to either CTA through distributed shared memory
+// (cluster.map_shared_rank); __syncthreads becomes cluster.sync (xfft16.cuh, last section; index
+// arithmetic emulated on the CPU).  NOT YET RUN ON A GPU: opt-in with PMWD_XPASS16_2048=1, the
+// radix-4 kernel of xpass.cu stays the default for nx = 2048 until it has been validated.
+#include <cooperative_groups.h>
 #include <cuda_pipeline.h>
+#include <stdlib.h>
 
 #include "xfft16.cuh"
 #include "xpass.cuh"
@@ -34,41 +44,89 @@ using r16::TP;
 
 template <int NX>
 struct K16 {
-  static constexpr int THREADS = Cfg<NX>::J * TP;
-  static constexpr int CTAS = NX == 1024 ? 1 : NX == 512 ? 2 : 4;
-  static constexpr size_t EX = (size_t)Cfg<NX>::ROWS * TP * sizeof(float2);     // one-column exchange (padded rows)
-  static constexpr size_t STG = (size_t)NX * TP * sizeof(float4);              // [16][THREADS] staging slots
+  static constexpr bool CL = NX == 2048;                       // two-CTA cluster per tile
+  static constexpr int THREADS = CL ? 512 : Cfg<NX>::J * TP;   // per CTA
+  static constexpr int CTAS = NX >= 1024 ? 1 : NX == 512 ? 2 : 4;
+  static constexpr int LROWS = CL ? Cfg<1024>::ROWS : Cfg<NX>::ROWS;            // rows of this CTA's exchange buffer
+  static constexpr size_t EX = (size_t)LROWS * TP * sizeof(float2);             // one-column exchange (padded rows)
+  static constexpr size_t STG = (size_t)16 * THREADS * sizeof(float4);         // [16][THREADS] staging slots
   static constexpr size_t SMEM = EX + STG + (size_t)NX * sizeof(float2) + (size_t)NX * sizeof(float);
 };
+
+namespace cg = cooperative_groups;
+
+// Who a thread is within its tile, and where the exchange buffers are.  One CTA: j = jl, both
+// entries of ex[] are the CTA's own buffer.  Cluster: j = 64 rank + jl, ex[r] = CTA r's buffer.
+struct XCtx {
+  int j, jl, cp, rank;
+  float2* ex[2];
+};
+
+template <int NX>
+__device__ __forceinline__ XCtx make_ctx(float2* ex_local) {
+  XCtx c;
+  c.cp = threadIdx.x % TP;
+  c.jl = threadIdx.x / TP;
+  if (K16<NX>::CL) {
+    cg::cluster_group cl = cg::this_cluster();
+    c.rank = (int)cl.block_rank();
+    c.j = 64 * c.rank + c.jl;
+    c.ex[c.rank] = ex_local;
+    c.ex[c.rank ^ 1] = cl.map_shared_rank(ex_local, c.rank ^ 1);
+  } else {
+    c.rank = 0;
+    c.j = c.jl;
+    c.ex[0] = c.ex[1] = ex_local;
+  }
+  return c;
+}
+
+// barrier over everything that shares the exchange buffer(s)
+template <int NX>
+__device__ __forceinline__ void xsync() {
+  if (K16<NX>::CL) cg::this_cluster().sync(); else __syncthreads();
+}
+template <int NX>
+__device__ __forceinline__ void xwrite1(const XCtx& c, const float2 (&v)[16]) {
+  if constexpr (K16<NX>::CL) r16::c2k_write1(c.ex, c.j, c.cp, v); else r16::ex_write1<NX>(c.ex[0], c.j, c.cp, v);
+}
+template <int NX>
+__device__ __forceinline__ void xwrite2(const XCtx& c, const float2 (&v)[16]) {
+  if constexpr (K16<NX>::CL) r16::c2k_write2(c.ex, c.j, c.cp, v); else r16::ex_write2<NX>(c.ex[0], c.j, c.cp, v);
+}
+template <int NX>
+__device__ __forceinline__ void xread(const XCtx& c, float2 (&v)[16]) {
+  if constexpr (K16<NX>::CL) r16::ex_read<1024>(c.ex[c.rank], c.jl, c.cp, v); else r16::ex_read<NX>(c.ex[0], c.j, c.cp, v);
+}
 
 // Both columns of a thread through the one-column exchange buffer, a then b; the register
 // arithmetic of one column sits between the barriers of the other column's exchange.
 template <int NX, bool INV>
-__device__ __forceinline__ void fft16x2(float2 (&a)[16], float2 (&b)[16], float2* ex, const float2* tw, int j, int cp) {
+__device__ __forceinline__ void fft16x2(float2 (&a)[16], float2 (&b)[16], const XCtx& c, const float2* tw) {
   r16::dft16<INV>(a);
-  __syncthreads();                       // every earlier read of the exchange buffer is done
-  r16::ex_write1<NX>(ex, j, cp, a);
+  xsync<NX>();                           // every earlier read of the exchange buffer is done
+  xwrite1<NX>(c, a);
   r16::dft16<INV>(b);
-  __syncthreads();
-  r16::ex_read<NX>(ex, j, cp, a);
-  __syncthreads();
-  r16::ex_write1<NX>(ex, j, cp, b);
-  r16::twiddle2<NX, INV>(a, tw, j);
+  xsync<NX>();
+  xread<NX>(c, a);
+  xsync<NX>();
+  xwrite1<NX>(c, b);
+  r16::twiddle2<NX, INV>(a, tw, c.j);
   r16::dft16<INV>(a);
-  __syncthreads();
-  r16::ex_read<NX>(ex, j, cp, b);
-  __syncthreads();
-  r16::ex_write2<NX>(ex, j, cp, a);
-  r16::twiddle2<NX, INV>(b, tw, j);
+  xsync<NX>();
+  xread<NX>(c, b);
+  xsync<NX>();
+  xwrite2<NX>(c, a);
+  r16::twiddle2<NX, INV>(b, tw, c.j);
   r16::dft16<INV>(b);
-  __syncthreads();
-  r16::ex_read<NX>(ex, j, cp, a);
-  __syncthreads();
-  r16::ex_write2<NX>(ex, j, cp, b);
-  r16::stage3<NX, INV>(a, tw, j);
-  __syncthreads();
-  r16::ex_read<NX>(ex, j, cp, b);
-  r16::stage3<NX, INV>(b, tw, j);
+  xsync<NX>();
+  xread<NX>(c, a);
+  xsync<NX>();
+  xwrite2<NX>(c, b);
+  r16::stage3<NX, INV>(a, tw, c.j);
+  xsync<NX>();
+  xread<NX>(c, b);
+  r16::stage3<NX, INV>(b, tw, c.j);
 }
 
 // cp.async this thread's 16 float4 words (two columns x 16 points) of `src` into its staging slots
@@ -130,24 +188,27 @@ __global__ void __launch_bounds__(K16<NX>::THREADS, K16<NX>::CTAS) xr16_force_ke
   constexpr int J = Cfg<NX>::J, THREADS = K16<NX>::THREADS;
   float2* ex = reinterpret_cast<float2*>(smem_raw);               // [ROWS][TP]  one-column exchange buffer
   float4* stg = reinterpret_cast<float4*>(smem_raw + K16<NX>::EX); // [16][THREADS]  staging slots
-  float2* tw = reinterpret_cast<float2*>(stg + NX * TP);          // [NX]
+  float2* tw = reinterpret_cast<float2*>(stg + 16 * THREADS);     // [NX]
   float* kx = reinterpret_cast<float*>(tw + NX);                  // [NX]
   build_tables16<NX>(P, tw, kx);
 
   const int64_t plane = (int64_t)P.ny_l * P.nzc;                  // columns; even (checked by the host)
   const int64_t ntiles = (plane + 2 * TP - 1) / (2 * TP);
-  const int cp = threadIdx.x % TP;
-  const int j = threadIdx.x / TP;
+  const XCtx cx = make_ctx<NX>(ex);
+  const int cp = cx.cp, j = cx.j;
   float4* mine = stg + threadIdx.x;
+  // one tile per CTA, or per cluster of two
+  const int64_t tile0 = K16<NX>::CL ? blockIdx.x >> 1 : blockIdx.x;
+  const int64_t tstep = K16<NX>::CL ? gridDim.x >> 1 : gridDim.x;
 
   {
-    const int64_t m = (int64_t)blockIdx.x * (2 * TP) + 2 * cp;
+    const int64_t m = tile0 * (2 * TP) + 2 * cp;
     stage_in<NX>(mine, P.in[0], (int64_t)j * plane + m, plane, m < plane);
     __pipeline_commit();
   }
-  __syncthreads();                                                // tables
+  xsync<NX>();                                                    // tables; peer CTA is resident
 
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  for (int64_t tile = tile0; tile < ntiles; tile += tstep) {
     const int64_t m = tile * (2 * TP) + 2 * cp;                   // this thread's columns m, m + 1
     const bool live = m < plane;
     const ColK ka = col_k(P, live ? (unsigned)m : 0u), kb = col_k(P, live ? (unsigned)m + 1u : 0u);
@@ -162,7 +223,7 @@ __global__ void __launch_bounds__(K16<NX>::THREADS, K16<NX>::CTAS) xr16_force_ke
       a[e] = make_float2(q.x, q.y);
       b[e] = make_float2(q.z, q.w);
     }
-    fft16x2<NX, false>(a, b, ex, tw, j, cp);
+    fft16x2<NX, false>(a, b, cx, tw);
 
     // ---- pot = -(scale S)/k^2 stays in registers; q = -i kx pot is parked in the staging slots
 #pragma unroll
@@ -176,7 +237,7 @@ __global__ void __launch_bounds__(K16<NX>::THREADS, K16<NX>::CTAS) xr16_force_ke
     }
 
     // ---- P = IFFT_x(pot): G_y = -i ky P, G_z = -i kz P
-    fft16x2<NX, true>(a, b, ex, tw, j, cp);
+    fft16x2<NX, true>(a, b, cx, tw);
     if (live) {
       const bool zya = xnyq(ka.ky, P.nyq, P.eps), zza = xnyq(ka.kz, P.nyq, P.eps);
       const bool zyb = xnyq(kb.ky, P.nyq, P.eps), zzb = xnyq(kb.kz, P.nyq, P.eps);
@@ -196,11 +257,11 @@ __global__ void __launch_bounds__(K16<NX>::THREADS, K16<NX>::CTAS) xr16_force_ke
       b[e] = make_float2(q.z, q.w);
     }
     {
-      const int64_t mn = m + (int64_t)gridDim.x * (2 * TP);       // same columns of this CTA's next tile
+      const int64_t mn = m + tstep * (2 * TP);       // same columns of this CTA's next tile
       stage_in<NX>(mine, P.in[0], (int64_t)j * plane + mn, plane, mn < plane);
       __pipeline_commit();
     }
-    fft16x2<NX, true>(a, b, ex, tw, j, cp);
+    fft16x2<NX, true>(a, b, cx, tw);
     if (live) {
 #pragma unroll
       for (int e = 0; e < 16; ++e)
@@ -208,6 +269,7 @@ __global__ void __launch_bounds__(K16<NX>::THREADS, K16<NX>::CTAS) xr16_force_ke
     }
   }
   __pipeline_wait_prior(0);
+  xsync<NX>();                           // (cluster) the peer may still be writing into this CTA's buffer
 }
 
 // -------------------------------------------------------------------------- adjoint force
@@ -217,24 +279,26 @@ __global__ void __launch_bounds__(K16<NX>::THREADS, K16<NX>::CTAS) xr16_force_ad
   constexpr int J = Cfg<NX>::J, THREADS = K16<NX>::THREADS;
   float2* ex = reinterpret_cast<float2*>(smem_raw);
   float4* stg = reinterpret_cast<float4*>(smem_raw + K16<NX>::EX); // V_x, then FFT_x(V_x), then the next tile's V_x
-  float2* tw = reinterpret_cast<float2*>(stg + NX * TP);
+  float2* tw = reinterpret_cast<float2*>(stg + 16 * THREADS);
   float* kx = reinterpret_cast<float*>(tw + NX);
   build_tables16<NX>(P, tw, kx);
 
   const int64_t plane = (int64_t)P.ny_l * P.nzc;
   const int64_t ntiles = (plane + 2 * TP - 1) / (2 * TP);
-  const int cp = threadIdx.x % TP;
-  const int j = threadIdx.x / TP;
+  const XCtx cx = make_ctx<NX>(ex);
+  const int cp = cx.cp, j = cx.j;
   float4* mine = stg + threadIdx.x;
+  const int64_t tile0 = K16<NX>::CL ? blockIdx.x >> 1 : blockIdx.x;
+  const int64_t tstep = K16<NX>::CL ? gridDim.x >> 1 : gridDim.x;
 
   {
-    const int64_t m = (int64_t)blockIdx.x * (2 * TP) + 2 * cp;
+    const int64_t m = tile0 * (2 * TP) + 2 * cp;
     stage_in<NX>(mine, P.in[0], (int64_t)j * plane + m, plane, m < plane);
     __pipeline_commit();
   }
-  __syncthreads();                                                // tables
+  xsync<NX>();                                                    // tables; peer CTA is resident
 
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  for (int64_t tile = tile0; tile < ntiles; tile += tstep) {
     const int64_t m = tile * (2 * TP) + 2 * cp;
     const bool live = m < plane;
     const ColK ka = col_k(P, live ? (unsigned)m : 0u), kb = col_k(P, live ? (unsigned)m + 1u : 0u);
@@ -252,7 +316,7 @@ __global__ void __launch_bounds__(K16<NX>::THREADS, K16<NX>::CTAS) xr16_force_ad
       a[e] = make_float2(q.x, q.y);
       b[e] = make_float2(q.z, q.w);
     }
-    fft16x2<NX, false>(a, b, ex, tw, j, cp);
+    fft16x2<NX, false>(a, b, cx, tw);
 #pragma unroll
     for (int e = 0; e < 16; ++e) mine[e * THREADS] = r16::pack4(a[e], b[e]);
 
@@ -268,7 +332,7 @@ __global__ void __launch_bounds__(K16<NX>::THREADS, K16<NX>::CTAS) xr16_force_ad
       a[e] = make_float2(-(kyma * vy.y) - kzma * vz.y, kyma * vy.x + kzma * vz.x);
       b[e] = make_float2(-(kymb * vy.w) - kzmb * vz.w, kymb * vy.z + kzmb * vz.z);
     }
-    fft16x2<NX, false>(a, b, ex, tw, j, cp);
+    fft16x2<NX, false>(a, b, cx, tw);
 
     // ---- S = (FFT(W) + i kx FFT(V_x)) * (-scale / k^2); then the next tile's V_x streams in
 #pragma unroll
@@ -281,11 +345,11 @@ __global__ void __launch_bounds__(K16<NX>::THREADS, K16<NX>::CTAS) xr16_force_ad
       b[e] = make_float2((b[e].x - k0m * sx.w) * gb, (b[e].y + k0m * sx.z) * gb);
     }
     {
-      const int64_t mn = m + (int64_t)gridDim.x * (2 * TP);
+      const int64_t mn = m + tstep * (2 * TP);
       stage_in<NX>(mine, P.in[0], (int64_t)j * plane + mn, plane, mn < plane);
       __pipeline_commit();
     }
-    fft16x2<NX, true>(a, b, ex, tw, j, cp);
+    fft16x2<NX, true>(a, b, cx, tw);
     if (live) {
 #pragma unroll
       for (int e = 0; e < 16; ++e)
@@ -293,29 +357,45 @@ __global__ void __launch_bounds__(K16<NX>::THREADS, K16<NX>::CTAS) xr16_force_ad
     }
   }
   __pipeline_wait_prior(0);
+  xsync<NX>();                           // (cluster) the peer may still be writing into this CTA's buffer
 }
 
 template <int NX>
 static int launch16(cudaStream_t st, const XParams& P, bool adjoint) {
   const int64_t plane = (int64_t)P.ny_l * P.nzc;
   const int64_t ntiles = (plane + 2 * TP - 1) / (2 * TP);
-  const int64_t cap = (int64_t)sm_count() * K16<NX>::CTAS;
-  const int grid = (int)(ntiles < cap ? ntiles : cap);
+  const int csize = K16<NX>::CL ? 2 : 1;                                   // CTAs per tile
+  const int64_t cap = (int64_t)sm_count() * K16<NX>::CTAS / csize;         // resident tiles
+  const int grid = (int)(ntiles < cap ? ntiles : cap) * csize;
   const int smem = (int)K16<NX>::SMEM;
-  if (adjoint) {
-    PMWD_CUDA_TRY(cudaFuncSetAttribute(xr16_force_adj_kernel<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    xr16_force_adj_kernel<NX><<<grid, K16<NX>::THREADS, smem, st>>>(P);
-  } else {
-    PMWD_CUDA_TRY(cudaFuncSetAttribute(xr16_force_kernel<NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    xr16_force_kernel<NX><<<grid, K16<NX>::THREADS, smem, st>>>(P);
-  }
+  void (*kern)(XParams) = adjoint ? xr16_force_adj_kernel<NX> : xr16_force_kernel<NX>;
+  PMWD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(K16<NX>::THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = K16<NX>::CL ? 1 : 0;
+  PMWD_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, P));
   PMWD_LAUNCH_CHECK();
   return PMWD_OK;
 }
 
-// 16-byte accesses need an even number of columns per x plane and 16-byte aligned arrays
+// 16-byte accesses need an even number of columns per x plane and 16-byte aligned arrays.
+// nx = 2048 (two-CTA clusters) is opt-in until it has run on a GPU: PMWD_XPASS16_2048=1.
 bool xpass16_supported(const XParams& P, bool adjoint) {
-  if (!(P.nx == 256 || P.nx == 512 || P.nx == 1024)) return false;
+  static const bool allow2k = [] {
+    const char* e = getenv("PMWD_XPASS16_2048");
+    return e && e[0] == '1';
+  }();
+  if (!(P.nx == 256 || P.nx == 512 || P.nx == 1024 || (P.nx == 2048 && allow2k))) return false;
   if ((((int64_t)P.ny_l * P.nzc) & 1) != 0) return false;
   const int nin = adjoint ? 3 : 1, nout = adjoint ? 1 : 3;
   for (int i = 0; i < nin; ++i)
@@ -330,7 +410,8 @@ int xpass16_launch(cudaStream_t st, const XParams& P, bool adjoint) {
     case 256: return launch16<256>(st, P, adjoint);
     case 512: return launch16<512>(st, P, adjoint);
     case 1024: return launch16<1024>(st, P, adjoint);
-    default: PMWD_REQUIRE(false, "register x-pass supports nx in {256,512,1024}");
+    case 2048: return launch16<2048>(st, P, adjoint);
+    default: PMWD_REQUIRE(false, "register x-pass supports nx in {256,512,1024,2048}");
   }
   return PMWD_EINVAL;
 }

@@ -126,6 +126,89 @@ static double run2() {
   return std::sqrt(err2 / ref2);
 }
 
+// NX = 2048 on a two-CTA cluster: threads 0..1023, rank = t / 512; two exchange buffers
+template <bool INV>
+static double run2k() {
+  constexpr int NX = 2048;
+  using C = Cfg<NX>;
+  const int NT = 1024, ROWS = Cfg<1024>::ROWS;
+  std::vector<float2> tw(NX);
+  for (int n = 0; n < NX; ++n) {
+    const double a = -2.0 * M_PI * n / NX;
+    tw[n] = mk2((float)std::cos(a), (float)std::sin(a));
+  }
+  std::vector<std::complex<double>> in((size_t)NX * T);
+  for (auto& z : in) z = {drand48() - 0.5, drand48() - 0.5};
+  std::vector<float2[16]> reg(NT);
+  for (int t = 0; t < NT; ++t) {
+    const int rank = t / 512, jl = (t % 512) / T, c = t % T, j = 64 * rank + jl;
+    for (int e = 0; e < 16; ++e) {
+      const auto z = in[(size_t)(j + C::J * e) * T + c];
+      reg[t][e] = mk2((float)z.real(), (float)z.imag());
+    }
+  }
+  const float2 poison = mk2(NAN, NAN);
+  std::vector<float2> b0((size_t)ROWS * T, poison), b1((size_t)ROWS * T, poison);
+  float2* ex[2] = {b0.data(), b1.data()};
+  auto J = [](int t) { return 64 * (t / 512) + (t % 512) / T; };
+  // coverage / collisions of both write patterns
+  for (int which = 1; which <= 2; ++which) {
+    std::vector<int> h0(b0.size(), 0), h1(b1.size(), 0);
+    for (int t = 0; t < NT; ++t)
+      for (int s = 0; s < 16; ++s) {
+        const int j = J(t), c = t % T;
+        const int own = which == 1 ? c2k_owner1(j) : c2k_owner2(s);
+        const int ad = which == 1 ? c2k_addr1(j, s, c) : c2k_addr2(j, s, c);
+        if (ad < 0 || ad >= ROWS * T) { std::printf("2k write%d out of range\n", which); std::exit(1); }
+        ++(own ? h1 : h0)[ad];
+      }
+    long tot = 0;
+    for (auto* h : {&h0, &h1}) for (int v : *h) { if (v > 1) { std::printf("2k collision write%d\n", which); std::exit(1); } tot += v; }
+    if (tot != (long)NX * T) { std::printf("2k write%d covers %ld\n", which, tot); std::exit(1); }
+  }
+  for (int t = 0; t < NT; ++t) dft16<INV>(reg[t]);
+  for (int t = 0; t < NT; ++t) c2k_write1(ex, J(t), t % T, reg[t]);
+  for (int t = 0; t < NT; ++t) { ex_read<1024>(ex[t / 512], (t % 512) / T, t % T, reg[t]); twiddle2<NX, INV>(reg[t], tw.data(), J(t)); }
+  std::fill(b0.begin(), b0.end(), poison); std::fill(b1.begin(), b1.end(), poison);
+  for (int t = 0; t < NT; ++t) dft16<INV>(reg[t]);
+  for (int t = 0; t < NT; ++t) c2k_write2(ex, J(t), t % T, reg[t]);
+  for (int t = 0; t < NT; ++t) { ex_read<1024>(ex[t / 512], (t % 512) / T, t % T, reg[t]); stage3<NX, INV>(reg[t], tw.data(), J(t)); }
+  double err2 = 0, ref2 = 0;
+  for (int c = 0; c < T; ++c)
+    for (int k = 0; k < NX; ++k) {
+      std::complex<double> acc = 0;
+      for (int n = 0; n < NX; ++n) {
+        const double a = (INV ? 2.0 : -2.0) * M_PI * (double)((long)n * k % NX) / NX;
+        acc += in[(size_t)n * T + c] * std::complex<double>(std::cos(a), std::sin(a));
+      }
+      const int j = k % C::J, e = k / C::J;
+      const int t = 512 * (j / 64) + (j % 64) * T + c;
+      const float2 g = reg[t][e];
+      err2 += std::norm(acc - std::complex<double>(g.x, g.y));
+      ref2 += std::norm(acc);
+    }
+  return std::sqrt(err2 / ref2);
+}
+
+// half-warp bank model for the cluster write patterns (16 lanes = 2 consecutive j x 8 columns)
+static int conflicts2k() {
+  int bad = 0;
+  for (int w = 0; w < 1024 / 16; ++w)
+    for (int which = 1; which <= 2; ++which)
+      for (int s = 0; s < 16; ++s) {
+        int seen[16] = {0}, owner = -1;
+        for (int l = 0; l < 16; ++l) {
+          const int t = w * 16 + l, c = t % T, j = 64 * (t / 512) + (t % 512) / T;
+          const int own = which == 1 ? c2k_owner1(j) : c2k_owner2(s);
+          const int ad = which == 1 ? c2k_addr1(j, s, c) : c2k_addr2(j, s, c);
+          if (owner < 0) owner = own;
+          if (own != owner) ++bad;            // a half-warp must target one CTA
+          if (seen[ad % 16]++) ++bad;
+        }
+      }
+  return bad;
+}
+
 // bank-conflict model for 64-bit shared accesses: a half-warp (16 lanes) is one wavefront if
 // its 16 words fall in 16 distinct 8-byte bank pairs (word index mod 16)
 template <int NX>
@@ -161,7 +244,9 @@ int main() {
   e = run2<512, true>(); std::printf("NX=512 x2 inv rel err %.3g\n", e); worst = std::fmax(worst, e);
   e = run2<1024, false>(); std::printf("NX=1024 x2 fwd rel err %.3g\n", e); worst = std::fmax(worst, e);
   e = run2<1024, true>(); std::printf("NX=1024 x2 inv rel err %.3g\n", e); worst = std::fmax(worst, e);
-  const int bc = conflicts<256>() + conflicts<512>() + conflicts<1024>();
+  e = run2k<false>(); std::printf("NX=2048 (cluster) fwd rel err %.3g\n", e); worst = std::fmax(worst, e);
+  e = run2k<true>(); std::printf("NX=2048 (cluster) inv rel err %.3g\n", e); worst = std::fmax(worst, e);
+  const int bc = conflicts<256>() + conflicts<512>() + conflicts<1024>() + conflicts2k();
   std::printf("bank conflicts (64-bit half-warp model): %d\n", bc);
   if (!(worst < 1e-6) || bc != 0) { std::printf("FAIL\n"); return 1; }
   std::printf("OK\n");

@@ -502,7 +502,8 @@ def test_full_gradient_pipeline():
 
 # the last three shapes have more tiles than resident CTAs (persistent loop + cp.async prefetch)
 @pytest.mark.parametrize('shape', [(64, 8, 10), (128, 6, 9), (256, 4, 6), (512, 4, 4), (1024, 2, 4), (2048, 2, 4),
-                                   (256, 80, 130), (512, 40, 130), (1024, 24, 130)])
+                                   (256, 80, 130), (512, 40, 130), (1024, 24, 130), (2048, 24, 130)],
+                         ids=lambda shp: 'x'.join(str(n) for n in shp))
 def test_fused_xpass_vs_cufft3d(shape):
     """csrc/xpass.cu / xpass16.cu (on-chip FFT along x fused with the k-space algebra) against the
     plain pipeline cuFFT-3D -> pmwd_kspace_force(_adj) -> cuFFT-3D, forward and adjoint, incl. the
@@ -538,7 +539,9 @@ def test_fused_xpass_vs_cufft3d(shape):
     arr = (C.c_void_p * 3)(*[t.data_ptr() for t in outs])
     _lib.check(lib.pmwd_xpass_force(st, shp, y0, nyl, cell, scale, _lib.ptr(s2s), arr), 'xpass slab')
     nzc = nz // 2 + 1
-    same_kernel = nx not in (256, 512, 1024) or (nyl * nzc) % 2 == (ny * nzc) % 2
+    import os
+    reg = (256, 512, 1024, 2048) if os.environ.get('PMWD_XPASS16_2048') == '1' else (256, 512, 1024)
+    same_kernel = nx not in reg or (nyl * nzc) % 2 == (ny * nzc) % 2
     for a in range(3):
         if same_kernel:     # per-column arithmetic does not depend on the slab
             assert torch.equal(outs[a], out[a][:, y0:y0 + nyl])
@@ -558,3 +561,21 @@ def test_fused_xpass_vs_cufft3d(shape):
     _lib.check(lib.pmwd_xpass_force_adj(st, shp, 0, ny, cell, scale, arr, _lib.ptr(o2)), 'xpass adj')
     r = torch.fft.irfft2(o2, s=(ny, nz), norm='forward')
     assert _rms((r - ref_r).cpu().numpy()) <= 2e-6 * _rms(ref_r.cpu().numpy())
+
+
+@pytest.mark.skipif(__import__('os').environ.get('PMWD_RUN_UNVALIDATED') != '1',
+                    reason='two-CTA cluster x-pass (nx = 2048): first GPU validation pending '
+                           '(set PMWD_RUN_UNVALIDATED=1)')
+def test_fused_xpass_2048_cluster_variant():
+    """The nx = 2048 register x-pass on two-CTA clusters (csrc/xpass16.cu, PMWD_XPASS16_2048=1) through
+    the same parity test as the default kernels, in a process of its own (the switch is read once)."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, PMWD_XPASS16_2048='1')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(root, 'tests', 'test_gpu_gravity.py'), '-q', '-x',
+                        '-m', 'gpu', '-k', 'test_fused_xpass_vs_cufft3d and 2048x'], env=env, cwd=root,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert '2 passed' in r.stdout
