@@ -68,14 +68,12 @@ def run(n, sigma, results):
     del scratch
     rec('memset', timeit(lambda: mesh.zero_()), 4 * Nm)
 
-    from pmwd_b200.gravity import _lib as L  # noqa
     acc = ptcl.acc
 
-    def gath(kick):
-        import pmwd_b200.gravity as G
-        # direct call of the fused gather through a tiny force-less path: use lib symbol via force pieces
-        pass
-    # gather3 has no standalone C entry: time it through pmwd_force minus the rest below.
+    def gath3():          # pmwd_gather3: the three force meshes in one pass (gravity.py:61-70)
+        _lib.check(lib.pmwd_gather3(st, C.byref(desc), _lib.ptr(ptcl.pmid), _lib.ptr(ptcl.disp), _lib.ptr(F[0]),
+                                    _lib.ptr(F[1]), _lib.ptr(F[2]), _lib.ptr(acc), None, 0.0), 'gather3')
+    rec('gather3', timeit(gath3), 30 * Np + 12 * Nm)
 
     def kforce():
         arr = (C.c_void_p * 3)(*[g_.data_ptr() for g_ in gk])
