@@ -337,6 +337,31 @@ def test_nbody_config1_vs_oracle(mode):
     assert 30 < out.disp.std().item() / ptcl.disp.std().item() < 60
 
 
+def test_nbody_config2_full_size_steps_vs_compiled_oracle():
+    """BASELINE config 2 at its full size (256^3 particles / 512^3 mesh, 63-step schedule): 2LPT
+    initial conditions, then the first 6 leapfrog steps through the public nbody_init / nbody_step
+    against the oracle's compiled twin (oracle/cpm.c).  Positions within 1e-4 cell (RMS and the
+    99.9th percentile), velocities and accelerations 1e-5 / 1e-4 relative."""
+    from oracle import cpm
+    pm, conf, oconf, cosmo, ocosmo, ic, ptcl = _ic(256)
+    a = conf.a_nbody
+    nsteps = 6
+    p, _ = pm.nbody_init(a[0], ptcl, None, cosmo, conf)
+    for i in range(nsteps):
+        p, _ = pm.nbody_step(a[i], a[i + 1], p, None, cosmo, conf)
+    q = cpm.nbody_init(float(a[0]), dict(ic), ocosmo, oconf)
+    for i in range(nsteps):
+        q = cpm.nbody_step(float(a[i]), float(a[i + 1]), q, ocosmo, oconf)
+    dpos = np.abs(p.disp.cpu().numpy() - q['disp']) / conf.cell_size
+    stats = dict(rms=_rms(dpos), p999=float(np.quantile(dpos[::7], 0.999)), max=float(dpos.max()))
+    print('position error [cell]:', stats)
+    assert stats['rms'] <= 1e-4 and stats['p999'] <= 1e-4, stats
+    assert _rms(p.vel.cpu().numpy() - q['vel']) <= 1e-5 * _rms(q['vel'])
+    assert _rms(p.acc.cpu().numpy() - q['acc']) <= 1e-4 * _rms(q['acc'])
+    # the run did something: displacements grew with the growth factor over the 6 steps
+    assert p.disp.std().item() > 1.05 * ptcl.disp.std().item()
+
+
 @pytest.mark.parametrize('mode', ['atomic', 'deterministic'])
 def test_storage_reorder_is_transparent(mode):
     """Re-sorting the integrator's particle storage by mesh cell (csrc/reorder.cu) must not
