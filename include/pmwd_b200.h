@@ -190,13 +190,15 @@ int pmwd_kspace_force_adj_slab(void* stream, const int32_t* shape, int y0, int n
                                double spacing, float scale, const void* const* v_c64,
                                void* out_c64);
 
-/* Fused x-pass (csrc/xpass.cu): on data[nx][ny_local][nz/2+1] already transformed over (y, z),
- * FFT along x in shared memory + laplace/neg_grad algebra + inverse FFT along x in ONE pass.
+/* Fused x-pass (csrc/xpass16.cu, csrc/xpass.cu): on data[nx][ny_local][nz/2+1] already transformed
+ * over (y, z), FFT along x on chip + laplace/neg_grad algebra + inverse FFT along x in ONE pass.
  * forward: rho2d -> g2d[0..2] (the three force spectra, still to be inverse-transformed over
  * (y, z));  adjoint: v2d[0..2] -> out2d.  `shape` is the GLOBAL mesh shape, nx in
  * {64..2048} powers of two (pmwd_xpass_supported).  Replaces gravity.py:56-64's
- * rfftn-x / laplace / neg_grad / irfftn-x chain. */
-/* The output arrays must not overlap the inputs. */
+ * rfftn-x / laplace / neg_grad / irfftn-x chain.
+ * nx in {256, 512, 1024} with an even ny_local * (nz/2+1) and 16-byte aligned arrays runs the
+ * register-resident kernels (16-byte accesses); anything else the shared-memory radix-4 ones.
+ * The output arrays must not overlap the inputs. */
 int pmwd_xpass_supported(int nx);
 int pmwd_xpass_force(void* stream, const int32_t* shape, int y0, int ny_local, double spacing,
                      float scale, const void* rho2d_c64, void* const* g2d_c64);
