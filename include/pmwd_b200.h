@@ -161,6 +161,13 @@ int pmwd_strain(void* stream, int rank, const int32_t* shape, double spacing, in
 int pmwd_powspec_bin(void* stream, const int32_t* shape, const void* f_c64, const void* g_c64,
                      int has_deconv, double deconv, const double* edges_f64, int nedges, int right,
                      double* out_f64);
+/* k-space half of the auto spectrum's VJP w.r.t. the field: out = w_k f_k with
+ * w_k = wbin_f64[bin(k)] * prod_a sinc(k_a)^-deconv (wbin_f64: nedges + 1 device float64, indexed like the
+ * bins above, = Pbar_b * spacing^3 / N_total / N_b); the field cotangent is twice the unnormalised
+ * C2R transform of out.  out_c64 may alias f_c64. */
+int pmwd_powspec_weight(void* stream, const int32_t* shape, const void* f_c64, int has_deconv,
+                        double deconv, const double* edges_f64, int nedges, int right,
+                        const double* wbin_f64, void* out_c64);
 
 /* ---- slab-decomposed (multi-GPU) building blocks ------------------------------------- */
 /* The reference's own (offset, mesh shape) semantics describe a slab: a mesh array holding

@@ -70,6 +70,7 @@ _SIGNATURES = {
     'pmwd_kspace_force_adj': (_i, [_vp, _i, _i32p, _d, _f, C.POINTER(_vp), _vp]),
     'pmwd_strain': (_i, [_vp, _i, _i32p, _d, _i, _i, _vp, _vp]),
     'pmwd_powspec_bin': (_i, [_vp, _i32p, _vp, _vp, _i, _d, _vp, _i, _i, _vp]),
+    'pmwd_powspec_weight': (_i, [_vp, _i32p, _vp, _i, _d, _vp, _i, _i, _vp, _vp]),
     'pmwd_scatter_soa': (_i, [_vp, _descp, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp]),
     'pmwd_gather3': (_i, [_vp, _descp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f]),
     'pmwd_gather3_kdk': (_i, [_vp, _descp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f]),

@@ -67,9 +67,53 @@ __global__ void __launch_bounds__(256) powspec_kernel(PsParams P) {
     if (hist[t] != 0.0) atomicAdd(P.out + t, hist[t]);
 }
 
+// out_k = w_k f_k (see ps::weight): the k-space half of powspec's VJP
+__global__ void __launch_bounds__(256) powspec_weight_kernel(PsParams P, const double* wbin, float2* out) {
+  extern __shared__ double ps_smem[];
+  double* edges = ps_smem;                       // [nedges]
+  double* wb = ps_smem + P.nedges;               // [nedges + 1]
+  for (int t = threadIdx.x; t < P.nedges; t += blockDim.x) edges[t] = P.edges[t];
+  for (int t = threadIdx.x; t <= P.nedges; t += blockDim.x) wb[t] = wbin[t];
+  __syncthreads();
+  const int64_t n = (int64_t)P.nx * P.ny * P.nzc;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+    const int l = (int)(q % P.nzc);
+    const int64_t row = q / P.nzc;
+    const int j = (int)(row % P.ny), i = (int)(row / P.ny);
+    const float w = ps::weight(i, j, l, P.nx, P.ny, P.nz, P.has_deconv != 0, P.deconv, edges, P.nedges,
+                               P.right != 0, wb);
+    const float2 f = P.f[q];
+    out[q] = make_float2(f.x * w, f.y * w);
+  }
+}
+
 }  // namespace pmwd
 
 using namespace pmwd;
+
+// VJP helper of the auto spectrum: out_c64 = w_k f_k with w_k = wbin[bin(k)] * prod_a sinc(k_a)^-deconv
+// (wbin: device float64[nedges + 1], indexed like pmwd_powspec_bin's bins).  The field cotangent is
+// twice the unnormalised C2R transform of out_c64.  out_c64 may alias f_c64.
+extern "C" int pmwd_powspec_weight(void* stream, const int32_t* shape, const void* f_c64, int has_deconv,
+                                   double deconv, const double* edges_dev, int nedges, int right,
+                                   const double* wbin_dev, void* out_c64) {
+  PMWD_REQUIRE(shape && f_c64 && edges_dev && wbin_dev && out_c64, "null buffer");
+  PMWD_REQUIRE(shape[0] > 0 && shape[1] > 0 && shape[2] > 0, "bad shape");
+  PMWD_REQUIRE(nedges > 0 && nedges <= PS_MAX_EDGES, "1 <= nedges <= 512");
+  PsParams P;
+  P.nx = shape[0]; P.ny = shape[1]; P.nz = shape[2]; P.nzc = shape[2] / 2 + 1;
+  P.nedges = nedges; P.right = right; P.has_g = 0; P.has_deconv = has_deconv;
+  P.deconv = (float)deconv;
+  P.f = (const float2*)f_c64; P.g = nullptr; P.edges = edges_dev; P.out = nullptr;
+  const int64_t n = (int64_t)P.nx * P.ny * P.nzc;
+  const int64_t want = (n + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  const int grid = (int)(want < cap ? want : cap);
+  const size_t smem = (size_t)(2 * nedges + 1) * sizeof(double);
+  powspec_weight_kernel<<<grid, 256, smem, as_stream(stream)>>>(P, wbin_dev, (float2*)out_c64);
+  PMWD_LAUNCH_CHECK();
+  return PMWD_OK;
+}
 
 // Accumulates (+=) into out[4][nedges + 1] (device float64: sum k N, sum Re P N, sum Im P N, sum N
 // per np.digitize bin 0..nedges); the caller zeroes it, and may call again for further fields

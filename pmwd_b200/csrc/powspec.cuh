@@ -74,5 +74,18 @@ PMWD_PS_HD Mode mode(int i, int j, int l, int nx, int ny, int nz, float fr, floa
   return m;
 }
 
+// VJP of the auto spectrum w.r.t. the field: with L = sum_b Pbar_b P_b and
+// wbin[b] = Pbar_b * (spacing^3 / N_total) / N_b (0 outside the returned bins),
+//   dL/df(x) = 2 * sum_{k in full spectrum} w_k f_k e^{+ikx},  w_k = wbin[bin(k)] * prod_a sinc(k_a)^-deconv,
+// i.e. twice the unnormalised C2R transform of w_k f_k.  This returns w_k for one mode.
+PMWD_PS_HD float weight(int i, int j, int l, int nx, int ny, int nz, bool has_deconv, float deconv,
+                        const double* edges, int nedges, bool right, const double* wbin) {
+  const float kx = freq(i, nx, false), ky = freq(j, ny, false), kz = freq(l, nz, true);
+  const float k = sqrtf((kx * kx + ky * ky) + kz * kz);
+  float w = (float)wbin[digitize((double)k, edges, nedges, right)];
+  if (has_deconv) w = ((w * sinc_pow(kx, deconv)) * sinc_pow(ky, deconv)) * sinc_pow(kz, deconv);
+  return w;
+}
+
 }  // namespace ps
 }  // namespace pmwd

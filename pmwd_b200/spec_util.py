@@ -3,8 +3,9 @@
 The FFT is cuFFT (``pm_util.fftfwd``); |f_k|^2 (or f_k conj(g_k)), the sinc deconvolution, the
 Hermitian multiplicities and the ``digitize`` binning are one CUDA pass (``pmwd_powspec_bin``)
 accumulating in float64; the handful of per-bin divisions happen in float64 torch on the device.
-Forward only: the estimator is the parity metric of the N-body path; a field that requires grad
-is rejected rather than silently detached.
+The auto spectrum is differentiable w.r.t. the field (it is the typical objective): the VJP is one
+weighting pass (``pmwd_powspec_weight``) and one unnormalised C2R transform.  A cross spectrum of
+fields that require grad is rejected rather than silently detached.
 """
 import ctypes as C
 import math
@@ -46,29 +47,11 @@ def _getbins(grid_shape, bins, cut_nyq):
     raise ValueError(f'{bins=} not supported')
 
 
-def powspec(f, spacing, bins=1j / 3, g=None, deconv=None, cut_zero=True, cut_nyq=True):
-    """Auto or cross power spectrum in 3-D averaged in spherical bins
-    (``pmwd/spec_util.py:50-147``).  Returns ``(k, P, N, bins)`` as float64 tensors
-    (``P`` complex128 for a cross spectrum) on the device of ``f``."""
-    f = torch.as_tensor(f)
-    _lib.require_cuda(f)
-    if f.requires_grad or (isinstance(g, torch.Tensor) and g.requires_grad):
-        raise NotImplementedError('powspec is forward only; detach the field first')
-    if g is not None:
-        g = torch.as_tensor(g, device=f.device)
-        if f.shape != g.shape:
-            raise ValueError(f'shape mismatch: {tuple(f.shape)} != {tuple(g.shape)}')
-    if f.ndim < 3:
-        raise ValueError('the field needs at least 3 axes')
-    grid_shape = tuple(f.shape[-3:])
-    bnum, bcut, edges, right = _getbins(grid_shape, bins, cut_nyq)
-
-    dev = f.device
+def _bin_sums(fields, others, grid_shape, edges_t, bnum, right, deconv):
+    """float64 sums per digitize bin: rows = (k N, Re P N, Im P N, N), columns 0..bnum."""
+    dev = fields.device
     lib = _lib.lib()
-    edges_t = torch.tensor(edges, dtype=torch.float64, device=dev)
     sums = torch.zeros((4, bnum + 1), dtype=torch.float64, device=dev)
-    fields = f.reshape((-1,) + grid_shape).to(torch.float32)
-    others = None if g is None else g.reshape((-1,) + grid_shape).to(torch.float32)
     with torch.cuda.device(dev):
         for n in range(fields.shape[0]):                     # leading axes are summed (:112-113)
             fk = fftfwd(fields[n]).contiguous()
@@ -77,8 +60,69 @@ def powspec(f, spacing, bins=1j / 3, g=None, deconv=None, cut_zero=True, cut_nyq
                 _lib.stream_ptr(dev), _lib.shape_arr(grid_shape), _lib.ptr(fk), _lib.ptr(gk),
                 int(deconv is not None), float(deconv or 0.), _lib.ptr(edges_t), bnum, int(right),
                 _lib.ptr(sums)), 'pmwd_powspec_bin')
-    ksum, pre, pim, num = (sums[i, :bnum] for i in range(4))
-    P = pre if g is None else torch.complex(pre, pim)
+    return sums
+
+
+class _AutoSpec(torch.autograd.Function):
+    """``fields (n, X, Y, Z) -> (sum Re P N per bin)``; everything else of powspec is
+    field independent.  VJP: see ``pmwd_powspec_weight``."""
+
+    @staticmethod
+    def forward(ctx, fields, grid_shape, edges_t, bnum, right, deconv):
+        sums = _bin_sums(fields, None, grid_shape, edges_t, bnum, right, deconv)
+        ctx.save_for_backward(fields, edges_t)
+        ctx.meta = (grid_shape, bnum, right, deconv)
+        ctx.mark_non_differentiable(sums)
+        return sums[1].clone(), sums
+
+    @staticmethod
+    def backward(ctx, pbar, _):
+        fields, edges_t = ctx.saved_tensors
+        grid_shape, bnum, right, deconv = ctx.meta
+        dev = fields.device
+        lib = _lib.lib()
+        wbin = pbar.to(torch.float64).contiguous()           # cotangent of sum_{k in b} N_k D_k |f_k|^2
+        grad = torch.empty_like(fields)
+        with torch.cuda.device(dev):
+            for n in range(fields.shape[0]):
+                fk = fftfwd(fields[n]).contiguous()
+                _lib.check(lib.pmwd_powspec_weight(
+                    _lib.stream_ptr(dev), _lib.shape_arr(grid_shape), _lib.ptr(fk),
+                    int(deconv is not None), float(deconv or 0.), _lib.ptr(edges_t), bnum, int(right),
+                    _lib.ptr(wbin), _lib.ptr(fk)), 'pmwd_powspec_weight')
+                # d|f_k|^2/df(x) summed over the full spectrum = 2 x unnormalised C2R of w_k f_k
+                grad[n] = 2 * torch.fft.irfftn(fk, s=grid_shape, norm='forward')
+        return grad, None, None, None, None, None
+
+
+def powspec(f, spacing, bins=1j / 3, g=None, deconv=None, cut_zero=True, cut_nyq=True):
+    """Auto or cross power spectrum in 3-D averaged in spherical bins
+    (``pmwd/spec_util.py:50-147``).  Returns ``(k, P, N, bins)`` as float64 tensors
+    (``P`` complex128 for a cross spectrum) on the device of ``f``."""
+    f = torch.as_tensor(f)
+    _lib.require_cuda(f)
+    if g is not None:
+        g = torch.as_tensor(g, device=f.device)
+        if f.shape != g.shape:
+            raise ValueError(f'shape mismatch: {tuple(f.shape)} != {tuple(g.shape)}')
+        if f.requires_grad or g.requires_grad:
+            raise NotImplementedError('the cross spectrum is forward only; detach the fields first')
+    if f.ndim < 3:
+        raise ValueError('the field needs at least 3 axes')
+    grid_shape = tuple(f.shape[-3:])
+    bnum, bcut, edges, right = _getbins(grid_shape, bins, cut_nyq)
+
+    dev = f.device
+    edges_t = torch.tensor(edges, dtype=torch.float64, device=dev)
+    fields = f.reshape((-1,) + grid_shape).to(torch.float32)
+    if g is None:
+        pre, sums = _AutoSpec.apply(fields, grid_shape, edges_t, bnum, right, deconv)
+        P = pre[:bnum]
+    else:
+        others = g.reshape((-1,) + grid_shape).to(torch.float32)
+        sums = _bin_sums(fields, others, grid_shape, edges_t, bnum, right, deconv)
+        P = torch.complex(sums[1, :bnum], sums[2, :bnum])
+    ksum, num = sums[0, :bnum], sums[3, :bnum]
 
     lo = int(bool(cut_zero))
     k, P, N = ksum[lo:bcut], P[lo:bcut], num[lo:bcut]

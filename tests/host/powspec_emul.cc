@@ -19,3 +19,17 @@ extern "C" void ps_emul(const int* shape, const float* f, const float* g, int ha
         out[3 * nb + m.bin] += m.N;
       }
 }
+
+extern "C" void ps_weight_emul(const int* shape, const float* f, int has_deconv, double deconv, const double* edges,
+                               int nedges, int right, const double* wbin, float* out) {
+  const int nx = shape[0], ny = shape[1], nz = shape[2], nzc = nz / 2 + 1;
+  for (int i = 0; i < nx; ++i)
+    for (int j = 0; j < ny; ++j)
+      for (int l = 0; l < nzc; ++l) {
+        const long q = ((long)i * ny + j) * nzc + l;
+        const float w = pmwd::ps::weight(i, j, l, nx, ny, nz, has_deconv != 0, (float)deconv, edges, nedges,
+                                         right != 0, wbin);
+        out[2 * q] = f[2 * q] * w;
+        out[2 * q + 1] = f[2 * q + 1] * w;
+      }
+}
