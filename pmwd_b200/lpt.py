@@ -52,28 +52,36 @@ def _strain(kvec, i, j, pot, conf):
 
 
 def _L(kvec, pot_m, pot_n, conf):
-    """2LPT source (``pmwd/lpt.py:40-76``)."""
+    """2LPT source (``pmwd/lpt.py:40-76``).  Same terms in the same summation order as the
+    reference, but every strain component is transformed once and reused (6 inverse FFTs instead
+    of 9 for ``pot_n is None``, 12 instead of 15 otherwise)."""
     m_eq_n = pot_n is None
     if m_eq_n:
         pot_n = pot_m
+    cache = {}
+
+    def strain(which, pot, i, j):
+        key = (which if not m_eq_n else 'm', i, j)
+        if key not in cache:
+            cache[key] = _strain(kvec, i, j, pot, conf)
+        return cache[key]
+
     L = torch.zeros(conf.ptcl_grid_shape, dtype=conf.float_dtype, device=pot_m.device)
     for i in range(conf.dim):
-        strain_m = _strain(kvec, i, i, pot_m, conf)
+        strain_m = strain('m', pot_m, i, i)
         for j in range(conf.dim - 1, i, -1):
-            strain_n = _strain(kvec, j, j, pot_n, conf)
-            L = L + strain_m * strain_n
+            L = L + strain_m * strain('n', pot_n, j, j)
         if not m_eq_n:
             for j in range(i - 1, -1, -1):
-                strain_n = _strain(kvec, j, j, pot_n, conf)
-                L = L + strain_m * strain_n
+                L = L + strain_m * strain('n', pot_n, j, j)
     if not m_eq_n:
         L = L * 0.5
     for i in range(conf.dim - 1):
         for j in range(i + 1, conf.dim):
-            strain_m = _strain(kvec, i, j, pot_m, conf)
+            strain_m = strain('m', pot_m, i, j)
             strain_n = strain_m
             if not m_eq_n:
-                strain_n = _strain(kvec, j, i, pot_n, conf)
+                strain_n = strain('n', pot_n, j, i)
             L = L - strain_m * strain_n
     return L
 

@@ -122,3 +122,54 @@ def test_no_cpu_path_for_kernels():
                  lambda: pm.powspec(torch.zeros(conf.mesh_shape), 1.0)):
         with pytest.raises(PmwdError):
             call()
+
+
+def test_lpt_source_reuses_strain_transforms(monkeypatch):
+    """``lpt._L`` (``pmwd/lpt.py:40-76``): the same terms in the same order as the reference's loops,
+    each strain component transformed once (6 instead of 9 inverse FFTs at 2LPT, 12 instead of 15 for
+    two potentials).  Checked structurally with a stand-in for the strain transform."""
+    import types
+    import sys
+    import pmwd_b200.lpt  # noqa: F401
+    mod = sys.modules['pmwd_b200.lpt']
+    calls = []
+
+    def fake(kvec, i, j, pot, conf):
+        tag = int(pot.sum().item())
+        calls.append((tag, i, j))
+        g = torch.Generator().manual_seed(100 * tag + 10 * i + j)
+        return torch.randn(4, 4, 4, generator=g)
+
+    monkeypatch.setattr(mod, '_strain', fake)
+    conf = types.SimpleNamespace(dim=3, ptcl_grid_shape=(4, 4, 4), float_dtype=torch.float32)
+
+    def reference_loops(pot_m, pot_n):
+        same = pot_n is None
+        if same:
+            pot_n = pot_m
+        out = torch.zeros(4, 4, 4)
+        for i in range(3):
+            sm = fake(None, i, i, pot_m, conf)
+            for j in range(2, i, -1):
+                out = out + sm * fake(None, j, j, pot_n, conf)
+            if not same:
+                for j in range(i - 1, -1, -1):
+                    out = out + sm * fake(None, j, j, pot_n, conf)
+        if not same:
+            out = out * 0.5
+        for i in range(2):
+            for j in range(i + 1, 3):
+                sm = fake(None, i, j, pot_m, conf)
+                sn = sm if same else fake(None, j, i, pot_n, conf)
+                out = out - sm * sn
+        return out
+
+    p1, p2 = torch.ones(1), torch.full((1,), 2.)
+    for pots, n_ours, n_ref in (((p1, None), 6, 9), ((p1, p2), 12, 15)):
+        calls.clear()
+        got = mod._L(None, *pots, conf)
+        assert len(calls) == n_ours and len(set(calls)) == n_ours
+        calls.clear()
+        want = reference_loops(*pots)
+        assert len(calls) == n_ref
+        assert torch.equal(got, want)
