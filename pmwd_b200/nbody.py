@@ -292,6 +292,64 @@ def nbody_step(a_prev, a_next, ptcl, obsvbl, cosmo, conf):
     return ptcl, obsvbl
 
 
+_host_streams = {}
+
+
+def nbody_step_host(a_prev, a_next, host, cosmo, conf, out=None):
+    """``nbody_step`` for a state that lives in (pinned) HOST memory: ``host`` and the returned
+    dict map ``'pmid'`` (int16), ``'disp'``, ``'vel'``, ``'acc'`` (float32) to CPU tensors of
+    shape ``(N, 3)``; ``out`` may supply the output buffers (``pmid`` is passed through).
+
+    Same arithmetic as ``nbody_step`` (``nbody.py:204-212``).  The copies are part of the call:
+    the three dynamic arrays go up first, the leading half-kick + drift run as soon as they are
+    there, and the new displacements -- final after the drift -- are copied back on a second
+    stream WHILE the force is computed; velocities and accelerations follow the fused
+    force + trailing half-kick.  Everything is enqueued asynchronously: synchronise the device
+    (or the current stream) before reading the outputs.  Default KDK splitting on the 3-D fast
+    path; other configurations take the plain copy -> ``integrate`` -> copy route.
+    """
+    dev = torch.device(conf.device if getattr(conf, 'device', None) is not None else 'cuda')
+    if dev.type != 'cuda' or not torch.cuda.is_available():
+        raise _lib.PmwdError('pmwd_b200 kernels need a CUDA device (there is no CPU fallback)')
+    for k in ('pmid', 'disp', 'vel', 'acc'):
+        if host[k].is_cuda:
+            raise ValueError(f"host['{k}'] is a CUDA tensor; use nbody_step for device-resident state")
+    if out is None:
+        out = {k: torch.empty_like(host[k]).pin_memory() for k in ('disp', 'vel', 'acc')}
+    out['pmid'] = host['pmid']
+    a_prev, a_next = _f(a_prev), _f(a_next)
+    with torch.no_grad(), torch.cuda.device(dev):
+        cur = torch.cuda.current_stream(dev)
+        acc = host['acc'].to(dev, non_blocking=True)
+        vel = host['vel'].to(dev, non_blocking=True)
+        disp = host['disp'].to(dev, non_blocking=True)
+        pmid = host['pmid'].to(dev, non_blocking=True)
+        p = Particles(conf, pmid, disp, vel=vel, acc=acc)
+        default = tuple(tuple(x) for x in conf.symp_splits) == ((0, 0.5), (1, 0.5))
+        if not (default and _fast_ok(p, conf)):
+            q = _integrate_inplace(a_prev, a_next, p, cosmo, conf)
+            for k in ('disp', 'vel', 'acc'):
+                out[k].copy_(getattr(q, k), non_blocking=True)
+            return out
+        am = a_prev * 0.5 + a_next * 0.5
+        K1 = _f32(kick_factor(a_prev, a_prev, am, cosmo, conf))
+        D = _f32(drift_factor(am, a_prev, a_next, cosmo, conf))
+        K2 = _f32(kick_factor(a_next, am, a_next, cosmo, conf))
+        _kick_drift(p, K1, D, True, True)
+        side = _host_streams.get(dev)
+        if side is None:
+            side = _host_streams[dev] = torch.cuda.Stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            out['disp'].copy_(p.disp, non_blocking=True)
+        p.disp.record_stream(side)
+        force_into(p.pmid, p.disp, float(cosmo.Omega_m), conf, p.acc, p.vel, K2)
+        out['vel'].copy_(p.vel, non_blocking=True)
+        out['acc'].copy_(p.acc, non_blocking=True)
+        cur.wait_stream(side)
+    return out
+
+
 class _Stepper:
     """Pipelined KDK stepping over a schedule of scale factors on a ``_Store``: with the default
     splitting on the 3-D fast path every step is ONE ``pmwd_force_kdk`` call (force + trailing

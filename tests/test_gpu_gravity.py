@@ -604,3 +604,30 @@ def test_fused_xpass_2048_cluster_variant():
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert '2 passed' in r.stdout
+
+
+@pytest.mark.skipif(__import__('os').environ.get('PMWD_RUN_UNVALIDATED') != '1',
+                    reason='nbody_step_host (stream-overlapped host-array step): first GPU validation pending '
+                           '(set PMWD_RUN_UNVALIDATED=1); bench.py checks it against the plain route at run time')
+@pytest.mark.parametrize('splits', [((0, 0.5), (1, 0.5)), ((0.5, 0), (0.5, 1))])
+def test_nbody_step_host_matches_nbody_step(splits):
+    """Host-array entry point == copy up, nbody_step, copy down: displacements bit-identical, velocities and
+    accelerations up to the scatter's summation order; also in place (out = host) over several steps and for
+    a non-default splitting (plain route inside)."""
+    pm, conf, oconf, cosmo, ocosmo, ic, ptcl = _ic(32, a_nbody_maxstep=1 / 16, symp_splits=splits)
+    a = conf.a_nbody
+    p0, _ = pm.nbody_init(a[0], ptcl, None, cosmo, conf)
+    host = {k: getattr(p0, k).cpu().pin_memory() for k in ('pmid', 'disp', 'vel', 'acc')}
+    ref = p0
+    for i in range(3):
+        ref, _ = pm.nbody_step(a[i], a[i + 1], ref, None, cosmo, conf)
+        host = pm.nbody_step_host(a[i], a[i + 1], host, cosmo, conf, out=host if i else None)
+        torch.cuda.synchronize()
+        assert torch.equal(host['pmid'], ref.pmid.cpu())
+        if i == 0:
+            assert torch.equal(host['disp'], ref.disp.cpu())
+        for k in ('disp', 'vel', 'acc'):
+            r = getattr(ref, k).cpu()
+            assert (host[k] - r).abs().max().item() <= 1e-5 * r.abs().max().item(), (i, k)
+    with pytest.raises(ValueError):
+        pm.nbody_step_host(a[0], a[1], dict(host, disp=host['disp'].cuda()), cosmo, conf)

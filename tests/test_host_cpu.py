@@ -119,7 +119,9 @@ def test_no_cpu_path_for_kernels():
                  lambda: pm.gravity(1., ptcl, cosmo, conf),
                  lambda: pm.nbody(ptcl, None, cosmo, conf),
                  lambda: pm.lpt(torch.zeros((4, 4, 3), dtype=torch.complex64), cosmo, conf),
-                 lambda: pm.powspec(torch.zeros(conf.mesh_shape), 1.0)):
+                 lambda: pm.powspec(torch.zeros(conf.mesh_shape), 1.0),
+                 lambda: pm.nbody_step_host(0.5, 0.6, dict(pmid=ptcl.pmid, disp=ptcl.disp, vel=ptcl.vel,
+                                                           acc=ptcl.vel), cosmo, conf)):
         with pytest.raises(PmwdError):
             call()
 
