@@ -11,3 +11,5 @@ echo "--- radix-4 shared-memory kernel (default today)"
 python tools/time_xpass.py 2048 256 2>&1 | tail -1
 echo "--- two-CTA cluster register kernel"
 PMWD_XPASS16_2048=1 python tools/time_xpass.py 2048 256 2>&1 | tail -1
+echo "--- framework baseline on the same GPU (literal torch transcription of the reference step)"
+python tools/torch_baseline.py 256 5 2>&1 | tail -1
