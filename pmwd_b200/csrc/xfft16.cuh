@@ -294,15 +294,15 @@ PMWD_HD int c2k_addr2(int j, int s, int c) {
   const int xl = 64 * hi + 16 * (s & 3) + (j & 15);
   return (xl + 4 * hi + (s & 3)) * T + c;
 }
-// ex[0], ex[1]: the two CTAs' buffers as seen from the calling thread
-PMWD_HD void c2k_write1(float2* const ex[2], int j, int c, const float2 (&v)[16]) {
-  float2* p = ex[c2k_owner1(j)];
+// ex0, ex1: the two CTAs' buffers as seen from the calling thread
+PMWD_HD void c2k_write1(float2* ex0, float2* ex1, int j, int c, const float2 (&v)[16]) {
+  float2* p = c2k_owner1(j) ? ex1 : ex0;
 #pragma unroll
   for (int s = 0; s < 16; ++s) p[c2k_addr1(j, s, c)] = v[s];
 }
-PMWD_HD void c2k_write2(float2* const ex[2], int j, int c, const float2 (&v)[16]) {
+PMWD_HD void c2k_write2(float2* ex0, float2* ex1, int j, int c, const float2 (&v)[16]) {
 #pragma unroll
-  for (int s = 0; s < 16; ++s) ex[c2k_owner2(s)][c2k_addr2(j, s, c)] = v[s];
+  for (int s = 0; s < 16; ++s) (c2k_owner2(s) ? ex1 : ex0)[c2k_addr2(j, s, c)] = v[s];
 }
 
 }  // namespace r16

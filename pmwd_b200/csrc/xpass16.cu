@@ -55,11 +55,12 @@ struct K16 {
 
 namespace cg = cooperative_groups;
 
-// Who a thread is within its tile, and where the exchange buffers are.  One CTA: j = jl, both
-// entries of ex[] are the CTA's own buffer.  Cluster: j = 64 rank + jl, ex[r] = CTA r's buffer.
+// Who a thread is within its tile, and where the exchange buffers are.  One CTA: j = jl and all
+// three pointers are the CTA's own buffer.  Cluster: j = 64 rank + jl, ex0 / ex1 = the buffers of
+// CTA 0 / 1 (one of them through distributed shared memory), self = this CTA's own.
 struct XCtx {
   int j, jl, cp, rank;
-  float2* ex[2];
+  float2 *ex0, *ex1, *self;
 };
 
 template <int NX>
@@ -71,13 +72,15 @@ __device__ __forceinline__ XCtx make_ctx(float2* ex_local) {
     cg::cluster_group cl = cg::this_cluster();
     c.rank = (int)cl.block_rank();
     c.j = 64 * c.rank + c.jl;
-    c.ex[c.rank] = ex_local;
-    c.ex[c.rank ^ 1] = cl.map_shared_rank(ex_local, c.rank ^ 1);
+    float2* peer = cl.map_shared_rank(ex_local, c.rank ^ 1);
+    c.ex0 = c.rank == 0 ? ex_local : peer;
+    c.ex1 = c.rank == 0 ? peer : ex_local;
   } else {
     c.rank = 0;
     c.j = c.jl;
-    c.ex[0] = c.ex[1] = ex_local;
+    c.ex0 = c.ex1 = ex_local;
   }
+  c.self = ex_local;
   return c;
 }
 
@@ -88,15 +91,15 @@ __device__ __forceinline__ void xsync() {
 }
 template <int NX>
 __device__ __forceinline__ void xwrite1(const XCtx& c, const float2 (&v)[16]) {
-  if constexpr (K16<NX>::CL) r16::c2k_write1(c.ex, c.j, c.cp, v); else r16::ex_write1<NX>(c.ex[0], c.j, c.cp, v);
+  if constexpr (K16<NX>::CL) r16::c2k_write1(c.ex0, c.ex1, c.j, c.cp, v); else r16::ex_write1<NX>(c.self, c.j, c.cp, v);
 }
 template <int NX>
 __device__ __forceinline__ void xwrite2(const XCtx& c, const float2 (&v)[16]) {
-  if constexpr (K16<NX>::CL) r16::c2k_write2(c.ex, c.j, c.cp, v); else r16::ex_write2<NX>(c.ex[0], c.j, c.cp, v);
+  if constexpr (K16<NX>::CL) r16::c2k_write2(c.ex0, c.ex1, c.j, c.cp, v); else r16::ex_write2<NX>(c.self, c.j, c.cp, v);
 }
 template <int NX>
 __device__ __forceinline__ void xread(const XCtx& c, float2 (&v)[16]) {
-  if constexpr (K16<NX>::CL) r16::ex_read<1024>(c.ex[c.rank], c.jl, c.cp, v); else r16::ex_read<NX>(c.ex[0], c.j, c.cp, v);
+  if constexpr (K16<NX>::CL) r16::ex_read<1024>(c.self, c.jl, c.cp, v); else r16::ex_read<NX>(c.self, c.j, c.cp, v);
 }
 
 // Both columns of a thread through the one-column exchange buffer, a then b; the register

@@ -167,11 +167,11 @@ static double run2k() {
     if (tot != (long)NX * T) { std::printf("2k write%d covers %ld\n", which, tot); std::exit(1); }
   }
   for (int t = 0; t < NT; ++t) dft16<INV>(reg[t]);
-  for (int t = 0; t < NT; ++t) c2k_write1(ex, J(t), t % T, reg[t]);
+  for (int t = 0; t < NT; ++t) c2k_write1(ex[0], ex[1], J(t), t % T, reg[t]);
   for (int t = 0; t < NT; ++t) { ex_read<1024>(ex[t / 512], (t % 512) / T, t % T, reg[t]); twiddle2<NX, INV>(reg[t], tw.data(), J(t)); }
   std::fill(b0.begin(), b0.end(), poison); std::fill(b1.begin(), b1.end(), poison);
   for (int t = 0; t < NT; ++t) dft16<INV>(reg[t]);
-  for (int t = 0; t < NT; ++t) c2k_write2(ex, J(t), t % T, reg[t]);
+  for (int t = 0; t < NT; ++t) c2k_write2(ex[0], ex[1], J(t), t % T, reg[t]);
   for (int t = 0; t < NT; ++t) { ex_read<1024>(ex[t / 512], (t % 512) / T, t % T, reg[t]); stage3<NX, INV>(reg[t], tw.data(), J(t)); }
   double err2 = 0, ref2 = 0;
   for (int c = 0; c < T; ++c)
