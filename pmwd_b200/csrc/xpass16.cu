@@ -368,14 +368,11 @@ static int launch16(cudaStream_t st, const XParams& P, bool adjoint) {
   const int64_t plane = (int64_t)P.ny_l * P.nzc;
   const int64_t ntiles = (plane + 2 * TP - 1) / (2 * TP);
   const int csize = K16<NX>::CL ? 2 : 1;                                   // CTAs per tile
-  const int64_t cap = (int64_t)sm_count() * K16<NX>::CTAS / csize;         // resident tiles
-  const int grid = (int)(ntiles < cap ? ntiles : cap) * csize;
   const int smem = (int)K16<NX>::SMEM;
   void (*kern)(XParams) = adjoint ? xr16_force_adj_kernel<NX> : xr16_force_kernel<NX>;
   PMWD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(K16<NX>::THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
@@ -386,6 +383,22 @@ static int launch16(cudaStream_t st, const XParams& P, bool adjoint) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = K16<NX>::CL ? 1 : 0;
+  // resident tiles: every tile slot must be co-resident (persistent loop), so a cluster launch asks
+  // the driver how many clusters fit at once (GPC boundaries can leave an SM without a partner)
+  int64_t cap = (int64_t)sm_count() * K16<NX>::CTAS / csize;
+  if (K16<NX>::CL) {
+    static int max_clusters[2] = {0, 0};
+    if (max_clusters[adjoint] == 0) {
+      cfg.gridDim = dim3((unsigned)(cap * csize));
+      int n = 0;
+      PMWD_CUDA_TRY(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+      PMWD_REQUIRE(n > 0, "no two-CTA cluster of the x-pass kernel fits on this device");
+      max_clusters[adjoint] = n;
+    }
+    if (cap > max_clusters[adjoint]) cap = max_clusters[adjoint];
+  }
+  const int grid = (int)(ntiles < cap ? ntiles : cap) * csize;
+  cfg.gridDim = dim3(grid);
   PMWD_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, P));
   PMWD_LAUNCH_CHECK();
   return PMWD_OK;
