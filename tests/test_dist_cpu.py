@@ -52,6 +52,19 @@ WORKER = textwrap.dedent('''
     want = (torch.arange(comm.x0 - h, comm.x0 + comm.mx + h) %% Mx).float().reshape(-1, 1, 1).expand(-1, My, Mz)
     assert torch.equal(ext3[1], want)
     assert comm.allreduce_max(torch.tensor(float(r))) == P - 1
+    # transposed-layout wavevectors and the parity-mode white noise: rank slices of the global objects
+    import math
+    from pmwd_b200.dist import _kvec_T, white_noise_slab
+    kT = _kvec_T(conf, comm, conf.mesh_shape, conf.cell_size, 'cpu')
+    period = 2 * math.pi / conf.cell_size
+    np.testing.assert_array_equal(kT[0].ravel().numpy(), (np.fft.fftfreq(Mx) * period).astype(np.float32))
+    np.testing.assert_array_equal(kT[1].ravel().numpy(),
+                                  (np.fft.fftfreq(My) * period).astype(np.float32)[comm.y0:comm.y0 + comm.my])
+    np.testing.assert_array_equal(kT[2].ravel().numpy(), (np.fft.rfftfreq(Mz) * period).astype(np.float32))
+    wn = white_noise_slab(3, conf, comm, 'cpu')
+    full_wn = np.random.default_rng(3).standard_normal(conf.ptcl_grid_shape, dtype=np.float32)
+    np.testing.assert_array_equal(wn.numpy(), full_wn[comm.px0:comm.px0 + comm.pnx])
+    assert comm.pnx == conf.ptcl_grid_shape[0] // P and comm.px0 == r * comm.pnx
     print('rank', r, 'ok')
 ''')
 
