@@ -1,0 +1,74 @@
+"""Eulerian particle ownership for the slab decomposition: groundwork, NOT wired into the
+stepping yet.
+
+Today particles stay on the rank that owns their Lagrangian x-slab and the mesh halo has to cover
+the largest displacement (70 planes of 2048^2 late in the 8-GPU run: 9.7 GB of halo traffic per
+step).  If a particle instead lives on the rank that owns its CURRENT base cell, the halo is the
+one plane the CIC stencil reaches into, at the price of moving the few particles that crossed a
+slab boundary after every drift.  This module holds that exchange as plain tensor code -- rank
+assignment with the kernels' own float32 cell arithmetic (``pmwd/pm_util.py:129-136``), a stable
+partition, one count exchange and one variable-size all-to-all per array, and the inverse that
+restores the reference's Lagrangian order -- so that it runs under gloo on the CPU
+(``tests/test_dist_cpu.py``) as well as under NCCL.
+"""
+import torch
+import torch.distributed as dist
+
+
+def owner_rank(pmid_x, disp_x, conf, nranks):
+    """Rank whose x-slab holds each particle's base cell: ``floor(disp / cell)`` in float32,
+    added to the int16 ``pmid`` and wrapped periodically, exactly as ``enmesh`` does."""
+    Mx = conf.mesh_shape[0]
+    t = disp_x.to(torch.float32) / float(torch.tensor(conf.cell_size, dtype=torch.float32))
+    cell = (pmid_x.to(torch.int64) + torch.floor(t).to(torch.int64)) % Mx
+    return cell // (Mx // nranks)
+
+
+def _counts(dest, nranks, group):
+    send = torch.bincount(dest, minlength=nranks).to(torch.int64)
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=group)
+    return send, recv
+
+
+def exchange(arrays, dest, group=None):
+    """Send row ``i`` of every tensor in ``arrays`` (dict name -> ``(n, ...)``) to rank
+    ``dest[i]``.  Returns the received rows, ordered by source rank and, within one source, in the
+    sender's order (stable), plus the ``(send, recv)`` row counts per rank."""
+    nranks = dist.get_world_size(group)
+    order = torch.sort(dest, stable=True).indices
+    send, recv = _counts(dest, nranks, group)
+    ssz, rsz = send.tolist(), recv.tolist()
+    out = {}
+    nrecv = int(sum(rsz))
+    for name, a in arrays.items():
+        # rows travel as raw bytes: one code path for int16 / int64 / float32 on every backend
+        rows = a.index_select(0, order).contiguous()
+        row_bytes = a.element_size()
+        for d in a.shape[1:]:
+            row_bytes *= int(d)
+        src = rows.view(torch.uint8).reshape(rows.shape[0], row_bytes)
+        got = torch.empty((nrecv, row_bytes), dtype=torch.uint8, device=a.device)
+        dist.all_to_all_single(got, src, output_split_sizes=rsz, input_split_sizes=ssz, group=group)
+        out[name] = got.view(a.dtype).reshape((nrecv,) + tuple(a.shape[1:]))
+    return out, (send, recv)
+
+
+def to_eulerian(arrays, conf, group=None):
+    """Move every particle to the rank that owns its current base cell.  ``arrays`` needs
+    ``'pmid'`` and ``'disp'``; all entries travel together (velocities, cotangents, the Lagrangian
+    index ``'lag'`` that ``to_lagrangian`` needs)."""
+    nranks = dist.get_world_size(group)
+    dest = owner_rank(arrays['pmid'][:, 0], arrays['disp'][:, 0], conf, nranks)
+    return exchange(arrays, dest, group)
+
+
+def to_lagrangian(arrays, ptcl_num, group=None):
+    """Inverse of any sequence of ``to_eulerian`` calls: send every particle back to the rank that
+    holds its index range of the reference's particle array and sort locally by ``arrays['lag']``
+    (global index, int64).  ``ptcl_num`` must be divisible by the number of ranks."""
+    nranks = dist.get_world_size(group)
+    per = ptcl_num // nranks
+    got, _ = exchange(arrays, arrays['lag'] // per, group)
+    order = torch.sort(got['lag']).indices
+    return {k: v.index_select(0, order) for k, v in got.items()}

@@ -65,6 +65,30 @@ WORKER = textwrap.dedent('''
     full_wn = np.random.default_rng(3).standard_normal(conf.ptcl_grid_shape, dtype=np.float32)
     np.testing.assert_array_equal(wn.numpy(), full_wn[comm.px0:comm.px0 + comm.pnx])
     assert comm.pnx == conf.ptcl_grid_shape[0] // P and comm.px0 == r * comm.pnx
+    # Eulerian ownership (groundwork, pmwd_b200/migrate.py): after to_eulerian every particle sits on the
+    # rank that owns its base cell and nothing is lost; to_lagrangian restores the reference order exactly
+    from pmwd_b200 import migrate
+    import oracle as O
+    oconf = O.Conf(1., conf.ptcl_grid_shape, mesh_shape=2)
+    pmid_all, disp_all, _, _ = O.gen_grid(oconf)
+    rng = np.random.default_rng(11)
+    disp_all = (disp_all + 3.0 * rng.standard_normal(disp_all.shape)).astype(np.float32)   # crosses slabs, wraps
+    vel_all = rng.standard_normal(disp_all.shape).astype(np.float32)
+    n_all = len(pmid_all)
+    mine = arrs = dict(pmid=torch.from_numpy(pmid_all[sl]), disp=torch.from_numpy(disp_all[sl]),
+                       vel=torch.from_numpy(vel_all[sl]), lag=torch.arange(sl.start, sl.stop))
+    eul, (sent, recvd) = migrate.to_eulerian(arrs, conf)
+    own = migrate.owner_rank(eul['pmid'][:, 0], eul['disp'][:, 0], conf, P)
+    assert bool((own == r).all()) and int(sent.sum()) == len(mine['lag'])
+    ind, _ = O.enmesh(eul['pmid'].numpy(), eul['disp'].numpy(), oconf.cell_size, oconf.mesh_shape, 0, None, None, False)
+    base_x = ind[:, 0, 0]
+    assert ((base_x >= comm.x0) & (base_x < comm.x0 + comm.mx)).all()        # same cell arithmetic as enmesh
+    total = torch.tensor([len(eul['lag'])]); dist.all_reduce(total)
+    assert int(total) == n_all
+    np.testing.assert_array_equal(eul['vel'].numpy(), vel_all[eul['lag'].numpy()])      # rows travel together
+    back = migrate.to_lagrangian(eul, n_all)
+    for k in ('pmid', 'disp', 'vel', 'lag'):
+        assert torch.equal(back[k], mine[k]), k
     print('rank', r, 'ok')
 ''')
 
