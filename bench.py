@@ -378,8 +378,9 @@ def run_ours(args):
     # on this box, it reproduces the plain route (copy up, nbody_step, copy down) on the warm-up step.
     api = 'pmwd_b200.nbody_step on pinned host arrays (explicit copies around it)'
     e2e_step = e2e_plain
-    chk = {k: torch.empty_like(host[k]).pin_memory() for k in ('disp', 'vel', 'acc')}
+    chk = None
     try:
+        chk = {k: torch.empty_like(host[k]).pin_memory() for k in ('disp', 'vel', 'acc')}
         e2e_host(0, host, chk)
         torch.cuda.synchronize()
         e2e_plain(0, host, host)                   # warm-up (state rolls forward on the host)
