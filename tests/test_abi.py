@@ -64,3 +64,28 @@ def test_sass_has_vector_red():
     from pmwd_b200.build import LIB
     out = subprocess.run(['cuobjdump', '-sass', LIB], capture_output=True, text=True).stdout
     assert 'REDG.E.ADD.F32x2' in out and 'REDG.E.ADD.F32.' in out
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/pmwd_b200.h must compile as C99 (-pedantic) and a plain
+    C program must link against the library and call it (no compute: ABI version and error string)."""
+    import shutil
+    import subprocess
+    if shutil.which('gcc') is None:
+        pytest.skip('gcc not available')
+    src = tmp_path / 'use_abi.c'
+    src.write_text('#include <string.h>\n#include "pmwd_b200.h"\n'
+                   'int main(void) {\n'
+                   '  char msg[64];\n'
+                   '  if (pmwd_abi_version() != 1) return 1;\n'
+                   '  /* a bad call must fail with a negative status and leave a message */\n'
+                   '  if (pmwd_laplace(0, 3, 0, 1.0, 0, 0) >= 0) return 2;\n'
+                   '  pmwd_last_error(msg, sizeof msg);\n'
+                   '  return strlen(msg) > 0 ? 0 : 3;\n'
+                   '}\n')
+    exe = tmp_path / 'use_abi'
+    libdir = os.path.join(ROOT, 'pmwd_b200')
+    subprocess.run(['gcc', '-std=c99', '-Wall', '-Wextra', '-pedantic', '-Werror', '-I' + os.path.join(ROOT, 'include'),
+                    str(src), '-L' + libdir, '-lpmwd_b200', '-Wl,-rpath,' + libdir, '-o', str(exe)], check=True)
+    r = subprocess.run([str(exe)])
+    assert r.returncode == 0
