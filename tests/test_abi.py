@@ -46,6 +46,25 @@ def test_abi_version_and_errors(lib):
     assert rc == -1 and 'dim' in _lib.last_error()
     rc = lib.pmwd_kick_drift(None, -1, None, ctypes.c_void_p(16), None, 0.0, 0.0, 1, 1)
     assert rc == -1
+    # power-spectrum entries: null buffers, too many bin edges
+    shp = _lib.shape_arr((8, 8, 8))
+    rc = lib.pmwd_powspec_bin(None, shp, None, None, 0, 0.0, ctypes.c_void_p(8), 4, 0, ctypes.c_void_p(8))
+    assert rc == -1 and 'null' in _lib.last_error()
+    rc = lib.pmwd_powspec_bin(None, shp, ctypes.c_void_p(8), None, 0, 0.0, ctypes.c_void_p(8), 100000, 0,
+                              ctypes.c_void_p(8))
+    assert rc == -1 and 'nedges' in _lib.last_error()
+    rc = lib.pmwd_powspec_weight(None, shp, ctypes.c_void_p(8), 0, 0.0, ctypes.c_void_p(8), 4, 0, None,
+                                 ctypes.c_void_p(8))
+    assert rc == -1
+    # fused x-pass: unsupported length, bad slab
+    bad = _lib.shape_arr((96, 8, 8))
+    arr = (ctypes.c_void_p * 3)(8, 8, 8)
+    rc = lib.pmwd_xpass_force(None, bad, 0, 8, 1.0, 1.0, ctypes.c_void_p(8), arr)
+    assert rc == -1 and 'nx' in _lib.last_error()
+    ok = _lib.shape_arr((256, 8, 8))
+    rc = lib.pmwd_xpass_force(None, ok, 4, 8, 1.0, 1.0, ctypes.c_void_p(8), arr)
+    assert rc == -1 and 'slab' in _lib.last_error()
+    assert lib.pmwd_xpass_supported(1024) == 1 and lib.pmwd_xpass_supported(96) == 0
 
 
 def test_product_never_imports_oracle():
