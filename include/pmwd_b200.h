@@ -203,10 +203,13 @@ int pmwd_kspace_force_adj_slab(void* stream, const int32_t* shape, int y0, int n
  * (y, z));  adjoint: v2d[0..2] -> out2d.  `shape` is the GLOBAL mesh shape, nx in
  * {64..2048} powers of two (pmwd_xpass_supported).  Replaces gravity.py:56-64's
  * rfftn-x / laplace / neg_grad / irfftn-x chain.
- * nx in {256, 512, 1024} with an even ny_local * (nz/2+1) and 16-byte aligned arrays runs the
- * register-resident kernels (16-byte accesses); anything else the shared-memory radix-4 ones.
+ * nx in {256, 512, 1024, 2048} with an even ny_local * (nz/2+1) and 16-byte aligned arrays runs
+ * the register-resident kernels (16-byte accesses; 2048: two-CTA clusters); anything else the
+ * shared-memory radix-4 ones.  pmwd_xpass_last_variant: 0 = none yet, 1 = radix-4, 2 = register
+ * kernel, for the last call of this process (test introspection).
  * The output arrays must not overlap the inputs. */
 int pmwd_xpass_supported(int nx);
+int pmwd_xpass_last_variant(void);
 int pmwd_xpass_force(void* stream, const int32_t* shape, int y0, int ny_local, double spacing,
                      float scale, const void* rho2d_c64, void* const* g2d_c64);
 int pmwd_xpass_force_adj(void* stream, const int32_t* shape, int y0, int ny_local, double spacing,

@@ -78,6 +78,7 @@ _SIGNATURES = {
     'pmwd_kspace_force_slab': (_i, [_vp, _i32p, _i, _i, _d, _f, _vp, C.POINTER(_vp)]),
     'pmwd_kspace_force_adj_slab': (_i, [_vp, _i32p, _i, _i, _d, _f, C.POINTER(_vp), _vp]),
     'pmwd_xpass_supported': (_i, [_i]),
+    'pmwd_xpass_last_variant': (_i, []),
     'pmwd_xpass_force': (_i, [_vp, _i32p, _i, _i, _d, _f, _vp, C.POINTER(_vp)]),
     'pmwd_xpass_force_adj': (_i, [_vp, _i32p, _i, _i, _d, _f, C.POINTER(_vp), _vp]),
     'pmwd_force_workspace_bytes': (_sz, [_descp, _i, _i]),

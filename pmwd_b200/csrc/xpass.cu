@@ -351,6 +351,9 @@ static int launch_x(cudaStream_t st, const XParams& P, bool adjoint) {
   return PMWD_OK;
 }
 
+// which implementation the last pmwd_xpass_* call of this process used (tests assert on it)
+static volatile int g_last_variant = 0;
+
 bool xpass_supported(int nx) {
   return nx == 64 || nx == 128 || nx == 256 || nx == 512 || nx == 1024 || nx == 2048;
 }
@@ -378,7 +381,11 @@ int xpass_run(cudaStream_t st, const int32_t* shape, int y0, int ny_l, double sp
     const char* e = getenv("PMWD_XPASS16");
     return !(e && e[0] == '0');
   }();
-  if (use16 && xpass16_supported(P, adjoint)) return xpass16_launch(st, P, adjoint);
+  if (use16 && xpass16_supported(P, adjoint)) {
+    g_last_variant = 2;
+    return xpass16_launch(st, P, adjoint);
+  }
+  g_last_variant = 1;
   switch (shape[0]) {
     case 64: return launch_x<64>(st, P, adjoint);
     case 128: return launch_x<128>(st, P, adjoint);
@@ -410,3 +417,5 @@ extern "C" int pmwd_xpass_force_adj(void* stream, const int32_t* shape, int y0, 
 }
 
 extern "C" int pmwd_xpass_supported(int nx) { return xpass_supported(nx) ? 1 : 0; }
+
+extern "C" int pmwd_xpass_last_variant(void) { return g_last_variant; }

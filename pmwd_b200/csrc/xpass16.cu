@@ -28,8 +28,9 @@
 // of the butterflies.  The exchange buffer is split between the two CTAs' shared memories so that
 // every read is local and the writes go to either CTA through distributed shared memory
 // (cluster.map_shared_rank); __syncthreads becomes cluster.sync (xfft16.cuh, last section; index
-// arithmetic emulated on the CPU).  NOT YET RUN ON A GPU: opt-in with PMWD_XPASS16_2048=1, the
-// radix-4 kernel of xpass.cu stays the default for nx = 2048 until it has been validated.
+// arithmetic emulated on the CPU).  Validated on B200 in round 2 (parity test green; the y-slab of
+// one of 8 GPUs at 2048^3: 9.0 ms forward / 9.6 ms adjoint against 15.5 / 12.3 ms for the radix-4
+// kernel of xpass.cu, profiles/r02_validate_pending.txt); PMWD_XPASS16_2048=0 selects the latter.
 #include <cooperative_groups.h>
 #include <cuda_pipeline.h>
 #include <stdlib.h>
@@ -405,11 +406,11 @@ static int launch16(cudaStream_t st, const XParams& P, bool adjoint) {
 }
 
 // 16-byte accesses need an even number of columns per x plane and 16-byte aligned arrays.
-// nx = 2048 (two-CTA clusters) is opt-in until it has run on a GPU: PMWD_XPASS16_2048=1.
+// nx = 2048 runs on two-CTA clusters; PMWD_XPASS16_2048=0 falls back to the radix-4 kernel (A/B).
 bool xpass16_supported(const XParams& P, bool adjoint) {
   static const bool allow2k = [] {
     const char* e = getenv("PMWD_XPASS16_2048");
-    return e && e[0] == '1';
+    return !(e && e[0] == '0');
   }();
   if (!(P.nx == 256 || P.nx == 512 || P.nx == 1024 || (P.nx == 2048 && allow2k))) return false;
   if ((((int64_t)P.ny_l * P.nzc) & 1) != 0) return false;

@@ -122,7 +122,10 @@ def powspec(f, spacing, bins=1j / 3, g=None, deconv=None, cut_zero=True, cut_nyq
         others = g.reshape((-1,) + grid_shape).to(torch.float32)
         sums = _bin_sums(fields, others, grid_shape, edges_t, bnum, right, deconv)
         P = torch.complex(sums[1, :bnum], sums[2, :bnum])
-    ksum, num = sums[0, :bnum], sums[3, :bnum]
+    # k N and N are field independent: the kernel accumulated them once per leading-axis field,
+    # the reference counts every mode once (spec_util.py:112-113 sums P only)
+    nfield = fields.shape[0]
+    ksum, num = sums[0, :bnum] / nfield, sums[3, :bnum] / nfield
 
     lo = int(bool(cut_zero))
     k, P, N = ksum[lo:bcut], P[lo:bcut], num[lo:bcut]

@@ -203,6 +203,49 @@ def test_gravity_vjp_vs_oracle(mode):
     assert _rms(got - dcot32) <= 1e-4 * _rms(dcot_ref)
 
 
+@pytest.mark.parametrize('shape', [(128, 4, 5), (256, 4, 9), (512, 4, 5), (512, 12, 65), (1024, 4, 5), (1024, 12, 33)],
+                         ids=lambda shp: 'x'.join(str(n) for n in shp))
+def test_register_xpass_force_and_vjp_vs_oracle(shape):
+    """The fused x-pass kernels behind the headline numbers (`xr16_force_kernel<nx>` /
+    `xr16_force_adj_kernel<nx>`, nx = mesh x extent = 2 x shape[0] in {256, 512, 1024, 2048}) inside
+    the whole force pipeline and its VJP, on anisotropic boxes small enough for the NumPy oracle:
+    pm.gravity / its backward (= pmwd_force, pmwd_force_adj) against O.gravity and O.gravity_vjp
+    (scipy pocketfft + the reference's laplace / neg_grad, gravity.py:9-72, nbody.py:108-118).
+    Tolerances as at the cubic sizes: acc rel-RMS <= 1e-5, disp cotangent cos >= 0.9999 and rel-RMS <= 1e-4,
+    Omega_m cotangent 1e-4."""
+    pm = _pm()
+    conf, oconf = _confs(shape)
+    o64 = O.Conf(1., shape, mesh_shape=2, float_dtype=np.float64)
+    assert tuple(conf.mesh_shape) == tuple(2 * n for n in shape)
+    pmid, disp, _, _ = O.gen_grid(oconf)
+    rng = np.random.default_rng(7)
+    disp = (disp + 1.5 * rng.standard_normal(disp.shape)).astype(np.float32)
+    pi = rng.standard_normal(disp.shape).astype(np.float32)
+    Om = torch.tensor(0.3, dtype=torch.float64, requires_grad=True)
+    cosmo = pm.SimpleLCDM(conf, Omega_m=Om)
+    d = torch.from_numpy(disp).cuda().requires_grad_(True)
+    ptcl = pm.Particles(conf, torch.from_numpy(np.ascontiguousarray(pmid)).cuda(), d)
+    from pmwd_b200 import _lib
+    n0 = _lib.lib().pmwd_launch_count()
+    acc = pm.gravity(1., ptcl, cosmo, conf)
+    acc.backward(torch.from_numpy(pi).cuda())
+    assert _lib.lib().pmwd_launch_count() > n0
+    # mesh x extent >= 256: the register kernels (xpass16.cu); 128: the radix-4 shared-memory kernel
+    assert _lib.lib().pmwd_xpass_last_variant() == (2 if conf.mesh_shape[0] >= 256 else 1)
+    acc64, dcot64, Om64 = O.gravity_vjp(pmid, disp.astype(np.float64), 0.3, o64, pi)
+    acc32, dcot32, _ = O.gravity_vjp(pmid, disp, 0.3, oconf, pi)
+    got = acc.detach().cpu().numpy()
+    scale = _rms(acc64)
+    assert _rms(got - acc64) <= 1e-5 * scale
+    assert _rms(got - acc32) <= 1e-5 * scale
+    assert _rms(got - acc64) <= 3 * _rms(acc32 - acc64) + 1e-7 * scale
+    gd = d.grad.cpu().numpy()
+    assert _cos(gd, dcot64) >= 0.9999
+    assert _rms(gd - dcot64) <= 1e-4 * _rms(dcot64)
+    assert _rms(gd - dcot32) <= 1e-4 * _rms(dcot64)
+    np.testing.assert_allclose(Om.grad.item(), Om64, rtol=1e-4)
+
+
 def test_gravity_general_dims():
     """1-D / 2-D gravity (composition path) vs oracle, incl. autograd VJP vs oracle VJP."""
     pm = _pm()
@@ -447,7 +490,15 @@ def test_nbody_adjoint_vs_oracle(mode):
     _, pc, cc = O.nbody_adj(final, cot, ocosmo, o64)
     assert _cos(d.grad.cpu().numpy(), pc['disp']) >= 0.9999
     assert _cos(v.grad.cpu().numpy(), pc['vel']) >= 0.9999
-    assert _rms(d.grad.cpu().numpy() - pc['disp']) <= 1e-3 * _rms(pc['disp'])
+    # CIC's weight gradient is piecewise constant (sign(-d), pm_util.py:144): one particle crossing a
+    # cell face under float32 summation-order noise flips an O(1) term of a few elements, so an RMS
+    # bound is a heavy-tailed statistic (the float32 oracle itself jumps from 6e-5 to 7e-3 under a 1e-6
+    # cell perturbation of the ICs).  Bound the bulk instead: median and 99th percentile of |error|.
+    for got, want in ((d.grad, pc['disp']), (v.grad, pc['vel'])):
+        e = np.abs(got.cpu().numpy() - want) / _rms(want)
+        # calibrated with the float32 oracle vs the float64 one over 8 draws of a 1e-6-cell IC
+        # perturbation: median 1.1e-5 .. 9.7e-5, p99 2e-4 .. 9e-3 (rms 6e-5 .. 6e-3, max up to 0.6)
+        assert np.median(e) <= 5e-4 and np.quantile(e, 0.99) <= 3e-2, (np.median(e), np.quantile(e, 0.99))
     # cosmology leaves: sums of float32 particle products over a chaotic 8-step 16^3 run;
     # compare with the float32 oracle's own distance from float64
     ic32 = dict(ic)
@@ -459,6 +510,42 @@ def test_nbody_adjoint_vs_oracle(mode):
     print('Omega_m cot rel err', err, 'float32-oracle rel err', noise)
     # (atomic and deterministic runs of ours differ from each other by ~1e-3 on this chaotic
     # 16^3 / 8-step configuration: that is the float32 noise level of this scalar)
+    assert err <= 1e-2
+    assert _cos(gt.grad.numpy(), cc['growth']) >= 0.9999
+
+
+def test_nbody_adjoint_config1_size_vs_oracle():
+    """BASELINE config 1 at its size (64^3 particles, 128^3 mesh, 10 leapfrog steps): the reverse-time
+    adjoint (nbody.py:226-276) against the float64 oracle's nbody_adj.  Cosine >= 0.9999 for the disp and
+    vel cotangents and for the growth-table cotangent; Omega_m cotangent within 1e-2 (a float32 sum over a
+    chaotic run; the bulk statistic of the particle cotangents as in the 16^3 test)."""
+    pm, conf, oconf, cosmo, ocosmo, ic, ptcl = _ic(64, a_nbody_maxstep=0.1)
+    assert conf.a_nbody_num == 10
+    rng = np.random.default_rng(5)
+    w_disp = rng.standard_normal(ic['disp'].shape).astype(np.float32)
+    w_vel = rng.standard_normal(ic['disp'].shape).astype(np.float32)
+    Om = torch.tensor(0.3, dtype=torch.float64, requires_grad=True)
+    gt = cosmo.growth.detach().clone().requires_grad_(True)
+    c = cosmo.replace(Omega_m=Om, growth=gt)
+    d = ptcl.disp.clone().requires_grad_(True)
+    v = ptcl.vel.clone().requires_grad_(True)
+    out, _ = pm.nbody(ptcl.replace(disp=d, vel=v), None, c, conf)
+    obj = (out.disp * torch.from_numpy(w_disp).cuda()).sum() + (out.vel * torch.from_numpy(w_vel).cuda()).sum()
+    obj.backward()
+
+    o64 = O.Conf(1., (64,) * 3, mesh_shape=2, float_dtype=np.float64, a_nbody_maxstep=0.1)
+    ic64 = dict(pmid=ic['pmid'], disp=ic['disp'].astype(np.float64), vel=ic['vel'].astype(np.float64))
+    final = O.nbody(ic64, ocosmo, o64)
+    cot = dict(disp=w_disp.astype(np.float64), vel=w_vel.astype(np.float64), acc=np.zeros_like(ic64['disp']))
+    _, pc, cc = O.nbody_adj(final, cot, ocosmo, o64)
+    for got, want in ((d.grad, pc['disp']), (v.grad, pc['vel'])):
+        g = got.cpu().numpy()
+        assert _cos(g, want) >= 0.9999
+        e = np.abs(g - want) / _rms(want)
+        print('cot err / rms: median', np.median(e), 'p99', np.quantile(e, 0.99), 'rms', _rms(e))
+        assert np.median(e) <= 5e-4 and np.quantile(e, 0.99) <= 3e-2
+    err = abs(Om.grad.item() / cc['Omega_m'] - 1)
+    print('Omega_m cot rel err', err)
     assert err <= 1e-2
     assert _cos(gt.grad.numpy(), cc['growth']) >= 0.9999
 
@@ -565,7 +652,7 @@ def test_fused_xpass_vs_cufft3d(shape):
     _lib.check(lib.pmwd_xpass_force(st, shp, y0, nyl, cell, scale, _lib.ptr(s2s), arr), 'xpass slab')
     nzc = nz // 2 + 1
     import os
-    reg = (256, 512, 1024, 2048) if os.environ.get('PMWD_XPASS16_2048') == '1' else (256, 512, 1024)
+    reg = (256, 512, 1024) if os.environ.get('PMWD_XPASS16_2048') == '0' else (256, 512, 1024, 2048)
     same_kernel = nx not in reg or (nyl * nzc) % 2 == (ny * nzc) % 2
     for a in range(3):
         if same_kernel:     # per-column arithmetic does not depend on the slab
@@ -588,16 +675,14 @@ def test_fused_xpass_vs_cufft3d(shape):
     assert _rms((r - ref_r).cpu().numpy()) <= 2e-6 * _rms(ref_r.cpu().numpy())
 
 
-@pytest.mark.skipif(__import__('os').environ.get('PMWD_RUN_UNVALIDATED') != '1',
-                    reason='two-CTA cluster x-pass (nx = 2048): first GPU validation pending '
-                           '(set PMWD_RUN_UNVALIDATED=1)')
-def test_fused_xpass_2048_cluster_variant():
-    """The nx = 2048 register x-pass on two-CTA clusters (csrc/xpass16.cu, PMWD_XPASS16_2048=1) through
-    the same parity test as the default kernels, in a process of its own (the switch is read once)."""
+def test_fused_xpass_2048_radix4_fallback():
+    """nx = 2048 defaults to the register x-pass on two-CTA clusters (csrc/xpass16.cu); the radix-4
+    shared-memory kernel (csrc/xpass.cu, PMWD_XPASS16_2048=0) stays as its A/B partner and runs through
+    the same parity test in a process of its own (the switch is read once)."""
     import os
     import subprocess
     import sys
-    env = dict(os.environ, PMWD_XPASS16_2048='1')
+    env = dict(os.environ, PMWD_XPASS16_2048='0')
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(root, 'tests', 'test_gpu_gravity.py'), '-q', '-x',
                         '-m', 'gpu', '-k', 'test_fused_xpass_vs_cufft3d and 2048x'], env=env, cwd=root,
@@ -606,9 +691,6 @@ def test_fused_xpass_2048_cluster_variant():
     assert '2 passed' in r.stdout
 
 
-@pytest.mark.skipif(__import__('os').environ.get('PMWD_RUN_UNVALIDATED') != '1',
-                    reason='nbody_step_host (stream-overlapped host-array step): first GPU validation pending '
-                           '(set PMWD_RUN_UNVALIDATED=1); bench.py checks it against the plain route at run time')
 @pytest.mark.parametrize('splits', [((0, 0.5), (1, 0.5)), ((0.5, 0), (0.5, 1))])
 def test_nbody_step_host_matches_nbody_step(splits):
     """Host-array entry point == copy up, nbody_step, copy down: displacements bit-identical, velocities and

@@ -2,10 +2,7 @@
 oracle (pmwd/spec_util.py:50-147).  Tolerances: mode counts exact, <k> 1e-12, P(k) 1e-5 relative
 (float32 FFTs of two libraries; the north star asks for 0.1 %).
 
-The kernel was written after the round's GPU budget was spent: its per-mode arithmetic is held to
-the oracle on the CPU (tests/test_powspec_host.py), the launch itself has not run on a GPU yet.
-Until it has, these tests only run with PMWD_RUN_UNVALIDATED=1."""
-import os
+The per-mode arithmetic is also held to the oracle on the CPU (tests/test_powspec_host.py)."""
 
 import numpy as np
 import pytest
@@ -13,10 +10,7 @@ import torch
 
 import oracle as O
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('PMWD_RUN_UNVALIDATED') != '1',
-                                 reason='pmwd_powspec_bin: first GPU validation pending '
-                                        '(set PMWD_RUN_UNVALIDATED=1)')]
+pytestmark = pytest.mark.gpu
 
 
 def _check(got, want):
