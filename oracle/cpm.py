@@ -1,5 +1,6 @@
 """ctypes front end of ``oracle/cpm.c``: the compiled (C + OpenMP) restatement of one
-forward KDK step, for the CPU baseline.  TEST INFRASTRUCTURE ONLY.
+forward KDK step and of one reverse-time adjoint step, for the CPU baseline and the
+full-size parity tests.  TEST INFRASTRUCTURE ONLY.
 
 ``oracle/cpm.c`` repeats the float32 arithmetic of the NumPy oracle (hence of the reference,
 see the citations there) with plain loops; ``tests/test_oracle_c.py`` holds it to the NumPy
@@ -13,7 +14,7 @@ import subprocess
 
 import numpy as np
 
-from .nbody import drift_factor, kick_factor
+from .nbody import drift_factor, kick_factor, factor_grads, _cot_axpy
 from .gravity import fftfwd, fftinv
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -57,7 +58,13 @@ def lib():
         L.cpm_kspace_force.argtypes = [i32p, C.c_double, vp, vp, vp, vp, C.c_int]
         L.cpm_contrast.argtypes = [i64, vp, f32, C.c_int]
         L.cpm_axpy.argtypes = [i64, vp, vp, f32, C.c_int]
-        for f in (L.cpm_scatter, L.cpm_gather, L.cpm_kspace_force, L.cpm_contrast, L.cpm_axpy):
+        L.cpm_scatter_val.argtypes = [i64, vp, vp, vp, C.c_int, f32, i32p, vp, C.c_int]
+        L.cpm_grad_gather.argtypes = [i64, vp, vp, f32, i32p, vp, vp, C.c_int, f32, vp, C.c_int]
+        L.cpm_kspace_force_adj.argtypes = [i32p, C.c_double, vp, vp, vp, vp, C.c_int]
+        L.cpm_dot.argtypes = [i64, vp, vp, C.c_int]
+        L.cpm_dot.restype = C.c_double
+        for f in (L.cpm_scatter, L.cpm_gather, L.cpm_kspace_force, L.cpm_contrast, L.cpm_axpy,
+                  L.cpm_scatter_val, L.cpm_grad_gather, L.cpm_kspace_force_adj):
             f.restype = None
         _lib = L
     return _lib
@@ -161,3 +168,108 @@ def nbody_step(a_prev, a_next, ptcl, cosmo, conf, threads=None):
             ptcl['vel'] = _axpy(ptcl['vel'], ptcl['acc'], f, threads)
             a_vel = a_vel_next
     return ptcl
+
+
+# ----------------------------------------------------------------------------- adjoint
+def gravity_vjp(pmid, disp, Omega_m, conf, acc_cot, threads=None):
+    """``oracle.gravity.gravity_vjp`` (what ``jax.vjp(gravity)`` evaluates at
+    ``pmwd/nbody.py:111-116``) on the compiled loops: returns ``(acc, disp_cot, Omega_m_cot)``.
+    Same float32 operation order as the NumPy oracle (bit-identical on one thread, the two
+    scatters' summation order aside on several)."""
+    _check_fast(pmid, disp, conf)
+    threads = max_threads() if threads is None else threads
+    L = lib()
+    n = len(pmid)
+    cell = np.float32(conf.cell_size)
+    shp = _shape(conf.mesh_shape)
+    acc_cot = np.ascontiguousarray(acc_cot, dtype=np.float32)
+    dens = scatter(pmid, disp, conf, threads)
+    dens1 = dens.copy()
+    forces = rho_to_force(dens1, conf, Omega_m, threads)          # consumes dens1
+    acc = gather(pmid, disp, conf, forces, threads)
+    disp_cot = np.zeros((n, 3), dtype=np.float32)
+    spec = []
+    for i in range(3):
+        F = np.ascontiguousarray(forces[i])
+        L.cpm_grad_gather(n, _p(pmid), _p(disp), cell, shp, _p(F), _p(acc_cot[:, i:]), 3, np.float32(0),
+                          _p(disp_cot), threads)                  # gather.py:106-110
+        V = np.zeros(conf.mesh_shape, dtype=np.float32)
+        L.cpm_scatter_val(n, _p(pmid), _p(disp), _p(acc_cot[:, i:]), 3, cell, shp, _p(V), threads)   # :113
+        spec.append(np.ascontiguousarray(fftfwd(V)))
+        del V
+    out = np.empty_like(spec[0])
+    L.cpm_kspace_force_adj(shp, float(conf.cell_size), _p(spec[0]), _p(spec[1]), _p(spec[2]), _p(out), threads)
+    del spec
+    rhop_cot = fftinv(out, shape=conf.mesh_shape).astype(np.float32, copy=False)
+    scale = np.float32(1.5 * np.float64(Omega_m))
+    Om_cot = 1.5 * np.sum(rhop_cot.astype(np.float64) * (dens.astype(np.float64) - 1))
+    dens_cot = np.ascontiguousarray(rhop_cot * scale)
+    val = np.float32(conf.mesh_size / conf.ptcl_num)
+    L.cpm_grad_gather(n, _p(pmid), _p(disp), cell, shp, _p(dens_cot), None, 0, val, _p(disp_cot), threads)
+    return acc, disp_cot, Om_cot
+
+
+def force_adj(a, ptcl, ptcl_cot, cosmo, conf, threads=None):
+    """``oracle.nbody.force_adj`` (``pmwd/nbody.py:108-118``)."""
+    acc, disp_cot, Om_cot = gravity_vjp(ptcl['pmid'], ptcl['disp'], cosmo.Omega_m, conf, ptcl_cot['vel'], threads)
+    ptcl = dict(ptcl); ptcl['acc'] = acc
+    ptcl_cot = dict(ptcl_cot); ptcl_cot['acc'] = disp_cot
+    return ptcl, ptcl_cot, Om_cot
+
+
+def _dot(x, y, threads):
+    x = np.ascontiguousarray(x); y = np.ascontiguousarray(y)
+    return lib().cpm_dot(x.size, _p(x), _p(y), threads)
+
+
+def nbody_adj_step(a_prev, a_next, ptcl, ptcl_cot, cosmo, cosmo_cot, cosmo_cot_force, conf, threads=None):
+    """``oracle.nbody.integrate_adj`` (``pmwd/nbody.py:143-162`` with ``kick_adj`` :80-99 and
+    ``drift_adj`` :49-67 inlined) on the compiled kernels.  The two dot products per step are
+    accumulated in float64 by threads (the NumPy oracle sums in float32)."""
+    threads = max_threads() if threads is None else threads
+    ptcl, ptcl_cot = dict(ptcl), dict(ptcl_cot)
+    K = D = 0
+    a_disp = a_vel = a_acc = a_prev
+    for d, k in reversed(conf.symp_splits):
+        if k != 0:
+            K += k
+            a_vel_next = a_prev * (1 - K) + a_next * K
+            factor, grads = factor_grads(kick_factor, a_acc, a_vel, a_vel_next, cosmo, conf)
+            f = np.float32(factor)
+            ptcl['vel'] = _axpy(ptcl['vel'], ptcl['acc'], f, threads)
+            ptcl_cot['disp'] = _axpy(ptcl_cot['disp'], ptcl_cot['acc'], -f, threads)
+            s = _dot(ptcl_cot['vel'], ptcl['acc'], threads)
+            cosmo_cot = _cot_axpy(cosmo_cot, s, grads)
+            cosmo_cot = dict(cosmo_cot)
+            cosmo_cot['Omega_m'] = cosmo_cot['Omega_m'] - cosmo_cot_force * np.float64(f)
+            a_vel = a_vel_next
+        if d != 0:
+            D += d
+            a_disp_next = a_prev * (1 - D) + a_next * D
+            factor, grads = factor_grads(drift_factor, a_vel, a_disp, a_disp_next, cosmo, conf)
+            f = np.float32(factor)
+            ptcl['disp'] = _axpy(ptcl['disp'], ptcl['vel'], f, threads)
+            ptcl_cot['vel'] = _axpy(ptcl_cot['vel'], ptcl_cot['disp'], -f, threads)
+            s = _dot(ptcl_cot['disp'], ptcl['vel'], threads)
+            cosmo_cot = _cot_axpy(cosmo_cot, s, grads)
+            a_disp = a_disp_next
+            ptcl, ptcl_cot, cosmo_cot_force = force_adj(a_disp, ptcl, ptcl_cot, cosmo, conf, threads)
+            a_acc = a_disp
+    return ptcl, ptcl_cot, cosmo_cot, cosmo_cot_force
+
+
+def nbody_adj_init(a, ptcl, ptcl_cot, cosmo, conf, threads=None):
+    """``pmwd/nbody.py:226-236``: returns ``(ptcl, ptcl_cot, cosmo_cot, cosmo_cot_force)``."""
+    ptcl, ptcl_cot, cosmo_cot_force = force_adj(a, ptcl, ptcl_cot, cosmo, conf, threads)
+    cosmo_cot = {'Omega_m': np.float64(0), 'growth': np.zeros_like(cosmo.growth)}
+    return ptcl, ptcl_cot, cosmo_cot, cosmo_cot_force
+
+
+def nbody_adj(ptcl, ptcl_cot, cosmo, conf, threads=None):
+    """``oracle.nbody.nbody_adj`` (``pmwd/nbody.py:226-260``)."""
+    a_nbody = conf.a_nbody
+    ptcl, ptcl_cot, cosmo_cot, ccf = nbody_adj_init(a_nbody[-1], ptcl, ptcl_cot, cosmo, conf, threads)
+    for a_prev, a_next in zip(a_nbody[:0:-1], a_nbody[-2::-1]):
+        ptcl, ptcl_cot, cosmo_cot, ccf = nbody_adj_step(a_prev, a_next, ptcl, ptcl_cot, cosmo, cosmo_cot, ccf,
+                                                        conf, threads)
+    return ptcl, ptcl_cot, cosmo_cot

@@ -132,10 +132,13 @@ class _Store:
         if self.lag is None:
             self.lag = torch.arange(n, dtype=torch.int32, device=dev)   # bit pattern of uint32
             self._perm = torch.empty(n, dtype=torch.int32, device=dev)
-            nbytes = lib.pmwd_cell_sort_scratch_bytes(C.byref(desc))
-            self._scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             self._alt = {k: torch.empty_like(v) for k, v in a.items()}
             self._alt['lag'] = torch.empty_like(self.lag)
+        # the sort's key width follows the mesh the descriptor spans (slab + halos, which grow
+        # during a run): re-query the scratch size every time and grow the buffer when needed
+        nbytes = lib.pmwd_cell_sort_scratch_bytes(C.byref(desc))
+        if self._scratch is None or self._scratch.numel() < nbytes:
+            self._scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
             _lib.check(lib.pmwd_cell_sort_perm(st, C.byref(desc), _lib.ptr(a['pmid']), _lib.ptr(a['disp']),
@@ -438,12 +441,13 @@ def _factor_valgrad(fun, a0, a1, a2, cosmo, conf):
     return float(val.detach()), grads
 
 
-def nbody_adj(ptcl, ptcl_cot, obsvbl_cot, cosmo, conf, reverse=False, _slab=None):
+def nbody_adj(ptcl, ptcl_cot, obsvbl_cot, cosmo, conf, reverse=False, _slab=None, _a_nbody=None):
     """N-body time integration with adjoint equation (``nbody.py:226-260``).
 
     ``_slab`` (internal): a ``dist.SlabForce`` when the particles are one rank's slab of a
     multi-GPU run; forces then go through the slab pipeline and the float64 dot products are
-    all-reduced once at the end.
+    all-reduced once at the end.  ``_a_nbody`` (internal, bench): a section of the schedule
+    (increasing scale factors) to integrate back over instead of ``conf.a_nbody``.
 
     Returns ``(ptcl, ptcl_cot, cosmo_cot)``; ``cosmo_cot`` is a dict leaf-name -> float64
     tensor over the leaves ``nbody`` can touch (all other leaves of the reference's
@@ -451,7 +455,7 @@ def nbody_adj(ptcl, ptcl_cot, obsvbl_cot, cosmo, conf, reverse=False, _slab=None
     """
     if not _fast_ok(ptcl, conf):
         raise NotImplementedError('the reverse-time adjoint runs on the 3-D int16 fast path')
-    a_nbody = conf.a_nbody.tolist()
+    a_nbody = conf.a_nbody.tolist() if _a_nbody is None else [float(x) for x in _a_nbody]
     if reverse:
         a_nbody = a_nbody[::-1]
     dev = ptcl.disp.device

@@ -80,3 +80,39 @@ def test_step_matches_numpy_oracle():
     for k in ('disp', 'vel', 'acc'):
         scale = np.abs(ref[k]).max()
         np.testing.assert_allclose(many[k], ref[k], rtol=0, atol=2e-5 * scale)
+
+
+def test_gravity_vjp_is_bit_exact_on_one_thread():
+    """The compiled adjoint force (scatter of pi, weight-gradient gathers, transposed k-space
+    algebra) against oracle.gravity_vjp: same float32 operation order -> same bits."""
+    conf, pmid, disp = _state(n=10, sigma=2.5)
+    rng = np.random.default_rng(3)
+    pi = rng.standard_normal(disp.shape).astype(np.float32)
+    acc, dcot, om = O.gravity_vjp(pmid, disp, 0.3, conf, pi)
+    acc1, dcot1, om1 = cpm.gravity_vjp(pmid, disp, 0.3, conf, pi, threads=1)
+    np.testing.assert_array_equal(acc1, acc)
+    np.testing.assert_array_equal(dcot1, dcot)
+    np.testing.assert_allclose(om1, om, rtol=1e-12)
+    accn, dcotn, omn = cpm.gravity_vjp(pmid, disp, 0.3, conf, pi, threads=4)
+    np.testing.assert_allclose(dcotn, dcot, rtol=0, atol=2e-5 * np.abs(dcot).max())
+    np.testing.assert_allclose(omn, om, rtol=1e-5)
+
+
+def test_adjoint_matches_numpy_oracle():
+    """cpm.nbody_adj (compiled reverse-time adjoint) vs oracle.nbody_adj on a 4-step 16^3 run."""
+    conf = O.Conf(1., (16, 16, 16), mesh_shape=2, a_nbody_maxstep=0.25)
+    cosmo = O.boltzmann(O.SimpleLCDM(conf), conf)
+    ptcl = O.lpt(O.linear_modes(O.white_noise(0, conf), cosmo, conf), cosmo, conf)
+    final = O.nbody(ptcl, cosmo, conf)
+    rng = np.random.default_rng(4)
+    cot = dict(disp=rng.standard_normal(final['disp'].shape).astype(np.float32),
+               vel=rng.standard_normal(final['disp'].shape).astype(np.float32),
+               acc=np.zeros_like(final['disp']))
+    p0, c0, cc0 = O.nbody_adj(dict(final), dict(cot), cosmo, conf)
+    p1, c1, cc1 = cpm.nbody_adj(dict(final), dict(cot), cosmo, conf, threads=1)
+    for k in ('disp', 'vel', 'acc'):
+        np.testing.assert_array_equal(p1[k], p0[k])
+        np.testing.assert_array_equal(c1[k], c0[k])
+    # the dot products are float64 here, float32 in NumPy: last digits of the cosmology cotangents
+    np.testing.assert_allclose(cc1['Omega_m'], cc0['Omega_m'], rtol=1e-5)
+    np.testing.assert_allclose(cc1['growth'], cc0['growth'], rtol=1e-4, atol=1e-6 * np.abs(cc0['growth']).max())
