@@ -60,6 +60,11 @@ typedef struct pmwd_cic_desc {
   double offset[3];       /* enmesh b12 */
 } pmwd_cic_desc;
 
+/* Which kernels a descriptor selects: 0 = general path (csrc/cic_generic.cu); 1 = fused 3-D fast
+ * path on an x-slab (int16 pmid, cell_size=None, offset = whole float32-cell planes along x, full
+ * y and z extents -- the multi-GPU slabs); 2 = fast path on the whole mesh (what pmwd_force needs). */
+int pmwd_cic_fast_path(const pmwd_cic_desc* d);
+
 /* ---- library / context ------------------------------------------------------------ */
 
 int pmwd_abi_version(void);

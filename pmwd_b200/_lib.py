@@ -47,6 +47,7 @@ _SIGNATURES = {
     'pmwd_abi_version': (_i, []),
     'pmwd_last_error': (_i, [C.c_char_p, _sz]),
     'pmwd_launch_count': (C.c_longlong, []),
+    'pmwd_cic_fast_path': (_i, [C.c_void_p]),
     'pmwd_profile_enable': (_i, [_i]),
     'pmwd_profile_stage_count': (_i, []),
     'pmwd_profile_stage_name': (C.c_char_p, [_i]),

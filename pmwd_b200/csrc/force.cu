@@ -150,6 +150,13 @@ static int force_forward(pmwd_ctx* ctx, cudaStream_t st, const pmwd_cic_desc* d,
 
 using namespace pmwd;
 
+// 1 if the descriptor qualifies for the fused 3-D kernels (int16 pmid, cell_size=None, offset =
+// whole planes along x only, full y / z extents); 2 if it additionally spans the whole mesh
+extern "C" int pmwd_cic_fast_path(const pmwd_cic_desc* d) {
+  if (!cic_is_fast(d)) return 0;
+  return cic_is_full_mesh(d) ? 2 : 1;
+}
+
 extern "C" size_t pmwd_scatter_scratch_bytes(const pmwd_cic_desc* d, int mode) {
   if (mode != PMWD_SCATTER_DETERMINISTIC) return 0;
   return scatter_det_scratch_bytes(d);

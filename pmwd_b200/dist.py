@@ -353,7 +353,10 @@ class SlabForce:
     def _desc(self, pmid, h):
         conf, comm = self.conf, self.comm
         _, My, Mz = conf.mesh_shape
-        off = ((comm.x0 - h) * conf.cell_size, 0.0, 0.0)
+        # whole planes of the float32 cell size enmesh divides by (pm_util.py:120: divmod(b12, a1)
+        # with a1 = float32(cell_size)), so that the remainder is exactly zero for ANY cell size,
+        # also one that float32 cannot represent (1/3, 0.05, ...): the fast-path kernels need it
+        off = ((comm.x0 - h) * float(np.float32(conf.cell_size)), 0.0, 0.0)
         return make_desc(conf, pmid, (comm.mx + 2 * h, My, Mz), 1, off, None)
 
     def _buffers(self, dev, h):
@@ -652,12 +655,12 @@ class SlabStepper:
         self.store.maybe_reorder(sync_max=self.comm.allreduce_max)
 
 
-def nbody_adj_slab(ptcl, ptcl_cot, cosmo, conf, comm, reverse=False, force=None):
+def nbody_adj_slab(ptcl, ptcl_cot, cosmo, conf, comm, reverse=False, force=None, _a_nbody=None):
     """``nbody_adj`` (pmwd/nbody.py:251-260) on this rank's slab: returns
     ``(ptcl, ptcl_cot, cosmo_cot)`` with ``cosmo_cot`` already summed over ranks."""
     from .nbody import nbody_adj
     force = force or SlabForce(conf, comm)
-    return nbody_adj(ptcl, ptcl_cot, None, cosmo, conf, reverse=reverse, _slab=force)
+    return nbody_adj(ptcl, ptcl_cot, None, cosmo, conf, reverse=reverse, _slab=force, _a_nbody=_a_nbody)
 
 
 def nbody_step_slab(a_prev, a_next, ptcl, cosmo, conf, comm, force=None):
@@ -762,6 +765,51 @@ def run_bench(args):
     assert torch.isfinite(store.arrays['disp']).all()
     Np = conf.ptcl_num
 
+    # ---- reverse-time adjoint back over the section just timed (BASELINE config 5: forward + adjoint
+    # on the slab decomposition; float64 dot products all-reduced once at the end)
+    fwd_adjoint = adjoint = None
+    if not getattr(args, 'no_adjoint', False):
+        i_end = stepper.i
+        ka = max(1, min(K, i_end))
+        section = a[i_end - ka:i_end + 1]
+        with torch.no_grad():
+            disp, vel = store.lagrangian('disp', 'vel')
+            final = Particles(conf, ic.pmid, disp, vel=vel)
+            g = torch.Generator(device=dev).manual_seed(1 + rank)
+            cot = Particles(conf, ic.pmid, torch.randn(disp.shape, device=dev, generator=g),
+                            vel=torch.randn(disp.shape, device=dev, generator=g))
+            del store, stepper, disp, vel
+            torch.cuda.empty_cache()
+            TIMERS.on = True
+            la0 = _lib.launch_count()
+            torch.cuda.synchronize(); dist.barrier()
+            e0.record()
+            _, pc, cc = nbody_adj_slab(final, cot, cosmo, conf, comm, force=force, _a_nbody=section)
+            e1.record()
+            torch.cuda.synchronize(); dist.barrier()
+            ams = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+            dist.all_reduce(ams, op=dist.ReduceOp.MAX)
+            ams = float(ams)
+            aphases = {k: round(v[0] / ka, 3) for k, v in TIMERS.read().items()}
+            TIMERS.on = False
+            launches_adj = _lib.launch_count() - la0
+        assert torch.isfinite(pc.disp).all() and torch.isfinite(pc.vel).all()
+        aper = ams / ka
+        Nm_ = conf.mesh_size
+        peak_, _src = B._peaks()
+        adjoint = {'ms_per_step': aper, 'steps': ka, 'includes': 'nbody_adj init (one force_adj) + steps',
+                   'particle_steps_per_sec': Np / (aper * 1e-3), 'adjoint_over_forward': aper / (ms / K),
+                   'gpu_launches': launches_adj, 'phase_ms_per_step_rank0': aphases,
+                   'step_frac': (312 * Np + 156 * Nm_) / world / aper / 1e6 / peak_,
+                   'cosmo_cot_Omega_m': float(cc['Omega_m'])}
+        fwd_adjoint = {'value': Np / ((aper + ms / K) * 1e-3),
+                       'unit': 'particle-steps/s (one forward + one adjoint step)',
+                       'ms_per_step': aper + ms / K, 'adjoint_ms_per_step': aper, 'forward_ms_per_step': ms / K,
+                       'step_frac': (444 * Np + 224 * Nm_) / world / (aper + ms / K) / 1e6 / peak_}
+        del final, cot, pc
+        torch.cuda.empty_cache()
+    store = stepper = None
+
     # ---- e2e: per-rank pinned host slabs -> device -> nbody_step_slab -> host, every step
     ke = max(1, min(K, args.e2e_steps))
     with torch.no_grad():
@@ -770,7 +818,7 @@ def run_bench(args):
                 for k in ('pmid', 'disp', 'vel', 'acc')}
         for k in host:
             host[k].copy_(getattr(p0, k))
-        del p0, store, stepper
+        del p0
         torch.cuda.empty_cache()
         h2d = sum(t.numel() * t.element_size() for t in host.values()) * world
         d2h = sum(host[k].numel() * host[k].element_size() for k in ('disp', 'vel', 'acc')) * world
@@ -808,7 +856,7 @@ def run_bench(args):
                          'kernel': 'whole step (per GPU)', 'traffic': None,
                          'achieved': (132 * Np + 68 * Nm) / world / (ms / K) / 1e6,
                          'frac': (132 * Np + 68 * Nm) / world / (ms / K) / 1e6 / peak},
-            'e2e': e2e, 'cpu_baseline': None,
+            'e2e': e2e, 'fwd_adjoint': fwd_adjoint, 'adjoint': adjoint, 'cpu_baseline': None,
         }
         getattr(args, '_emit', lambda l: print(json.dumps(l), flush=True))(line)
     dist.barrier()

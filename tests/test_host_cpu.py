@@ -175,3 +175,29 @@ def test_lpt_source_reuses_strain_transforms(monkeypatch):
         want = reference_loops(*pots)
         assert len(calls) == n_ref
         assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize('spacing, mesh_shape', [(1.0, 2), (1.0, 3), (0.1, 2), (0.7, 2), (0.041, 1), (1.0, 2.5)])
+def test_slab_descriptor_selects_the_fast_path_for_any_cell_size(spacing, mesh_shape):
+    """dist.SlabForce._desc must qualify for the fused slab kernels (pmwd_cic_fast_path >= 1) also when
+    conf.cell_size is not float32-representable (1/3, 0.05, 0.35, ...): the x offset is built from the
+    float32 cell size enmesh divides by (pm_util.py:120), so divmod leaves no remainder."""
+    import ctypes as C
+    import types
+    import torch
+    from pmwd_b200 import _lib
+    from pmwd_b200.configuration import Configuration
+    from pmwd_b200.dist import SlabForce
+    conf = Configuration(spacing, (8, 8, 8), mesh_shape=mesh_shape, device='cpu')
+    Mx = conf.mesh_shape[0]
+    pmid = torch.zeros((4, 3), dtype=torch.int16)
+    for P in (2, 4):
+        if Mx % P:
+            continue
+        for rank in range(P):
+            comm = types.SimpleNamespace(x0=rank * (Mx // P), mx=Mx // P, rank=rank, size=P)
+            for h in (1, 2, 5):
+                desc = SlabForce(conf, comm)._desc(pmid, h)
+                assert _lib.lib().pmwd_cic_fast_path(C.byref(desc)) == 1, (conf.cell_size, rank, h)
+    full = SlabForce(conf, types.SimpleNamespace(x0=0, mx=Mx, rank=0, size=1))._desc(pmid, 0)
+    assert _lib.lib().pmwd_cic_fast_path(C.byref(full)) == 2

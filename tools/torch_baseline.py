@@ -88,14 +88,9 @@ def check():
     return err
 
 
-def main():
-    if '--check' in sys.argv:
-        check()
-        return
-    args = [a for a in sys.argv[1:] if not a.startswith('--')]
-    n = int(args[0]) if args else 256
-    steps = int(args[1]) if len(args) > 1 else 5
-    dev = torch.device('cuda' if torch.cuda.is_available() else 'cpu')
+def time_steps(n=256, steps=5, dev=None):
+    """(particle-updates/s, ms/step) of the transcription at n^3 particles / (2n)^3 mesh."""
+    dev = dev or torch.device('cuda' if torch.cuda.is_available() else 'cpu')
     shape = (2 * n,) * 3
     g = torch.Generator(device=dev).manual_seed(0)
     ax = torch.arange(n, device=dev, dtype=torch.int16) * 2
@@ -111,8 +106,20 @@ def main():
         disp, vel, acc = step(pmid, disp, vel, acc, 0.5, shape, 0.3, 8.0, 1e-3, 1e-3, 1e-3)
     sync()
     dt = (time.perf_counter() - t0) / steps
-    print(f'torch transcription on {dev}: {n}^3 particles / {2 * n}^3 mesh, {dt * 1e3:.1f} ms/step = '
-          f'{n ** 3 / dt:.3g} particle-updates/s')
+    return n ** 3 / dt, dt * 1e3
+
+
+def main():
+    if '--check' in sys.argv:
+        check()
+        return
+    args = [a for a in sys.argv[1:] if not a.startswith('--')]
+    n = int(args[0]) if args else 256
+    steps = int(args[1]) if len(args) > 1 else 5
+    dev = torch.device('cuda' if torch.cuda.is_available() else 'cpu')
+    rate, ms = time_steps(n, steps, dev)
+    print(f'torch transcription on {dev}: {n}^3 particles / {2 * n}^3 mesh, {ms:.1f} ms/step = '
+          f'{rate:.3g} particle-updates/s')
 
 
 if __name__ == '__main__':
