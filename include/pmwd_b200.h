@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PMWD_B200_ABI_VERSION 1
+#define PMWD_B200_ABI_VERSION 2
 
 enum {
   PMWD_OK = 0,
@@ -59,6 +59,20 @@ typedef struct pmwd_cic_desc {
   double cell_size2;      /* user cell_size (enmesh a2); ignored unless general */
   double offset[3];       /* enmesh b12 */
 } pmwd_cic_desc;
+
+/* Tiled ("pencil sweep") CIC deposit, csrc/scatter_sweep.cu: particle storage sorted by
+ * (y-pencil of `ty` rows, x-plane, ...) + a table of the particle range of every (pencil, plane).
+ * Passed to pmwd_force / pmwd_force_kdk / pmwd_force_adj / pmwd_scatter_soa as an optional argument
+ * (NULL, or a descriptor that does not match the mesh: the per-particle RED kernel is used). */
+typedef struct pmwd_sweep {
+  const uint32_t* table;  /* device, [ny / ty][planes][2] = (first, one-past-last) particle slot */
+  int32_t ty;             /* rows per pencil (pmwd_sweep_pick_ty) */
+  int32_t lx;             /* planes per x segment of a work item (64 is a good value) */
+  int32_t nx_ext;         /* planes of the mesh array the table was built for (== desc mesh_shape[0]) */
+  int32_t xoff;           /* global index of its plane 0 (offset[0] / cell) */
+  void* scratch;          /* device, pmwd_sweep_scratch_bytes: work counters + straggler list */
+  size_t scratch_bytes;
+} pmwd_sweep;
 
 /* Which kernels a descriptor selects: 0 = general path (csrc/cic_generic.cu); 1 = fused 3-D fast
  * path on an x-slab (int16 pmid, cell_size=None, offset = whole float32-cell planes along x, full
@@ -181,6 +195,24 @@ int pmwd_powspec_weight(void* stream, const int32_t* shape, const void* f_c64, i
  * SoA scatter of 1 or 3 channels (rho, or the three V_i = scatter(pi_i) of gather.py:113): */
 int pmwd_scatter_soa(void* stream, const pmwd_cic_desc* d, const void* pmid, const float* disp,
                      const float* val, float val_scalar, int nch, float* m0, float* m1, float* m2);
+/* The same deposit through the tiled sweep kernels (see pmwd_sweep): the meshes are OVERWRITTEN
+ * (no memset by the caller); nch = 3 needs per-particle values float[N][3]. */
+int pmwd_scatter_sweep(void* stream, const pmwd_cic_desc* d, const pmwd_sweep* sweep, const void* pmid,
+                       const float* disp, const float* val, float val_scalar, int nch, float* m0,
+                       float* m1, float* m2);
+/* Pencil height for this mesh (8, 4 or 2; 0 = the sweep kernels do not support it), size of the
+ * (pencil, plane) table and of the scratch area (work counters + straggler list). */
+int pmwd_sweep_pick_ty(const pmwd_cic_desc* d);
+size_t pmwd_sweep_table_bytes(const pmwd_cic_desc* d, int ty);
+size_t pmwd_sweep_scratch_bytes(const pmwd_cic_desc* d);
+/* Build the table from the sorted keys of pmwd_cell_sort_perm(..., ty) (pmwd_cell_sort_sorted_keys)
+ * or, with keys == NULL, from pmid alone (storage in the Lagrangian C order of particles.py:135-139).
+ * status (device, 16 bytes): after synchronising, uint32 [0] must be 0 and uint64 [1] == ptcl_num,
+ * otherwise the storage order does not have one contiguous run per (pencil, plane). */
+int pmwd_sweep_table(void* stream, const pmwd_cic_desc* d, int ty, const uint32_t* keys,
+                     const void* pmid, uint32_t* table, void* status);
+/* Stragglers (particles outside their tile's window) of the last recording sweep; synchronises. */
+long long pmwd_sweep_last_stragglers(void* stream, const pmwd_sweep* sweep);
 /* acc[N][3] = (gather(f0), gather(f1), gather(f2)) in one pass (gravity.py:61-70), optionally
  * followed by vel += acc * kick_factor (nbody.py:70-77). */
 int pmwd_gather3(void* stream, const pmwd_cic_desc* d, const void* pmid, const float* disp,
@@ -228,28 +260,34 @@ size_t pmwd_force_workspace_bytes(const pmwd_cic_desc* d, int adjoint, int mode)
  * 3-D only; requires pmwd_ctx_reserve(ctx, 3, mesh_shape). */
 int pmwd_force(pmwd_ctx* ctx, void* stream, const pmwd_cic_desc* d, const void* pmid,
                const float* disp, double Omega_m, float* acc, float* kick_vel,
-               float kick_factor, int mode, void* workspace, size_t workspace_bytes);
+               float kick_factor, int mode, void* workspace, size_t workspace_bytes,
+               const pmwd_sweep* sweep);
 /* One whole KDK step (pmwd/nbody.py:121-140, pipelined across steps) in one call: the force at
  * the incoming disp, this step's trailing half-kick (K2) and the NEXT step's leading half-kick
  * and drift (K1_next, D_next) all applied in the gather pass.  disp/vel are updated in place;
  * float32 operation order identical to pmwd_force(+kick) followed by pmwd_kick_drift. */
 int pmwd_force_kdk(pmwd_ctx* ctx, void* stream, const pmwd_cic_desc* d, const void* pmid,
                    float* disp, double Omega_m, float* acc, float* vel, float K2, float K1_next,
-                   float D_next, int mode, void* workspace, size_t workspace_bytes);
+                   float D_next, int mode, void* workspace, size_t workspace_bytes,
+                   const pmwd_sweep* sweep);
 /* force_adj (pmwd/nbody.py:108-118): acc = gravity(ptcl) and alpha = VJP_disp(gravity)(pi).
  * The Omega_m cotangent is sum(pi . acc) / Omega_m, which pmwd_kick_adj reduces anyway. */
 int pmwd_force_adj(pmwd_ctx* ctx, void* stream, const pmwd_cic_desc* d, const void* pmid,
                    const float* disp, double Omega_m, const float* pi, float* acc,
-                   float* alpha, int mode, void* workspace, size_t workspace_bytes);
+                   float* alpha, int mode, void* workspace, size_t workspace_bytes,
+                   const pmwd_sweep* sweep);
 
 /* ---- Eulerian re-ordering of the particle storage (no reference counterpart) ---------- */
 /* The reference stores particles in Lagrangian order (pmwd/particles.py:135-139); the
  * integrator here periodically re-sorts its private copies by mesh cell so that scatter /
  * gather stay coalesced, and restores the reference order on output.
- * perm[i] = storage index of the particle that moves to sorted slot i (stable by cell). */
+ * perm[i] = storage index of the particle that moves to sorted slot i (stable by cell).
+ * ty == 0: key = (x>>1, y>>1, z) (2x2-cell columns along z); ty > 0: the sweep scatter's layout
+ * (y / ty, x, (y % ty) >> 1, z).  The sorted keys stay in `scratch` (pmwd_cell_sort_sorted_keys). */
 size_t pmwd_cell_sort_scratch_bytes(const pmwd_cic_desc* d);
 int pmwd_cell_sort_perm(void* stream, const pmwd_cic_desc* d, const void* pmid, const float* disp,
-                        uint32_t* perm, void* scratch, size_t scratch_bytes);
+                        uint32_t* perm, void* scratch, size_t scratch_bytes, int ty);
+const uint32_t* pmwd_cell_sort_sorted_keys(const pmwd_cic_desc* d, const void* scratch);
 /* For each of `narr` row-major arrays (row_bytes[a] bytes per particle, even):
  * inverse == 0: dst[i] = src[perm[i]];  inverse != 0: dst[perm[i]] = src[i]. */
 int pmwd_permute_rows(void* stream, int64_t n, const uint32_t* perm, int narr,

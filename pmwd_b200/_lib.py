@@ -36,6 +36,19 @@ class CicDesc(C.Structure):
     ]
 
 
+class Sweep(C.Structure):
+    """``pmwd_sweep`` of include/pmwd_b200.h."""
+    _fields_ = [
+        ('table', C.c_void_p),
+        ('ty', C.c_int32),
+        ('lx', C.c_int32),
+        ('nx_ext', C.c_int32),
+        ('xoff', C.c_int32),
+        ('scratch', C.c_void_p),
+        ('scratch_bytes', C.c_size_t),
+    ]
+
+
 _lib = None
 _lock = threading.Lock()
 
@@ -83,11 +96,18 @@ _SIGNATURES = {
     'pmwd_xpass_force': (_i, [_vp, _i32p, _i, _i, _d, _f, _vp, C.POINTER(_vp)]),
     'pmwd_xpass_force_adj': (_i, [_vp, _i32p, _i, _i, _d, _f, C.POINTER(_vp), _vp]),
     'pmwd_force_workspace_bytes': (_sz, [_descp, _i, _i]),
-    'pmwd_force': (_i, [_vp, _vp, _descp, _vp, _vp, _d, _vp, _vp, _f, _i, _vp, _sz]),
-    'pmwd_force_kdk': (_i, [_vp, _vp, _descp, _vp, _vp, _d, _vp, _vp, _f, _f, _f, _i, _vp, _sz]),
-    'pmwd_force_adj': (_i, [_vp, _vp, _descp, _vp, _vp, _d, _vp, _vp, _vp, _i, _vp, _sz]),
+    'pmwd_force': (_i, [_vp, _vp, _descp, _vp, _vp, _d, _vp, _vp, _f, _i, _vp, _sz, _vp]),
+    'pmwd_force_kdk': (_i, [_vp, _vp, _descp, _vp, _vp, _d, _vp, _vp, _f, _f, _f, _i, _vp, _sz, _vp]),
+    'pmwd_force_adj': (_i, [_vp, _vp, _descp, _vp, _vp, _d, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
+    'pmwd_scatter_sweep': (_i, [_vp, _descp, _vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp]),
+    'pmwd_sweep_pick_ty': (_i, [_descp]),
+    'pmwd_sweep_table_bytes': (_sz, [_descp, _i]),
+    'pmwd_sweep_scratch_bytes': (_sz, [_descp]),
+    'pmwd_sweep_table': (_i, [_vp, _descp, _i, _vp, _vp, _vp, _vp]),
+    'pmwd_sweep_last_stragglers': (C.c_longlong, [_vp, _vp]),
     'pmwd_cell_sort_scratch_bytes': (_sz, [_descp]),
-    'pmwd_cell_sort_perm': (_i, [_vp, _descp, _vp, _vp, _vp, _vp, _sz]),
+    'pmwd_cell_sort_perm': (_i, [_vp, _descp, _vp, _vp, _vp, _vp, _sz, _i]),
+    'pmwd_cell_sort_sorted_keys': (_vp, [_descp, _vp]),
     'pmwd_permute_rows': (_i, [_vp, _i64, _vp, _i, C.POINTER(_vp), C.POINTER(_vp), _i32p, _i]),
     'pmwd_transpose_p2p': (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, C.POINTER(C.c_uint64)]),
     'pmwd_kick_drift': (_i, [_vp, _i64, _vp, _vp, _vp, _f, _f, _i, _i]),
@@ -113,7 +133,7 @@ def lib():
                 fn = getattr(handle, name)
                 fn.restype = res
                 fn.argtypes = args
-            if handle.pmwd_abi_version() != 1:
+            if handle.pmwd_abi_version() != 2:
                 raise PmwdError('libpmwd_b200.so ABI version mismatch')
             _lib = handle
     return _lib

@@ -68,6 +68,7 @@ class Configuration:
     reorder_every: int = 3                # re-sort the integrator's particle storage by mesh cell
                                           # every this many steps (0 = never; see csrc/reorder.cu)
     reorder_min_disp: float = 1.0         # ... once max |disp| exceeds this many cells
+    scatter_tiled: bool = True            # integrator deposits through shared-memory mesh tiles (csrc/scatter_sweep.cu)
     device: Union[str, torch.device] = 'cuda'
 
     def __post_init__(self):

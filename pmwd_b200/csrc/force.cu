@@ -35,6 +35,11 @@ int gather3_fast(cudaStream_t st, const pmwd_cic_desc* d, const void* pmid, cons
 int force_adj_gather(cudaStream_t st, const pmwd_cic_desc* d, const void* pmid, const float* disp,
                      const float* f0, const float* f1, const float* f2, const float* rho_cot,
                      const float* pi, float val, float* alpha);
+// scatter_sweep.cu
+bool sweep_usable(const pmwd_cic_desc* d, const pmwd_sweep* sw);
+int scatter_sweep(cudaStream_t st, const pmwd_cic_desc* d, const pmwd_sweep* sw, const void* pmid,
+                  const float* disp, const float* val, int vstride, float vscalar, float* mesh,
+                  bool reuse_stragglers);
 // scatter_det.cu
 size_t scatter_det_scratch_bytes(const pmwd_cic_desc* d);
 int scatter_det(cudaStream_t st, const pmwd_cic_desc* d, const void* pmid, const float* disp,
@@ -101,21 +106,25 @@ static int check_force_args(const pmwd_cic_desc* d) {
 
 static int force_forward(pmwd_ctx* ctx, cudaStream_t st, const pmwd_cic_desc* d, const void* pmid,
                          const float* disp, double Omega_m, int mode, char* ws,
-                         const ForceLayout& L, float* val_out) {
+                         const ForceLayout& L, float* val_out, const pmwd_sweep* sweep) {
   const int32_t* shape = d->mesh_shape;
   const int64_t nm = (int64_t)shape[0] * shape[1] * shape[2];
   float* rho = (float*)(ws + L.rho_f0);
   // scatter.py:37-39: val = conf.mesh_size / conf.ptcl_num (python float -> float32)
   const float val = (float)((double)nm / (double)d->ptcl_num);
   if (val_out) *val_out = val;
-  {
+  // tiled sweep scatter (scatter_sweep.cu): overwrites rho, no memset
+  const bool sweeping = mode != PMWD_SCATTER_DETERMINISTIC && sweep_usable(d, sweep);
+  if (!sweeping) {
     StageTimer t(ST_MEMSET, st);
     PMWD_CUDA_TRY(cudaMemsetAsync(rho, 0, (size_t)nm * sizeof(float), st));
   }
   int rc;
   {
     StageTimer t(ST_SCATTER, st);
-    if (mode == PMWD_SCATTER_DETERMINISTIC)
+    if (sweeping)
+      rc = scatter_sweep(st, d, sweep, pmid, disp, nullptr, 0, val, rho, false);
+    else if (mode == PMWD_SCATTER_DETERMINISTIC)
       rc = scatter_det(st, d, pmid, disp, nullptr, val, 1, rho, nullptr, nullptr, ws + L.det,
                        L.total - L.det);
     else
@@ -251,7 +260,8 @@ extern "C" size_t pmwd_force_workspace_bytes(const pmwd_cic_desc* d, int adjoint
 
 extern "C" int pmwd_force(pmwd_ctx* ctx, void* stream, const pmwd_cic_desc* d, const void* pmid,
                           const float* disp, double Omega_m, float* acc, float* kick_vel,
-                          float kick_factor, int mode, void* workspace, size_t workspace_bytes) {
+                          float kick_factor, int mode, void* workspace, size_t workspace_bytes,
+                          const pmwd_sweep* sweep) {
   int rc = check_force_args(d);
   if (rc) return rc;
   PMWD_REQUIRE(ctx && pmid && disp && acc && workspace, "null buffer");
@@ -264,7 +274,7 @@ extern "C" int pmwd_force(pmwd_ctx* ctx, void* stream, const pmwd_cic_desc* d, c
   }
   cudaStream_t st = as_stream(stream);
   char* ws = (char*)workspace;
-  rc = force_forward(ctx, st, d, pmid, disp, Omega_m, mode, ws, L, nullptr);
+  rc = force_forward(ctx, st, d, pmid, disp, Omega_m, mode, ws, L, nullptr, sweep);
   if (rc) return rc;
   StageTimer t(ST_GATHER, st);
   return gather3_fast(st, d, pmid, disp, (float*)(ws + L.rho_f0), (float*)(ws + L.f1),
@@ -280,7 +290,7 @@ extern "C" int pmwd_force(pmwd_ctx* ctx, void* stream, const pmwd_cic_desc* d, c
 extern "C" int pmwd_force_kdk(pmwd_ctx* ctx, void* stream, const pmwd_cic_desc* d, const void* pmid,
                               float* disp, double Omega_m, float* acc, float* vel, float K2,
                               float K1_next, float D_next, int mode, void* workspace,
-                              size_t workspace_bytes) {
+                              size_t workspace_bytes, const pmwd_sweep* sweep) {
   int rc = check_force_args(d);
   if (rc) return rc;
   PMWD_REQUIRE(ctx && pmid && disp && acc && vel && workspace, "null buffer");
@@ -293,7 +303,7 @@ extern "C" int pmwd_force_kdk(pmwd_ctx* ctx, void* stream, const pmwd_cic_desc* 
   }
   cudaStream_t st = as_stream(stream);
   char* ws = (char*)workspace;
-  rc = force_forward(ctx, st, d, pmid, disp, Omega_m, mode, ws, L, nullptr);
+  rc = force_forward(ctx, st, d, pmid, disp, Omega_m, mode, ws, L, nullptr, sweep);
   if (rc) return rc;
   const float next_kd[2] = {K1_next, D_next};
   StageTimer t(ST_GATHER, st);
@@ -304,7 +314,7 @@ extern "C" int pmwd_force_kdk(pmwd_ctx* ctx, void* stream, const pmwd_cic_desc* 
 extern "C" int pmwd_force_adj(pmwd_ctx* ctx, void* stream, const pmwd_cic_desc* d,
                               const void* pmid, const float* disp, double Omega_m,
                               const float* pi, float* acc, float* alpha, int mode,
-                              void* workspace, size_t workspace_bytes) {
+                              void* workspace, size_t workspace_bytes, const pmwd_sweep* sweep) {
   int rc = check_force_args(d);
   if (rc) return rc;
   PMWD_REQUIRE(ctx && pmid && disp && pi && acc && alpha && workspace, "null buffer");
@@ -320,7 +330,7 @@ extern "C" int pmwd_force_adj(pmwd_ctx* ctx, void* stream, const pmwd_cic_desc* 
   const int32_t* shape = d->mesh_shape;
   const int64_t nm = (int64_t)shape[0] * shape[1] * shape[2];
   float val = 0.f;
-  rc = force_forward(ctx, st, d, pmid, disp, Omega_m, mode, ws, L, &val);
+  rc = force_forward(ctx, st, d, pmid, disp, Omega_m, mode, ws, L, &val, sweep);
   if (rc) return rc;
   float* F[3] = {(float*)(ws + L.rho_f0), (float*)(ws + L.f1), (float*)(ws + L.f2)};
   {
@@ -332,13 +342,17 @@ extern "C" int pmwd_force_adj(pmwd_ctx* ctx, void* stream, const pmwd_cic_desc* 
   // V_i = scatter(pi_i): the mesh_cot of _gather_bwd (gather.py:113), SoA, in the (now free)
   // gradient-spectrum buffers
   float* V[3] = {(float*)(ws + L.g[0]), (float*)(ws + L.g[1]), (float*)(ws + L.g[2])};
-  {
+  const bool sweeping = mode != PMWD_SCATTER_DETERMINISTIC && sweep_usable(d, sweep);
+  if (!sweeping) {
     StageTimer t(ST_MEMSET, st);
     for (int a = 0; a < 3; ++a) PMWD_CUDA_TRY(cudaMemsetAsync(V[a], 0, (size_t)nm * sizeof(float), st));
   }
   {
     StageTimer t(ST_SCATTER3, st);
-    if (mode == PMWD_SCATTER_DETERMINISTIC)
+    if (sweeping) {
+      // one sweep per channel; the straggler list recorded by the density scatter is reused
+      for (int a = 0; a < 3 && !rc; ++a) rc = scatter_sweep(st, d, sweep, pmid, disp, pi + a, 3, 0.f, V[a], true);
+    } else if (mode == PMWD_SCATTER_DETERMINISTIC)
       rc = scatter_det(st, d, pmid, disp, pi, 0.f, 3, V[0], V[1], V[2], ws + L.det, L.total - L.det);
     else
       rc = scatter_fast(st, d, pmid, disp, pi, 0.f, 3, V[0], V[1], V[2]);

@@ -28,6 +28,7 @@ struct SortParams {
   int nx_ext, xoff; // slab: planes held locally and global index of the first one
   int shift;        // xy footprint of a storage "column" is (1<<shift)^2 cells
   int nyc;          // ceil(ny >> shift)
+  int ty;           // > 0: sweep layout (y / ty, x, (y % ty) >> 1, z) -- scatter_sweep.cu
   float cell;
 };
 
@@ -49,7 +50,12 @@ sort_keys_kernel(SortParams P, const short* __restrict__ pmid, const float* __re
     // columns of (1<<shift)^2 cells in (x, y), ordered by z inside: consecutive particles are
     // as dense along the contiguous z axis as the Lagrangian lattice was, which is what makes
     // a warp's 32 stencils share 32-byte sectors
-    keys[p] = (uint32_t)(((int64_t)(lx >> P.shift) * P.nyc + (c[1] >> P.shift)) * P.nz + c[2]);
+    if (P.ty > 0) {
+      const int pencil = c[1] / P.ty, yin = c[1] - pencil * P.ty;
+      keys[p] = (uint32_t)((((int64_t)pencil * P.nx_ext + lx) * (P.ty >> 1) + (yin >> 1)) * P.nz + c[2]);
+    } else {
+      keys[p] = (uint32_t)(((int64_t)(lx >> P.shift) * P.nyc + (c[1] >> P.shift)) * P.nz + c[2]);
+    }
     vals[p] = (uint32_t)p;
   }
 }
@@ -116,9 +122,14 @@ extern "C" size_t pmwd_cell_sort_scratch_bytes(const pmwd_cic_desc* d) {
   return L.total;
 }
 
+extern "C" const uint32_t* pmwd_cell_sort_sorted_keys(const pmwd_cic_desc* d, const void* scratch) {
+  if (!d || !scratch) return nullptr;
+  return (const uint32_t*)((const char*)scratch + 2 * align_up((size_t)d->ptcl_num * 4));
+}
+
 extern "C" int pmwd_cell_sort_perm(void* stream, const pmwd_cic_desc* d, const void* pmid,
                                    const float* disp, uint32_t* perm, void* scratch,
-                                   size_t scratch_bytes) {
+                                   size_t scratch_bytes, int ty) {
   PMWD_REQUIRE(d && d->dim == 3 && d->pmid_bytes == 2 && !d->general,
                "cell sort supports the 3-D int16 fast path");
   PMWD_REQUIRE(perm && scratch, "null buffer");
@@ -128,6 +139,9 @@ extern "C" int pmwd_cell_sort_perm(void* stream, const pmwd_cic_desc* d, const v
   P.nx_ext = d->mesh_shape[0];
   P.xoff = slab_xoff(d);
   P.cell = (float)d->cell_size;
+  PMWD_REQUIRE(ty >= 0 && (ty == 0 || (ty % 2 == 0 && d->wrap_shape[1] % ty == 0)),
+               "sweep key layout needs an even ty that divides the y extent");
+  P.ty = ty;
   {
     const char* e = getenv("PMWD_SORT_SHIFT");
     P.shift = e ? atoi(e) : 1;

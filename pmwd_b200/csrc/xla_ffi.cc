@@ -43,7 +43,8 @@ ffi::Error ForceImpl(cudaStream_t stream, ffi::Buffer<ffi::S16> pmid, ffi::Buffe
   pmwd_cic_desc d = FastDesc(pmid.dimensions()[0], mesh, cell_size);
   return Check(pmwd_force(reinterpret_cast<pmwd_ctx*>(ctx), stream, &d, pmid.typed_data(),
                           disp.typed_data(), Omega_m, acc->typed_data(), nullptr, 0.f,
-                          PMWD_SCATTER_ATOMIC, workspace.typed_data(), workspace.size_bytes()));
+                          PMWD_SCATTER_ATOMIC, workspace.typed_data(), workspace.size_bytes(),
+                          /*sweep=*/nullptr));
 }
 
 // force_adj(): pmwd/nbody.py:108-118 (gravity and its VJP w.r.t. disp for the cotangent pi)
@@ -55,7 +56,7 @@ ffi::Error ForceAdjImpl(cudaStream_t stream, ffi::Buffer<ffi::S16> pmid, ffi::Bu
   return Check(pmwd_force_adj(reinterpret_cast<pmwd_ctx*>(ctx), stream, &d, pmid.typed_data(),
                               disp.typed_data(), Omega_m, pi.typed_data(), acc->typed_data(),
                               alpha->typed_data(), PMWD_SCATTER_ATOMIC, workspace.typed_data(),
-                              workspace.size_bytes()));
+                              workspace.size_bytes(), /*sweep=*/nullptr));
 }
 
 // kick + drift: pmwd/nbody.py:39-46,70-77 (functional: outputs alias-free copies made by XLA)

@@ -142,7 +142,7 @@ def _mode(conf):
     return _lib.SCATTER_DETERMINISTIC if conf.scatter_mode == 'deterministic' else _lib.SCATTER_ATOMIC
 
 
-def force_into(pmid, disp, Omega_m, conf, acc, kick_vel=None, kick_factor=0.0):
+def force_into(pmid, disp, Omega_m, conf, acc, kick_vel=None, kick_factor=0.0, sweep=None):
     """Enqueue ``pmwd_force``: ``acc <- gravity`` (and ``kick_vel += acc * kick_factor``)."""
     dev = disp.device
     desc = _force_desc(pmid, conf)
@@ -155,10 +155,10 @@ def force_into(pmid, disp, Omega_m, conf, acc, kick_vel=None, kick_factor=0.0):
         _lib.check(lib.pmwd_force(
             ctx.handle, _lib.stream_ptr(dev), C.byref(desc), _lib.ptr(pmid), _lib.ptr(disp),
             float(Omega_m), _lib.ptr(acc), _lib.ptr(kick_vel), float(kick_factor), mode,
-            _lib.ptr(ws), ws.numel()), 'pmwd_force')
+            _lib.ptr(ws), ws.numel(), sweep), 'pmwd_force')
 
 
-def force_kdk_into(pmid, disp, Omega_m, conf, acc, vel, K2, K1_next, D_next):
+def force_kdk_into(pmid, disp, Omega_m, conf, acc, vel, K2, K1_next, D_next, sweep=None):
     """Enqueue ``pmwd_force_kdk``: force at ``disp``, trailing half-kick ``K2``, then the next
     step's leading half-kick ``K1_next`` and drift ``D_next`` -- one call per KDK step."""
     dev = disp.device
@@ -172,10 +172,10 @@ def force_kdk_into(pmid, disp, Omega_m, conf, acc, vel, K2, K1_next, D_next):
         _lib.check(lib.pmwd_force_kdk(
             ctx.handle, _lib.stream_ptr(dev), C.byref(desc), _lib.ptr(pmid), _lib.ptr(disp),
             float(Omega_m), _lib.ptr(acc), _lib.ptr(vel), float(K2), float(K1_next), float(D_next), mode,
-            _lib.ptr(ws), ws.numel()), 'pmwd_force_kdk')
+            _lib.ptr(ws), ws.numel(), sweep), 'pmwd_force_kdk')
 
 
-def force_adj_into(pmid, disp, Omega_m, conf, pi, acc, alpha):
+def force_adj_into(pmid, disp, Omega_m, conf, pi, acc, alpha, sweep=None):
     """Enqueue ``pmwd_force_adj``: ``acc <- gravity``, ``alpha <- VJP_disp(gravity)(pi)``."""
     dev = disp.device
     desc = _force_desc(pmid, conf)
@@ -188,7 +188,7 @@ def force_adj_into(pmid, disp, Omega_m, conf, pi, acc, alpha):
         _lib.check(lib.pmwd_force_adj(
             ctx.handle, _lib.stream_ptr(dev), C.byref(desc), _lib.ptr(pmid), _lib.ptr(disp),
             float(Omega_m), _lib.ptr(pi), _lib.ptr(acc), _lib.ptr(alpha), mode,
-            _lib.ptr(ws), ws.numel()), 'pmwd_force_adj')
+            _lib.ptr(ws), ws.numel(), sweep), 'pmwd_force_adj')
 
 
 def _gravity_general(ptcl, cosmo, conf):

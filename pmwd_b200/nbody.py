@@ -18,6 +18,7 @@ from .boltzmann import growth
 from .cosmology import E2, H_deriv
 from .gravity import gravity, force_into, force_adj_into, force_kdk_into, _force_desc
 from .particles import Particles
+from . import sweep as _sweep
 
 
 def _G_D(a, cosmo, conf):
@@ -99,6 +100,24 @@ class _Store:
         self.active = False
         self.reorders = 0
         self.desc_fn = None        # pmid -> pmwd_cic_desc used for the sort keys (slab runs)
+        self.sweep = None          # sweep.SweepState: table + scratch of the tiled deposit
+
+    def setup_sweep(self):
+        """Tiled deposit (csrc/scatter_sweep.cu) for the single-device fast path: the table is first
+        derived from pmid (Lagrangian C order), later rebuilt from every re-sort.  An order without
+        one contiguous run per (pencil, plane) leaves the RED kernel in charge until the first sort."""
+        conf, a = self.conf, self.arrays
+        if self.desc_fn is not None or not _sweep.enabled(conf) or conf.dim != 3 \
+                or a['pmid'].dtype != torch.int16:
+            return
+        desc = _force_desc(a['pmid'], conf)
+        st = _sweep.SweepState(desc, a['disp'].device)
+        if st.ty > 0:
+            st.build(desc, pmid=a['pmid'], check=True)
+            self.sweep = st
+
+    def sweep_arg(self):
+        return self.sweep.arg() if self.sweep is not None else None
 
     @property
     def ptcl(self):
@@ -141,9 +160,10 @@ class _Store:
             self._scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
+            ty = self.sweep.ty if self.sweep is not None else 0
             _lib.check(lib.pmwd_cell_sort_perm(st, C.byref(desc), _lib.ptr(a['pmid']), _lib.ptr(a['disp']),
                                                _lib.ptr(self._perm), _lib.ptr(self._scratch),
-                                               self._scratch.numel()), 'pmwd_cell_sort_perm')
+                                               self._scratch.numel(), ty), 'pmwd_cell_sort_perm')
             names = list(a) + ['lag']
             cur = dict(a, lag=self.lag)
             src = (C.c_void_p * len(names))(*[cur[k].data_ptr() for k in names])
@@ -157,6 +177,10 @@ class _Store:
         self._alt = dict(a, lag=self.lag)
         self.arrays, self.lag = new, new_lag
         self.reorders += 1
+        if self.sweep is not None:
+            # table of the new order from the sort's own keys (valid by construction: no read-back)
+            keys = lib.pmwd_cell_sort_sorted_keys(C.byref(desc), _lib.ptr(self._scratch))
+            self.sweep.build(desc, keys_ptr=C.c_void_p(keys), check=False)
 
     def lagrangian(self, *names):
         """Arrays restored to Lagrangian order (new tensors; storage untouched)."""
@@ -183,7 +207,9 @@ def _store_from(ptcl, conf, **extra):
     pmid = p.pmid.clone() if conf.reorder_every > 0 else p.pmid
     arrays = dict(pmid=pmid, disp=p.disp, vel=p.vel, acc=p.acc)
     arrays.update(extra)
-    return _Store(conf, arrays)
+    store = _Store(conf, arrays)
+    store.setup_sweep()
+    return store
 
 
 # --------------------------------------------------------------- reference-shaped pieces
@@ -385,7 +411,11 @@ class _Stepper:
         return len(self.a) - 1
 
     def init(self):
-        _force_inplace(self.store.ptcl, self.cosmo, self.conf)
+        p = self.store.ptcl
+        if _fast_ok(p, self.conf):
+            force_into(p.pmid, p.disp, float(self.cosmo.Omega_m), self.conf, p.acc, sweep=self.store.sweep_arg())
+        else:
+            _force_inplace(p, self.cosmo, self.conf)
 
     def step(self):
         i = self.i
@@ -400,10 +430,11 @@ class _Stepper:
             Om = float(self.cosmo.Omega_m)
             if i + 1 < self.nsteps:
                 k1n, dn, _ = self.factors(i + 1)
-                force_kdk_into(a['pmid'], a['disp'], Om, self.conf, a['acc'], a['vel'], k2, k1n, dn)
+                force_kdk_into(a['pmid'], a['disp'], Om, self.conf, a['acc'], a['vel'], k2, k1n, dn,
+                               sweep=st.sweep_arg())
                 self.pre = True
             else:
-                force_into(a['pmid'], a['disp'], Om, self.conf, a['acc'], a['vel'], k2)
+                force_into(a['pmid'], a['disp'], Om, self.conf, a['acc'], a['vel'], k2, sweep=st.sweep_arg())
                 self.pre = False
         self.i += 1
         st.maybe_reorder()
@@ -495,7 +526,8 @@ def nbody_adj(ptcl, ptcl_cot, obsvbl_cot, cosmo, conf, reverse=False, _slab=None
             if _slab is not None:
                 _slab.force_adj(a['pmid'], a['disp'], Om, a['pi'], a['acc'], a['alpha'])
             else:
-                force_adj_into(a['pmid'], a['disp'], Om, conf, a['pi'], a['acc'], a['alpha'])
+                force_adj_into(a['pmid'], a['disp'], Om, conf, a['pi'], a['acc'], a['alpha'],
+                               sweep=store.sweep_arg())
 
         # nbody_adj_init (nbody.py:226-236)
         f_adj()

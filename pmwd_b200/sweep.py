@@ -1,0 +1,87 @@
+"""Host side of the tiled ("pencil sweep") CIC deposit, ``csrc/scatter_sweep.cu``.
+
+The reference's ``_scatter`` (``pmwd/scatter.py:33-83``) is one XLA scatter-add over all particles.
+Inside the integrator the deposit instead goes through shared-memory mesh tiles: the particle
+storage is kept sorted by (y-pencil, x-plane, ...) -- or is still in the reference's Lagrangian C
+order (``pmwd/particles.py:135-139``), which has the same segment structure -- and a small table
+gives the particle range of every (pencil, plane).  This module owns that table and the scratch
+area (work counters + straggler list) and hands them to the C library as a ``pmwd_sweep``.
+"""
+import ctypes as C
+import os
+
+import torch
+
+from . import _lib
+
+LX = 64     # planes per x segment of a work item
+
+
+def enabled(conf):
+    return (getattr(conf, 'scatter_tiled', True) and conf.scatter_mode == 'atomic'
+            and os.environ.get('PMWD_SWEEP', '1') != '0')
+
+
+class SweepState:
+    """Table + scratch of one particle store for one mesh descriptor."""
+
+    def __init__(self, desc, dev, lx=LX):
+        lib = _lib.lib()
+        self.ty = int(lib.pmwd_sweep_pick_ty(C.byref(desc)))
+        self.ok = False
+        self.dev = dev
+        if self.ty <= 0:
+            return
+        self.lx = lx
+        self.nx_ext = int(desc.mesh_shape[0])
+        self.table = torch.zeros(lib.pmwd_sweep_table_bytes(C.byref(desc), self.ty) // 4, dtype=torch.int32,
+                                 device=dev)
+        self.scratch = torch.empty(lib.pmwd_sweep_scratch_bytes(C.byref(desc)), dtype=torch.uint8, device=dev)
+        self.status = torch.zeros(2, dtype=torch.int64, device=dev)
+        self._struct = None
+        self.n = int(desc.ptcl_num)
+
+    def _make_struct(self, desc):
+        s = _lib.Sweep()
+        s.table = self.table.data_ptr()
+        s.ty, s.lx = self.ty, self.lx
+        s.nx_ext = int(desc.mesh_shape[0])
+        a1 = float(torch.tensor(desc.cell_size, dtype=torch.float32))
+        s.xoff = int(desc.offset[0] // a1) % int(desc.wrap_shape[0])
+        s.scratch = self.scratch.data_ptr()
+        s.scratch_bytes = self.scratch.numel()
+        self._struct = s
+
+    def build(self, desc, pmid=None, keys_ptr=None, check=True):
+        """(Re)build the table from the sort's keys (``keys_ptr``) or from ``pmid`` (Lagrangian order).
+        With ``check`` the device-side validation is read back (one synchronisation); an invalid
+        table leaves the state unusable (``ok`` False) and the RED kernel in charge."""
+        if self.ty <= 0:
+            return False
+        lib = _lib.lib()
+        with torch.cuda.device(self.dev):
+            _lib.check(lib.pmwd_sweep_table(_lib.stream_ptr(self.dev), C.byref(desc), self.ty,
+                                            keys_ptr if keys_ptr is not None else None,
+                                            _lib.ptr(pmid) if keys_ptr is None else None,
+                                            _lib.ptr(self.table), _lib.ptr(self.status)), 'pmwd_sweep_table')
+        self.ok = True
+        if check:
+            st = self.status.cpu()
+            bad = int(st[0]) & 0xffffffff
+            total = int(st[1])
+            self.ok = bad == 0 and total == self.n
+        if self.ok:
+            self._make_struct(desc)
+        return self.ok
+
+    def arg(self):
+        """``const pmwd_sweep*`` for the C calls (NULL when unusable)."""
+        if not self.ok or self._struct is None:
+            return None
+        return C.byref(self._struct)
+
+    def stragglers(self):
+        if not self.ok:
+            return -1
+        with torch.cuda.device(self.dev):
+            return int(_lib.lib().pmwd_sweep_last_stragglers(_lib.stream_ptr(self.dev), C.byref(self._struct)))

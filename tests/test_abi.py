@@ -35,7 +35,7 @@ def test_header_symbols_exported(lib):
 
 def test_abi_version_and_errors(lib):
     from pmwd_b200 import _lib
-    assert lib.pmwd_abi_version() == 1
+    assert lib.pmwd_abi_version() == 2
     # bad arguments -> negative status + message, no crash, no GPU needed
     rc = lib.pmwd_laplace(None, 5, _lib.shape_arr((4, 4, 4)), 1.0, None, None)
     assert rc == -1 and 'rank' in _lib.last_error()
@@ -96,7 +96,7 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
     src.write_text('#include <string.h>\n#include "pmwd_b200.h"\n'
                    'int main(void) {\n'
                    '  char msg[64];\n'
-                   '  if (pmwd_abi_version() != 1) return 1;\n'
+                   '  if (pmwd_abi_version() != 2) return 1;\n'
                    '  /* a bad call must fail with a negative status and leave a message */\n'
                    '  if (pmwd_laplace(0, 3, 0, 1.0, 0, 0) >= 0) return 2;\n'
                    '  pmwd_last_error(msg, sizeof msg);\n'

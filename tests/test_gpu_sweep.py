@@ -1,0 +1,158 @@
+"""GPU parity of the tiled ("pencil sweep") CIC deposit (csrc/scatter_sweep.cu) against the oracle's
+scatter (pmwd/scatter.py:60-83) and against the per-particle RED kernel, in Lagrangian order, in
+re-sorted order, with stale sorts (stragglers), 3 channels, anisotropic meshes and slab descriptors.
+Tolerance: per-cell density rel. err <= 1e-5 (of max(density, 1)), the north-star figure."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(shape, sigma, seed=0, **kw):
+    import pmwd_b200 as pm
+    conf = pm.Configuration(1., shape, mesh_shape=2, **kw)
+    oconf = O.Conf(1., shape, mesh_shape=2)
+    pmid, disp, _, _ = O.gen_grid(oconf)
+    rng = np.random.default_rng(seed)
+    disp = (disp + sigma * conf.cell_size * rng.standard_normal(disp.shape)).astype(np.float32)
+    ptcl = pm.Particles(conf, torch.from_numpy(np.ascontiguousarray(pmid)).cuda(), torch.from_numpy(disp).cuda(),
+                        vel=torch.zeros(disp.shape, device='cuda'))
+    return pm, conf, oconf, pmid, disp, ptcl
+
+
+def _sweep_scatter(store, conf, val=None, nch=1):
+    from pmwd_b200 import _lib
+    from pmwd_b200.gravity import _force_desc
+    a = store.arrays
+    desc = _force_desc(a['pmid'], conf)
+    dev = a['disp'].device
+    # garbage-filled outputs: the sweep must overwrite every cell
+    m = [torch.full(tuple(conf.mesh_shape), 7.5, device=dev) for _ in range(nch)]
+    arg = store.sweep_arg()
+    assert arg is not None
+    _lib.check(_lib.lib().pmwd_scatter_sweep(
+        _lib.stream_ptr(dev), C.byref(desc), arg, _lib.ptr(a['pmid']), _lib.ptr(a['disp']),
+        _lib.ptr(val), float(conf.mesh_size / conf.ptcl_num), nch, _lib.ptr(m[0]),
+        _lib.ptr(m[1]) if nch == 3 else None, _lib.ptr(m[2]) if nch == 3 else None), 'pmwd_scatter_sweep')
+    torch.cuda.synchronize()
+    return m
+
+
+def _close(got, want):
+    got = got.cpu().numpy().astype(np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    assert abs(got.sum() - want.sum()) <= 1e-6 * abs(want).sum() + 1e-3
+    rel = np.abs(got - want) / np.maximum(np.abs(want), 1.0)
+    assert rel.max() <= 1e-5, rel.max()
+
+
+@pytest.mark.parametrize('shape, sigma', [((32, 32, 32), 0.3), ((32, 32, 32), 3.0), ((12, 10, 18), 0.4),
+                                          ((8, 8, 512), 0.5), ((40, 6, 34), 0.2), ((16, 16, 16), 40.0)],
+                         ids=lambda v: 'x'.join(str(n) for n in v) if isinstance(v, tuple) else str(v))
+def test_sweep_scatter_lagrangian_order_vs_oracle(shape, sigma):
+    """Storage in the reference's Lagrangian order, table derived from pmid.  Small displacements:
+    (almost) everything goes through the shared-memory tiles; large ones: mostly stragglers."""
+    from pmwd_b200.nbody import _store_from
+    pm, conf, oconf, pmid, disp, ptcl = _setup(shape, sigma)
+    store = _store_from(ptcl, conf)
+    assert store.sweep is not None and store.sweep.ok, 'sweep table from pmid must be valid for gen_grid order'
+    dens, = _sweep_scatter(store, conf)
+    _close(dens, O.scatter(pmid, disp, oconf))
+    n_strag = store.sweep.stragglers()
+    print('stragglers', n_strag, 'of', conf.ptcl_num)
+    if sigma <= 0.5:
+        assert n_strag < 0.6 * conf.ptcl_num
+
+
+@pytest.mark.parametrize('shape, sigma', [((32, 32, 32), 2.0), ((24, 16, 64), 5.0), ((8, 8, 512), 6.0)],
+                         ids=lambda v: 'x'.join(str(n) for n in v) if isinstance(v, tuple) else str(v))
+def test_sweep_scatter_sorted_and_stale_order(shape, sigma):
+    """After a re-sort (table from the sort's keys) no particle is a straggler; after the particles
+    have moved on without a re-sort the result is still exact and only the straggler count grows."""
+    from pmwd_b200.nbody import _store_from
+    pm, conf, oconf, pmid, disp, ptcl = _setup(shape, sigma)
+    store = _store_from(ptcl, conf)
+    store.reorder()
+    assert store.sweep.ok
+    dens, = _sweep_scatter(store, conf)
+    _close(dens, O.scatter(pmid, disp, oconf))
+    assert store.sweep.stragglers() == 0
+    # drift by up to ~1.5 cells without re-sorting
+    g = torch.Generator(device='cuda').manual_seed(3)
+    kick = 0.6 * conf.cell_size * torch.randn(store.arrays['disp'].shape, device='cuda', generator=g)
+    store.arrays['disp'] += kick
+    dens, = _sweep_scatter(store, conf)
+    lag = store.lagrangian('disp').cpu().numpy()
+    _close(dens, O.scatter(pmid, lag, oconf))
+    n_strag = store.sweep.stragglers()
+    print('stragglers after drift', n_strag, 'of', conf.ptcl_num)
+    assert 0 < n_strag < conf.ptcl_num
+
+
+def test_sweep_scatter_three_channels_vs_red_kernel():
+    """The adjoint's V_i = scatter(pi_i) (gather.py:113): three sweeps against pmwd_scatter_soa."""
+    from pmwd_b200 import _lib
+    from pmwd_b200.gravity import _force_desc
+    from pmwd_b200.nbody import _store_from
+    pm, conf, oconf, pmid, disp, ptcl = _setup((32, 32, 32), 2.0)
+    store = _store_from(ptcl, conf)
+    store.reorder()
+    a = store.arrays
+    g = torch.Generator(device='cuda').manual_seed(1)
+    pi = torch.randn(a['disp'].shape, device='cuda', generator=g)
+    dens, = _sweep_scatter(store, conf)          # records the stragglers (none) like force_adj does
+    V = _sweep_scatter(store, conf, val=pi, nch=3)
+    desc = _force_desc(a['pmid'], conf)
+    ref = [torch.zeros(tuple(conf.mesh_shape), device='cuda') for _ in range(3)]
+    _lib.check(_lib.lib().pmwd_scatter_soa(_lib.stream_ptr(), C.byref(desc), _lib.ptr(a['pmid']), _lib.ptr(a['disp']),
+                                           _lib.ptr(pi), 0.0, 3, _lib.ptr(ref[0]), _lib.ptr(ref[1]), _lib.ptr(ref[2])),
+               'pmwd_scatter_soa')
+    for c in range(3):
+        scale = ref[c].abs().max().item()
+        assert (V[c] - ref[c]).abs().max().item() <= 2e-6 * scale
+    # and against the oracle's gather VJP mesh cotangent for one channel
+    lag_disp, lag_pi = store.lagrangian('disp').cpu().numpy(), None
+    pi_lag = torch.empty_like(pi)
+    pi_lag[store.lag.long()] = pi
+    _, mc = O.gather_adj(pmid, lag_disp, oconf, np.zeros(oconf.mesh_shape, np.float32), pi_lag[:, 1].cpu().numpy())
+    assert np.abs(V[1].cpu().numpy() - mc).max() <= 2e-6 * np.abs(mc).max()
+
+
+def test_sweep_table_rejects_unordered_storage():
+    """A storage order without one contiguous run per (pencil, plane) must leave the RED kernel in
+    charge (no silent loss of particles): the table check fails and the sweep argument is NULL."""
+    from pmwd_b200.nbody import _store_from
+    pm, conf, oconf, pmid, disp, ptcl = _setup((16, 16, 16), 0.3)
+    perm = torch.randperm(conf.ptcl_num, device='cuda', generator=torch.Generator(device='cuda').manual_seed(0))
+    shuffled = pm.Particles(conf, ptcl.pmid[perm].contiguous(), ptcl.disp[perm].contiguous(), vel=ptcl.vel)
+    store = _store_from(shuffled, conf)
+    assert store.sweep is not None and not store.sweep.ok and store.sweep_arg() is None
+    store.reorder()                        # the first re-sort makes it usable
+    assert store.sweep.ok and store.sweep_arg() is not None
+    dens, = _sweep_scatter(store, conf)
+    _close(dens, O.scatter(pmid, disp, oconf))
+
+
+@pytest.mark.parametrize('tiled', [True, False])
+def test_nbody_same_result_with_and_without_tiles(tiled):
+    """The integrator with the tiled deposit (default) and with the RED kernel (scatter_tiled=False)
+    give the same trajectory up to float32 summation order: both within 1e-4 cell of the oracle."""
+    import pmwd_b200 as pm
+    n = 32
+    kw = dict(a_nbody_maxstep=1 / 8)
+    conf = pm.Configuration(1., (n,) * 3, mesh_shape=2, scatter_tiled=tiled, reorder_min_disp=0.5, **kw)
+    oconf = O.Conf(1., (n,) * 3, mesh_shape=2, **kw)
+    cosmo = pm.boltzmann(pm.SimpleLCDM(conf), conf)
+    ocosmo = O.boltzmann(O.SimpleLCDM(oconf), oconf).replace(growth=cosmo.growth.numpy())
+    ic = O.lpt(O.linear_modes(O.white_noise(0, oconf), ocosmo, oconf), ocosmo, oconf)
+    ptcl = pm.Particles(conf, torch.from_numpy(ic['pmid']).cuda(), torch.from_numpy(ic['disp']).cuda(),
+                        vel=torch.from_numpy(ic['vel']).cuda())
+    out, _ = pm.nbody(ptcl, None, cosmo, conf)
+    ref = O.nbody(dict(ic), ocosmo, oconf)
+    err = np.abs(out.disp.cpu().numpy() - ref['disp']) / conf.cell_size
+    assert np.sqrt(np.mean(err ** 2)) <= 1e-4 and np.quantile(err, 0.999) <= 1e-4
