@@ -262,7 +262,7 @@ scatter_sweep_kernel(SweepGeom G, const short* __restrict__ pmid, const float* _
         float v = 0.f;
         if (act) { r = rec[qbeg + c + lane]; v = recv[qbeg + c + lane]; }
         const int packed = __float_as_int(r.w);
-        const unsigned key = act ? (unsigned)packed : (0xc0000000u | (unsigned)lane);   // row field >= 0x400: never a real cell
+        const unsigned key = act ? (unsigned)packed : (0xc0000000u | (unsigned)lane);   // bits 30-31 set: never a real cell
         float wx[2], wy[2], wz[2];
         wx[0] = __fsub_rn(1.f, fabsf(r.x)); wx[1] = __fsub_rn(1.f, fabsf(__fsub_rn(r.x, 1.f)));
         wy[0] = __fsub_rn(1.f, fabsf(r.y)); wy[1] = __fsub_rn(1.f, fabsf(__fsub_rn(r.y, 1.f)));
@@ -455,7 +455,7 @@ static bool sweep_geom(const pmwd_cic_desc* d, int ty, int lx, SweepGeom* G) {
   G->bw_shift = ilog2_ceil_i((G->nz + SW_WARPS - 1) / SW_WARPS);
   if (G->bw_shift < 1) G->bw_shift = 1;
   if (d->ptcl_num >= ((int64_t)1 << 32)) return false;
-  return sweep_smem_bytes(*G) <= 227 * 1024;
+  return sweep_smem_bytes(*G) <= 226 * 1024;      // 227 KB per CTA minus the kernel's static shared memory
 }
 
 }  // namespace pmwd
@@ -533,7 +533,7 @@ int scatter_sweep(cudaStream_t st, const pmwd_cic_desc* d, const pmwd_sweep* sw,
   const size_t smem = sweep_smem_bytes(G);
   if (!smem_set) {
     PMWD_CUDA_TRY(cudaFuncSetAttribute(scatter_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       227 * 1024));
+                                       226 * 1024));
     smem_set = 1;
   }
   PMWD_CUDA_TRY(cudaMemsetAsync(counters, 0, reuse_stragglers ? 4 : 8, st));
