@@ -60,16 +60,18 @@ typedef struct pmwd_cic_desc {
   double offset[3];       /* enmesh b12 */
 } pmwd_cic_desc;
 
-/* Tiled ("pencil sweep") CIC deposit, csrc/scatter_sweep.cu: particle storage sorted by
- * (y-pencil of `ty` rows, x-plane, ...) + a table of the particle range of every (pencil, plane).
- * Passed to pmwd_force / pmwd_force_kdk / pmwd_force_adj / pmwd_scatter_soa as an optional argument
+/* Tiled ("tile sweep") CIC deposit, csrc/scatter_sweep.cu: particle storage sorted by
+ * (y-tile of `ty` rows, z-tile of `bw` cells, x-plane, y, z) + a table of the particle range of every
+ * (tile, plane).  Passed to pmwd_force / pmwd_force_kdk / pmwd_force_adj as an optional argument
  * (NULL, or a descriptor that does not match the mesh: the per-particle RED kernel is used). */
 typedef struct pmwd_sweep {
-  const uint32_t* table;  /* device, [ny / ty][planes][2] = (first, one-past-last) particle slot */
-  int32_t ty;             /* rows per pencil (pmwd_sweep_pick_ty) */
+  const uint32_t* table;  /* device, [ny / ty][nz / bw][planes][2] = (first, one-past-last) particle slot */
+  int32_t ty;             /* tile rows (pmwd_sweep_pick) */
+  int32_t bw;             /* tile cells along z */
   int32_t lx;             /* planes per x segment of a work item (64 is a good value) */
   int32_t nx_ext;         /* planes of the mesh array the table was built for (== desc mesh_shape[0]) */
   int32_t xoff;           /* global index of its plane 0 (offset[0] / cell) */
+  int32_t reserved;
   void* scratch;          /* device, pmwd_sweep_scratch_bytes: work counters + straggler list */
   size_t scratch_bytes;
 } pmwd_sweep;
@@ -200,17 +202,16 @@ int pmwd_scatter_soa(void* stream, const pmwd_cic_desc* d, const void* pmid, con
 int pmwd_scatter_sweep(void* stream, const pmwd_cic_desc* d, const pmwd_sweep* sweep, const void* pmid,
                        const float* disp, const float* val, float val_scalar, int nch, float* m0,
                        float* m1, float* m2);
-/* Pencil height for this mesh (8, 4 or 2; 0 = the sweep kernels do not support it), size of the
- * (pencil, plane) table and of the scratch area (work counters + straggler list). */
-int pmwd_sweep_pick_ty(const pmwd_cic_desc* d);
-size_t pmwd_sweep_table_bytes(const pmwd_cic_desc* d, int ty);
+/* Tile shape for this mesh (returns 0 if the sweep kernels do not support it), size of the
+ * (tile, plane) table and of the scratch area (work counters + straggler list). */
+int pmwd_sweep_pick(const pmwd_cic_desc* d, int* ty, int* bw);
+size_t pmwd_sweep_table_bytes(const pmwd_cic_desc* d, int ty, int bw);
 size_t pmwd_sweep_scratch_bytes(const pmwd_cic_desc* d);
-/* Build the table from the sorted keys of pmwd_cell_sort_perm(..., ty) (pmwd_cell_sort_sorted_keys)
- * or, with keys == NULL, from pmid alone (storage in the Lagrangian C order of particles.py:135-139).
- * status (device, 16 bytes): after synchronising, uint32 [0] must be 0 and uint64 [1] == ptcl_num,
- * otherwise the storage order does not have one contiguous run per (pencil, plane). */
-int pmwd_sweep_table(void* stream, const pmwd_cic_desc* d, int ty, const uint32_t* keys,
-                     const void* pmid, uint32_t* table, void* status);
+/* Build the table from the sorted keys of pmwd_cell_sort_perm(..., ty, bw) (pmwd_cell_sort_sorted_keys).
+ * status (device, 16 bytes): after synchronising, uint32 [0] == 0 and uint64 [1] == ptcl_num for a
+ * valid table (true by construction for sorted keys). */
+int pmwd_sweep_table(void* stream, const pmwd_cic_desc* d, int ty, int bw, const uint32_t* keys,
+                     uint32_t* table, void* status);
 /* Stragglers (particles outside their tile's window) of the last recording sweep; synchronises. */
 long long pmwd_sweep_last_stragglers(void* stream, const pmwd_sweep* sweep);
 /* acc[N][3] = (gather(f0), gather(f1), gather(f2)) in one pass (gravity.py:61-70), optionally
@@ -282,11 +283,11 @@ int pmwd_force_adj(pmwd_ctx* ctx, void* stream, const pmwd_cic_desc* d, const vo
  * integrator here periodically re-sorts its private copies by mesh cell so that scatter /
  * gather stay coalesced, and restores the reference order on output.
  * perm[i] = storage index of the particle that moves to sorted slot i (stable by cell).
- * ty == 0: key = (x>>1, y>>1, z) (2x2-cell columns along z); ty > 0: the sweep scatter's layout
- * (y / ty, x, (y % ty) >> 1, z).  The sorted keys stay in `scratch` (pmwd_cell_sort_sorted_keys). */
+ * ty == 0: key = (x>>1, y>>1, z) (2x2-cell columns along z); ty, bw > 0: the sweep scatter's layout
+ * (y / ty, z / bw, x, y % ty, z % bw).  The sorted keys stay in `scratch` (pmwd_cell_sort_sorted_keys). */
 size_t pmwd_cell_sort_scratch_bytes(const pmwd_cic_desc* d);
 int pmwd_cell_sort_perm(void* stream, const pmwd_cic_desc* d, const void* pmid, const float* disp,
-                        uint32_t* perm, void* scratch, size_t scratch_bytes, int ty);
+                        uint32_t* perm, void* scratch, size_t scratch_bytes, int ty, int bw);
 const uint32_t* pmwd_cell_sort_sorted_keys(const pmwd_cic_desc* d, const void* scratch);
 /* For each of `narr` row-major arrays (row_bytes[a] bytes per particle, even):
  * inverse == 0: dst[i] = src[perm[i]];  inverse != 0: dst[perm[i]] = src[i]. */

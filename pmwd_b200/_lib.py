@@ -41,9 +41,11 @@ class Sweep(C.Structure):
     _fields_ = [
         ('table', C.c_void_p),
         ('ty', C.c_int32),
+        ('bw', C.c_int32),
         ('lx', C.c_int32),
         ('nx_ext', C.c_int32),
         ('xoff', C.c_int32),
+        ('reserved', C.c_int32),
         ('scratch', C.c_void_p),
         ('scratch_bytes', C.c_size_t),
     ]
@@ -100,13 +102,13 @@ _SIGNATURES = {
     'pmwd_force_kdk': (_i, [_vp, _vp, _descp, _vp, _vp, _d, _vp, _vp, _f, _f, _f, _i, _vp, _sz, _vp]),
     'pmwd_force_adj': (_i, [_vp, _vp, _descp, _vp, _vp, _d, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
     'pmwd_scatter_sweep': (_i, [_vp, _descp, _vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp]),
-    'pmwd_sweep_pick_ty': (_i, [_descp]),
-    'pmwd_sweep_table_bytes': (_sz, [_descp, _i]),
+    'pmwd_sweep_pick': (_i, [_descp, _i32p, _i32p]),
+    'pmwd_sweep_table_bytes': (_sz, [_descp, _i, _i]),
     'pmwd_sweep_scratch_bytes': (_sz, [_descp]),
-    'pmwd_sweep_table': (_i, [_vp, _descp, _i, _vp, _vp, _vp, _vp]),
+    'pmwd_sweep_table': (_i, [_vp, _descp, _i, _i, _vp, _vp, _vp]),
     'pmwd_sweep_last_stragglers': (C.c_longlong, [_vp, _vp]),
     'pmwd_cell_sort_scratch_bytes': (_sz, [_descp]),
-    'pmwd_cell_sort_perm': (_i, [_vp, _descp, _vp, _vp, _vp, _vp, _sz, _i]),
+    'pmwd_cell_sort_perm': (_i, [_vp, _descp, _vp, _vp, _vp, _vp, _sz, _i, _i]),
     'pmwd_cell_sort_sorted_keys': (_vp, [_descp, _vp]),
     'pmwd_permute_rows': (_i, [_vp, _i64, _vp, _i, C.POINTER(_vp), C.POINTER(_vp), _i32p, _i]),
     'pmwd_transpose_p2p': (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, C.POINTER(C.c_uint64)]),

@@ -28,7 +28,7 @@ struct SortParams {
   int nx_ext, xoff; // slab: planes held locally and global index of the first one
   int shift;        // xy footprint of a storage "column" is (1<<shift)^2 cells
   int nyc;          // ceil(ny >> shift)
-  int ty;           // > 0: sweep layout (y / ty, x, (y % ty) >> 1, z) -- scatter_sweep.cu
+  int ty, bw;       // > 0: sweep layout (y / ty, z / bw, x, y % ty, z % bw) -- scatter_sweep.cu
   float cell;
 };
 
@@ -52,7 +52,9 @@ sort_keys_kernel(SortParams P, const short* __restrict__ pmid, const float* __re
     // a warp's 32 stencils share 32-byte sectors
     if (P.ty > 0) {
       const int pencil = c[1] / P.ty, yin = c[1] - pencil * P.ty;
-      keys[p] = (uint32_t)((((int64_t)pencil * P.nx_ext + lx) * (P.ty >> 1) + (yin >> 1)) * P.nz + c[2]);
+      const int band = c[2] / P.bw, zin = c[2] - band * P.bw;
+      const int64_t id = ((int64_t)pencil * (P.nz / P.bw) + band) * P.nx_ext + lx;
+      keys[p] = (uint32_t)((id * P.ty + yin) * P.bw + zin);
     } else {
       keys[p] = (uint32_t)(((int64_t)(lx >> P.shift) * P.nyc + (c[1] >> P.shift)) * P.nz + c[2]);
     }
@@ -129,7 +131,7 @@ extern "C" const uint32_t* pmwd_cell_sort_sorted_keys(const pmwd_cic_desc* d, co
 
 extern "C" int pmwd_cell_sort_perm(void* stream, const pmwd_cic_desc* d, const void* pmid,
                                    const float* disp, uint32_t* perm, void* scratch,
-                                   size_t scratch_bytes, int ty) {
+                                   size_t scratch_bytes, int ty, int bw) {
   PMWD_REQUIRE(d && d->dim == 3 && d->pmid_bytes == 2 && !d->general,
                "cell sort supports the 3-D int16 fast path");
   PMWD_REQUIRE(perm && scratch, "null buffer");
@@ -139,9 +141,10 @@ extern "C" int pmwd_cell_sort_perm(void* stream, const pmwd_cic_desc* d, const v
   P.nx_ext = d->mesh_shape[0];
   P.xoff = slab_xoff(d);
   P.cell = (float)d->cell_size;
-  PMWD_REQUIRE(ty >= 0 && (ty == 0 || (ty % 2 == 0 && d->wrap_shape[1] % ty == 0)),
-               "sweep key layout needs an even ty that divides the y extent");
+  PMWD_REQUIRE(ty >= 0 && (ty == 0 || (bw > 0 && d->wrap_shape[1] % ty == 0 && d->wrap_shape[2] % bw == 0)),
+               "sweep key layout needs tile sizes that divide the y and z extents");
   P.ty = ty;
+  P.bw = bw;
   {
     const char* e = getenv("PMWD_SORT_SHIFT");
     P.shift = e ? atoi(e) : 1;

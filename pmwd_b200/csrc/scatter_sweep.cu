@@ -1,36 +1,34 @@
-// Tiled CIC deposit through shared-memory mesh tiles ("pencil sweep"): pmwd/scatter.py:60-83 for
+// Tiled CIC deposit through shared-memory mesh tiles ("tile sweep"): pmwd/scatter.py:60-83 for
 // the gravity fast path (3-D, int16 pmid, offset = whole planes, cell_size=None).
 //
 // The per-particle global-RED kernel (cic_fast.cu) is bound by the LSU's atomic issue rate
 // (~1.3 cycles per lane: 31 cycles per RED warp instruction measured, profiles/r01_final_ncu_full.txt)
 // and moves 2.3x its algorithmic DRAM bytes (memset + read-modify-write of the whole mesh).  Shared
 // memory atomics are no way out on sm_100a (ATOMS: 2 cycles per lane, float add = CAS loop).  This
-// kernel instead accumulates with PLAIN shared-memory read-modify-writes made conflict free by
-// construction, and writes every mesh cell that only one CTA can touch with coalesced float4
-// STORES (no memset, no read):
+// kernel accumulates with PLAIN shared-memory read-modify-writes that are conflict free by
+// construction, and writes every mesh cell that only one warp can touch with float4 STORES (no
+// memset, no read).  A first version that binned 512-particle batches by z-band inside a CTA moved
+// 1.08x the algorithmic bytes but needed 948 instructions per particle and spent 47 % of its time at
+// CTA barriers (12-16 ms, profiles/r02_sweep_v1_ncu.txt); this one has no CTA barrier at all:
 //
-//  * the integrator keeps its particle storage sorted by (y-pencil, x-plane, y-pair, z)
-//    (reorder.cu; Lagrangian order has the same segment structure), and a table gives the
-//    particle range of every (pencil, plane);
-//  * a work item = one pencil (TY rows, all of z) x one segment of LX planes.  The CTA sweeps the
-//    segment plane by plane with a RING of four planes [(TY+1) rows][nz] in shared memory: a particle
-//    sorted at plane xs now sits at xs-1 .. xs+1 (it moved since the last re-sort) and touches
-//    planes xs-1 .. xs+2.  When plane xs is done, plane xs-1 is complete and is flushed;
-//  * each batch of 512 particles is binned by z-band (16 bands, one per warp): warp w alone updates
-//    band w of the ring, eight sequential phases (one per neighbour) of plain LDS/FADD/STS after the
-//    lanes that share a base cell have been merged (reduce_peers); only the first cell of every band,
-//    which the previous band's last cell spills into, takes shared atomics;
-//  * flush: rows 1 .. TY-1 of the planes only this item can reach -> float4 stores; the pencil's
-//    first row and halo row (shared with the neighbouring pencils) and the three planes at either
-//    end of the segment (shared with the neighbouring segments) -> red.global.add.v4.f32 onto cells
-//    that sweep_zero_kernel cleared beforehand (1/TY of the rows + 3 planes per LX);
-//  * particles outside their window (moved more than one plane, or out of the pencil in y) are
+//  * the integrator keeps its particle storage sorted by (y-tile, z-tile, x-plane, y, z) (reorder.cu,
+//    sweep key layout) and a table gives the particle range of every (tile, plane);
+//  * a work item = one (y, z) tile of TY x BW cells x one segment of LX planes, swept by ONE WARP
+//    with a private RING of four planes [(TY+1) rows][BW+1 cells] in shared memory: a particle sorted
+//    at plane xs now sits at xs-1 .. xs+1 (it moved since the last re-sort) and touches planes
+//    xs-1 .. xs+2; when plane xs is done, plane xs-1 is complete and is flushed;
+//  * per 32 particles: stencil in registers, lanes that share a base cell merged by shuffles, then
+//    eight phases (one per neighbour) of plain LDS/FADD/STS -- within a phase all lanes hit distinct
+//    cells, and nobody else ever touches this warp's ring;
+//  * flush: cells that only this warp can reach -> float4 stores; the tile's first row, its halo row,
+//    its first float4 along z and its halo column (shared with the neighbouring tiles) and the three
+//    planes at either end of the segment -> red.global.add(.v4).f32 onto cells that
+//    sweep_zero_kernel cleared beforehand;
+//  * particles outside their window (moved more than one plane, or out of the tile in y or z) are
 //    "stragglers": appended to a list and deposited by a second, per-particle RED kernel that runs
 //    after this one (so that it can never race with the plain stores).
 //
 // Correctness never depends on how fresh the sort is; only the straggler fraction does.
-#include <cooperative_groups.h>
-
 #include "cic.cuh"
 
 namespace pmwd {
@@ -38,8 +36,7 @@ namespace pmwd {
 int slab_xoff(const pmwd_cic_desc* d);
 bool cic_is_fast(const pmwd_cic_desc* d);
 
-constexpr int SW_THREADS = 512;
-constexpr int SW_WARPS = SW_THREADS / 32;
+constexpr int SW_MAX_WARPS = 24;
 
 struct SweepGeom {
   int64_t n;
@@ -47,9 +44,11 @@ struct SweepGeom {
   int nx_ext, xoff;   // planes held by the mesh array, global index of plane 0
   int periodic;       // the array spans the whole periodic x axis
   float cell;
-  int ty, npencil;    // rows per pencil, ny / ty
+  int ty, npencil;    // tile rows, ny / ty
+  int bw, nband;      // tile cells along z (multiple of 4), nz / bw
   int lx, nseg;       // planes per x segment, ceil(nx_ext / lx)
-  int bw_shift;       // z band width = 1 << bw_shift cells (<= SW_WARPS bands)
+  int rs, ps;         // ring row stride (bw + 1) and plane size (ty + 1) * rs, in floats
+  int nwarps;         // warps per CTA (each with its own ring)
 };
 
 __device__ __forceinline__ void red_add4(float* p, float4 v) {
@@ -86,45 +85,45 @@ struct PtclRegs {
   float v;
 };
 
-__global__ void __launch_bounds__(SW_THREADS, 1)
+// periodic wrap of pmid + floor(disp / cell): almost always within one box length
+__device__ __forceinline__ int wrap_fast(int i, int n) {
+  if (i >= n) { i -= n; if (i >= n) i %= n; }
+  else if (i < 0) { i += n; if (i < 0) { i %= n; if (i < 0) i += n; } }
+  return i;
+}
+
+__global__ void __launch_bounds__(SW_MAX_WARPS * 32, 1)
 scatter_sweep_kernel(SweepGeom G, const short* __restrict__ pmid, const float* __restrict__ disp,
                      const float* __restrict__ val, int vstride, float vscalar, float* __restrict__ mesh,
                      const uint2* __restrict__ table, unsigned* __restrict__ counters,
                      uint32_t* __restrict__ strag, int record_strag) {
-  extern __shared__ __align__(16) unsigned char smraw[];
-  const int plane_sz = (G.ty + 1) * G.nz;               // floats per ring plane (multiple of 4)
-  float* ring = reinterpret_cast<float*>(smraw);        // [4][ty+1][nz]
-  float4* rec = reinterpret_cast<float4*>(ring + 4 * (size_t)plane_sz);   // [SW_THREADS]
-  float* recv = reinterpret_cast<float*>(rec + SW_THREADS);               // [SW_THREADS]
-  int* cnt = reinterpret_cast<int*>(recv + SW_THREADS);                   // [SW_WARPS]
-  uint2* segs = reinterpret_cast<uint2*>(cnt + SW_WARPS);                 // [lx]
-  __shared__ int s_item;
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nitems = G.npencil * G.nseg;
-  const int bw_mask = (1 << G.bw_shift) - 1;
-  if (tid < SW_WARPS) cnt[tid] = 0;
+  extern __shared__ __align__(16) float smf[];
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* ring = smf + (size_t)warp * 4 * G.ps;          // [4][ty+1][bw+1], private to this warp
+  uint32_t* sbuf = reinterpret_cast<uint32_t*>(smf + (size_t)G.nwarps * 4 * G.ps) + warp * 64;   // straggler staging
+  int scount = 0;
+  const int nitems = G.npencil * G.nband * G.nseg;
+  const int ngr = G.bw >> 2;                            // float4 groups per tile row
 
   for (;;) {
-    __syncthreads();
-    if (tid == 0) s_item = (int)atomicAdd(&counters[0], 1u);
-    __syncthreads();
-    const int item = s_item;
+    int item = 0;
+    if (lane == 0) item = (int)atomicAdd(&counters[0], 1u);
+    item = __shfl_sync(full, item, 0);
     if (item >= nitems) break;
-    const int pencil = item % G.npencil, sgi = item / G.npencil;
+    const int band = item % G.nband;
+    const int t1 = item / G.nband;
+    const int pencil = t1 % G.npencil, sgi = t1 / G.npencil;
     const int xa = sgi * G.lx, xb = min(xa + G.lx, G.nx_ext);
-    const int y0 = pencil * G.ty;
-    for (int i = tid; i < xb - xa; i += SW_THREADS) segs[i] = table[(int64_t)pencil * G.nx_ext + xa + i];
-    {
-      float4* r4 = reinterpret_cast<float4*>(ring);
-      for (int i = tid; i < plane_sz; i += SW_THREADS) r4[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // 4 planes / 4
-    }
-    __syncthreads();
+    const int y0 = pencil * G.ty, z0 = band * G.bw;
+    const uint2* tab = table + ((int64_t)pencil * G.nband + band) * G.nx_ext;
+    for (int i = lane; i < 4 * G.ps; i += 32) ring[i] = 0.f;
+    __syncwarp();
 
-    // ---- flush one ring plane to the mesh and clear it
+    // ---- flush one ring plane of this warp to the mesh and clear it
     auto flush = [&](int pl) {
       const int slot = (pl - (xa - 1)) & 3;
-      float4* src = reinterpret_cast<float4*>(ring + (size_t)slot * plane_sz);
+      float* src = ring + slot * G.ps;
       bool valid = true;
       int gpl = pl;
       if (G.periodic) {
@@ -133,38 +132,52 @@ scatter_sweep_kernel(SweepGeom G, const short* __restrict__ pmid, const float* _
       } else {
         valid = pl >= 0 && pl < G.nx_ext;
       }
-      const bool all_red = (pl <= xa + 1) || (pl >= xb - 1);
-      const int nz4 = G.nz >> 2;
-      for (int i = tid; i < (plane_sz >> 2); i += SW_THREADS) {
-        const float4 v = src[i];
-        src[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!valid) continue;
-        const int row = i / nz4, z4 = i - row * nz4;
-        int gy = y0 + row;
-        if (gy == G.ny) gy = 0;
-        float* dst = mesh + ((int64_t)gpl * G.ny + gy) * G.nz + 4 * z4;
-        if (all_red || row == 0 || row == G.ty) {
-          if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) red_add4(dst, v);
-        } else {
-          __stcs(reinterpret_cast<float4*>(dst), v);
+      if (valid) {
+        const bool all_red = (pl <= xa + 1) || (pl >= xb - 1);
+        const int ntot = (G.ty + 1) * ngr;
+        for (int i = lane; i < ntot; i += 32) {
+          const int row = i / ngr, gq = i - row * ngr;
+          const float* sp = src + row * G.rs + 4 * gq;
+          const float4 v = make_float4(sp[0], sp[1], sp[2], sp[3]);
+          int gy = y0 + row;
+          if (gy == G.ny) gy = 0;
+          float* dst = mesh + ((int64_t)gpl * G.ny + gy) * G.nz + z0 + 4 * gq;
+          if (all_red || row == 0 || row == G.ty || gq == 0) {
+            if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) red_add4(dst, v);
+          } else {
+            __stcs(reinterpret_cast<float4*>(dst), v);
+          }
+        }
+        // halo column: the first cell of the next tile along z
+        const int zh = (z0 + G.bw == G.nz) ? 0 : z0 + G.bw;
+        for (int row = lane; row <= G.ty; row += 32) {
+          const float v = src[row * G.rs + G.bw];
+          if (v != 0.f) {
+            int gy = y0 + row;
+            if (gy == G.ny) gy = 0;
+            atomicAdd(mesh + ((int64_t)gpl * G.ny + gy) * G.nz + zh, v);
+          }
         }
       }
+      __syncwarp();
+      for (int i = lane; i < G.ps; i += 32) src[i] = 0.f;
+      __syncwarp();
     };
 
-    // ---- batch iterator over the item's (plane, particle range) list; uniform across the CTA
+    // ---- chunk iterator over the item's (plane, particle range) list; uniform across the warp
     int xs = xa;
     unsigned b0 = 0, bend = 0;
-    auto seek = [&]() {      // make (xs, b0, bend) point at a non-empty batch or xs == xb
+    auto seek = [&]() {      // make (xs, b0, bend) point at a non-empty chunk or xs == xb
       while (xs < xb) {
         if (b0 < bend) return;
         ++xs;
-        if (xs < xb) { const uint2 s = segs[xs - xa]; b0 = s.x; bend = s.y; }
+        if (xs < xb) { const uint2 s = __ldg(tab + xs); b0 = s.x; bend = s.y; }
       }
     };
-    { const uint2 s = segs[0]; b0 = s.x; bend = s.y; }
+    { const uint2 s = __ldg(tab + xa); b0 = s.x; bend = s.y; }
     seek();
     auto load = [&](int lxs, unsigned lb0, unsigned lbend, PtclRegs& R) -> bool {
-      const unsigned p = lb0 + tid;
+      const unsigned p = lb0 + lane;
       const bool act = lxs < xb && p < lbend;
       if (act) {
         R.pm[0] = pmid[3 * (int64_t)p + 0]; R.pm[1] = pmid[3 * (int64_t)p + 1]; R.pm[2] = pmid[3 * (int64_t)p + 2];
@@ -180,27 +193,24 @@ scatter_sweep_kernel(SweepGeom G, const short* __restrict__ pmid, const float* _
     while (xs < xb) {
       const int cxs = xs;
       const unsigned cb0 = b0;
-      // advance the iterator and prefetch the next batch before working on this one
-      b0 += SW_THREADS;
+      // advance the iterator and prefetch the next chunk before working on this one
+      b0 += 32;
       seek();
       const bool nxt_act = load(xs, b0, bend, nxt);
 
-      if (next_flush <= cxs - 2) {          // planes that can no longer be reached
-        while (next_flush <= cxs - 2) { flush(next_flush); ++next_flush; }
-        __syncthreads();
-      }
+      while (next_flush <= cxs - 2) { flush(next_flush); ++next_flush; }   // planes out of reach
 
-      // ---- stencil of this thread's particle
-      const unsigned p = cb0 + tid;
+      // ---- stencil of this lane's particle
+      const unsigned p = cb0 + lane;
       int g[3];
       float d0[3];
       const int nn[3] = {G.nx, G.ny, G.nz};
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
         const float t = __fdiv_rn(cur_act ? cur.dp[a] : 0.f, G.cell);
-        const int i0 = (int)floorf(t);
-        d0[a] = __fsub_rn(t, (float)i0);
-        g[a] = wrap_index((cur_act ? (int)cur.pm[a] : 0) + i0, nn[a]);
+        const float fl = floorf(t);
+        d0[a] = __fsub_rn(t, fl);
+        g[a] = wrap_fast((cur_act ? (int)cur.pm[a] : 0) + (int)fl, nn[a]);
       }
       int lp = g[0] - G.xoff;
       if (lp < 0) lp += G.nx;
@@ -209,118 +219,93 @@ scatter_sweep_kernel(SweepGeom G, const short* __restrict__ pmid, const float* _
         if (dxs > (G.nx >> 1)) dxs -= G.nx;
         else if (dxs < -(G.nx >> 1)) dxs += G.nx;
       }
-      const int dy = g[1] - y0;
-      const bool inwin = cur_act && dxs >= -1 && dxs <= 1 && dy >= 0 && dy < G.ty;
+      const int dy = g[1] - y0, dz = g[2] - z0;
+      const bool inwin = cur_act && dxs >= -1 && dxs <= 1 && dy >= 0 && dy < G.ty && dz >= 0 && dz < G.bw;
       if (record_strag) {
-        const unsigned sm = __ballot_sync(0xffffffffu, cur_act && !inwin);
+        // stragglers are staged in a per-warp buffer and appended to the global list 32 at a time
+        // (one global atomic per chunk on a single counter stalled half of all issue slots)
+        const unsigned sm = __ballot_sync(full, cur_act && !inwin);
         if (sm) {
-          const int leader = __ffs(sm) - 1;
-          unsigned base = 0;
-          if (lane == leader) base = atomicAdd(&counters[1], (unsigned)__popc(sm));
-          base = __shfl_sync(0xffffffffu, base, leader);
-          if (cur_act && !inwin) strag[base + __popc(sm & ((1u << lane) - 1u))] = p;
-        }
-      }
-      // ---- bin by z band: slot inside the band's queue
-      const int band = g[2] >> G.bw_shift;
-      int myoff = 0;
-      {
-        unsigned todo = __ballot_sync(0xffffffffu, inwin);
-        while (todo) {
-          const int leader = __ffs(todo) - 1;
-          const int b = __shfl_sync(0xffffffffu, band, leader);
-          const unsigned m = __ballot_sync(0xffffffffu, inwin && band == b);
-          int base = 0;
-          if (lane == leader) base = atomicAdd(&cnt[b], __popc(m));
-          base = __shfl_sync(0xffffffffu, base, leader);
-          if (inwin && band == b) myoff = base + __popc(m & ((1u << lane) - 1u));
-          todo &= ~m;
-        }
-      }
-      __syncthreads();                                                     // S1: counts final
-      int qbeg = 0, qlen = 0, mybase = 0;
-#pragma unroll
-      for (int b = 0; b < SW_WARPS; ++b) {
-        const int c = cnt[b];
-        if (b < warp) qbeg += c;
-        if (b == warp) qlen = c;
-        if (b < band) mybase += c;
-      }
-      if (inwin) {
-        const int slot = (cxs + dxs - (xa - 1)) & 3;
-        const int packed = (slot << 28) | (dy << 20) | g[2];
-        rec[mybase + myoff] = make_float4(d0[0], d0[1], d0[2], __int_as_float(packed));
-        recv[mybase + myoff] = cur.v;
-      }
-      __syncthreads();                                                     // S2: records visible
-      if (tid < SW_WARPS) cnt[tid] = 0;
-
-      // ---- warp `warp` deposits the particles of its band
-      for (int c = 0; c < qlen; c += 32) {
-        const bool act = c + lane < qlen;
-        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-        float v = 0.f;
-        if (act) { r = rec[qbeg + c + lane]; v = recv[qbeg + c + lane]; }
-        const int packed = __float_as_int(r.w);
-        const unsigned key = act ? (unsigned)packed : (0xc0000000u | (unsigned)lane);   // bits 30-31 set: never a real cell
-        float wx[2], wy[2], wz[2];
-        wx[0] = __fsub_rn(1.f, fabsf(r.x)); wx[1] = __fsub_rn(1.f, fabsf(__fsub_rn(r.x, 1.f)));
-        wy[0] = __fsub_rn(1.f, fabsf(r.y)); wy[1] = __fsub_rn(1.f, fabsf(__fsub_rn(r.y, 1.f)));
-        wz[0] = __fsub_rn(1.f, fabsf(r.z)); wz[1] = __fsub_rn(1.f, fabsf(__fsub_rn(r.z, 1.f)));
-        float c8[8];
-#pragma unroll
-        for (int bx = 0; bx < 2; ++bx)
-#pragma unroll
-          for (int by = 0; by < 2; ++by) {
-            const float wxy = __fmul_rn(wx[bx], wy[by]);
-#pragma unroll
-            for (int bz = 0; bz < 2; ++bz)
-              c8[(bx * 2 + by) * 2 + bz] = act ? __fmul_rn(v, __fmul_rn(wxy, wz[bz])) : 0.f;
+          if (cur_act && !inwin) sbuf[scount + __popc(sm & ((1u << lane) - 1u))] = p;
+          scount += __popc(sm);
+          __syncwarp();
+          if (scount >= 32) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(&counters[1], 32u);
+            base = __shfl_sync(full, base, 0);
+            strag[base + lane] = sbuf[lane];
+            __syncwarp();
+            if (lane < scount - 32) sbuf[lane] = sbuf[32 + lane];
+            scount -= 32;
+            __syncwarp();
           }
-        const unsigned peers = __match_any_sync(0xffffffffu, key);
-        const bool first = sweep_reduce_peers<8>(peers, c8);
-        const bool push = act && first;
-        const int slot = (packed >> 28) & 3, row = (packed >> 20) & 0xff, z = packed & 0xfffff;
-        const int z1 = (z + 1 == G.nz) ? 0 : z + 1;
+        }
+      }
+      // ---- contributions, merged over lanes with the same base cell
+      const unsigned key = inwin ? (unsigned)(((dxs + 1) * G.ty + dy) * G.bw + dz) : (0x80000000u | (unsigned)lane);
+      float wx[2], wy[2], wz[2];
+      wx[0] = __fsub_rn(1.f, fabsf(d0[0])); wx[1] = __fsub_rn(1.f, fabsf(__fsub_rn(d0[0], 1.f)));
+      wy[0] = __fsub_rn(1.f, fabsf(d0[1])); wy[1] = __fsub_rn(1.f, fabsf(__fsub_rn(d0[1], 1.f)));
+      wz[0] = __fsub_rn(1.f, fabsf(d0[2])); wz[1] = __fsub_rn(1.f, fabsf(__fsub_rn(d0[2], 1.f)));
+      float c8[8];
+#pragma unroll
+      for (int bx = 0; bx < 2; ++bx)
+#pragma unroll
+        for (int by = 0; by < 2; ++by) {
+          const float wxy = __fmul_rn(wx[bx], wy[by]);
+#pragma unroll
+          for (int bz = 0; bz < 2; ++bz)
+            c8[(bx * 2 + by) * 2 + bz] = inwin ? __fmul_rn(cur.v, __fmul_rn(wxy, wz[bz])) : 0.f;
+        }
+      const unsigned peers = __match_any_sync(full, key);
+      const bool first = sweep_reduce_peers<8>(peers, c8);
+      if (__any_sync(full, inwin)) {
+        const bool push = inwin && first;
+        const int slot = (cxs + dxs - (xa - 1)) & 3;
+        const int off = dy * G.rs + dz;
+        float* p0 = ring + slot * G.ps + off;
+        float* p1 = ring + ((slot + 1) & 3) * G.ps + off;
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
-          const int bx = n >> 2, by = (n >> 1) & 1, bz = n & 1;
-          if (push) {
-            const int zt = bz ? z1 : z;
-            float* cellp = ring + (size_t)((slot + bx) & 3) * plane_sz + (row + by) * G.nz + zt;
-            if ((zt & bw_mask) == 0) atomicAdd(cellp, c8[n]);     // a band's first cell: shared with the band below
-            else *cellp = *cellp + c8[n];
-          }
+          float* cellp = ((n & 4) ? p1 : p0) + ((n & 2) ? G.rs : 0) + (n & 1);
+          if (push) *cellp = *cellp + c8[n];
           __syncwarp();
         }
       }
-      __syncthreads();                                                     // S3: ring quiescent
-
       cur = nxt;
       cur_act = nxt_act;
     }
     // ---- the rest of the ring: planes up to xb + 1
     while (next_flush <= xb + 1) { flush(next_flush); ++next_flush; }
   }
+  if (scount > 0) {
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(&counters[1], (unsigned)scount);
+    base = __shfl_sync(full, base, 0);
+    if (lane < scount) strag[base + lane] = sbuf[lane];
+  }
 }
 
-// Cells that receive vector REDs must start at zero: the first row of every pencil (it is also the
-// halo row of the pencil below) on every plane, and whole planes b-1, b, b+1 at every segment
-// boundary b.  One warp per mesh row.
+// Cells that receive REDs must start at zero: the first row of every y-tile (it is also the halo row
+// of the tile below) and whole planes b-1, b, b+1 at every segment boundary b -> full rows; the first
+// float4 of every z-tile (it holds the halo cell of the tile before) -> 16 bytes per tile.  One warp per row.
 __global__ void __launch_bounds__(256)
 sweep_zero_kernel(SweepGeom G, float* __restrict__ mesh) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int64_t rows = (int64_t)G.nx_ext * G.ny;
-  const int nz4 = G.nz >> 2;
+  const int nz4 = G.nz >> 2, bw4 = G.bw >> 2;
   for (int64_t r = warp; r < rows; r += nwarp) {
     const int pl = (int)(r / G.ny), y = (int)(r - (int64_t)pl * G.ny);
     const int m = pl % G.lx;
-    const bool zero = (y % G.ty == 0) || m == 0 || m == 1 || m == G.lx - 1 || pl == G.nx_ext - 1;
-    if (!zero) continue;
+    const bool whole = (y % G.ty == 0) || m == 0 || m == 1 || m == G.lx - 1 || pl == G.nx_ext - 1;
     float4* row = reinterpret_cast<float4*>(mesh + r * G.nz);
-    for (int i = lane; i < nz4; i += 32) row[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (whole) {
+      for (int i = lane; i < nz4; i += 32) row[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      for (int b = lane; b < G.nband; b += 32) row[b * bw4] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
 }
 
@@ -369,48 +354,29 @@ sweep_straggler_kernel(SweepGeom G, const short* __restrict__ pmid, const float*
 }
 
 // ---------------------------------------------------------------------------------------------
-// (pencil, plane) segment table.  id(i) = pencil * nx_ext + plane of particle slot i, either from the
-// keys of the last cell sort (reorder.cu, sweep key layout) or from pmid alone (Lagrangian order:
-// the particle grid's C order has one contiguous run per (plane, pencil)).
+// (tile, plane) segment table from the keys of the last cell sort (reorder.cu, sweep key layout):
+// id(i) = key / (ty * bw) = (y-tile * nband + z-tile) * nx_ext + plane of particle slot i.
 __global__ void __launch_bounds__(256)
-sweep_table_kernel(int64_t n, const uint32_t* __restrict__ keys, uint32_t key_div,
-                   const short* __restrict__ pmid, SweepGeom G, uint2* __restrict__ table) {
+sweep_table_kernel(int64_t n, const uint32_t* __restrict__ keys, uint32_t key_div, uint2* __restrict__ table) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    auto id_of = [&](int64_t j) -> uint32_t {
-      if (keys) return keys[j] / key_div;
-      int lp = wrap_index((int)pmid[3 * j + 0], G.nx) - G.xoff;
-      if (lp < 0) lp += G.nx;
-      if (lp >= G.nx_ext) lp = G.nx_ext - 1;
-      const int gy = wrap_index((int)pmid[3 * j + 1], G.ny);
-      return (uint32_t)((gy / G.ty) * G.nx_ext + lp);
-    };
-    const uint32_t id = id_of(i);
-    if (i == 0 || id_of(i - 1) != id) {
+    const uint32_t id = keys[i] / key_div;
+    const uint32_t idp = i > 0 ? keys[i - 1] / key_div : 0xffffffffu;
+    if (i == 0 || idp != id) {
       table[id].x = (uint32_t)i;
-      if (i > 0) table[id_of(i - 1)].y = (uint32_t)i;
+      if (i > 0) table[idp].y = (uint32_t)i;
     }
     if (i == n - 1) table[id].y = (uint32_t)n;
   }
 }
 
-// every particle slot must lie inside the range of its own id (together with one run per id this
+// every particle slot must lie inside the range of its own id (together with the total length this
 // makes the table an exact partition): counts violations
 __global__ void __launch_bounds__(256)
 sweep_table_check_kernel(int64_t n, const uint32_t* __restrict__ keys, uint32_t key_div,
-                         const short* __restrict__ pmid, SweepGeom G, const uint2* __restrict__ table,
-                         unsigned* __restrict__ bad) {
+                         const uint2* __restrict__ table, unsigned* __restrict__ bad) {
   unsigned local = 0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    uint32_t id;
-    if (keys) {
-      id = keys[i] / key_div;
-    } else {
-      int lp = wrap_index((int)pmid[3 * i + 0], G.nx) - G.xoff;
-      if (lp < 0) lp += G.nx;
-      if (lp >= G.nx_ext) lp = G.nx_ext - 1;
-      id = (uint32_t)((wrap_index((int)pmid[3 * i + 1], G.ny) / G.ty) * G.nx_ext + lp);
-    }
-    const uint2 s = table[id];
+    const uint2 s = table[keys[i] / key_div];
     if (!((uint32_t)i >= s.x && (uint32_t)i < s.y)) ++local;
   }
   if (local) atomicAdd(bad, local);
@@ -429,15 +395,11 @@ sweep_table_cover_kernel(int64_t nid, const uint2* __restrict__ table, unsigned 
 }
 
 // ---------------------------------------------------------------------------------------------
-static int ilog2_ceil_i(int x) { int b = 0; while ((1 << b) < x) ++b; return b; }
+// per warp: the ring + 64 words of straggler staging
+static size_t sweep_ring_bytes(int ty, int bw) { return (size_t)4 * (ty + 1) * (bw + 1) * sizeof(float) + 256; }
 
-static size_t sweep_smem_bytes(const SweepGeom& G) {
-  return (size_t)4 * (G.ty + 1) * G.nz * sizeof(float) + SW_THREADS * (sizeof(float4) + sizeof(float)) +
-         SW_WARPS * sizeof(int) + (size_t)G.lx * sizeof(uint2) + 64;
-}
-
-// Fills G for (d, ty, lx); returns false if the geometry is not supported by the sweep kernels.
-static bool sweep_geom(const pmwd_cic_desc* d, int ty, int lx, SweepGeom* G) {
+// Fills G for (d, ty, bw, lx); returns false if the geometry is not supported by the sweep kernels.
+static bool sweep_geom(const pmwd_cic_desc* d, int ty, int bw, int lx, SweepGeom* G) {
   if (!cic_is_fast(d)) return false;
   G->n = d->ptcl_num;
   G->nx = d->wrap_shape[0]; G->ny = d->wrap_shape[1]; G->nz = d->wrap_shape[2];
@@ -446,34 +408,50 @@ static bool sweep_geom(const pmwd_cic_desc* d, int ty, int lx, SweepGeom* G) {
   G->periodic = (G->nx_ext == G->nx && G->xoff == 0) ? 1 : 0;
   if (!G->periodic && G->nx_ext > G->nx) return false;      // halos wider than the box: RED kernel
   G->cell = (float)d->cell_size;
-  if (ty < 2 || ty > 64 || G->ny % ty != 0 || (G->nz & 3) != 0 || G->nz > (1 << 20) || G->nz < 8) return false;
+  if (ty < 2 || ty > 64 || G->ny % ty != 0) return false;
+  if (bw < 4 || bw > 256 || (bw & 3) != 0 || G->nz % bw != 0) return false;
   if (lx < 1 || G->nx_ext < 4) return false;
-  G->ty = ty;
-  G->npencil = G->ny / ty;
+  G->ty = ty; G->npencil = G->ny / ty;
+  G->bw = bw; G->nband = G->nz / bw;
   G->lx = lx < G->nx_ext ? lx : G->nx_ext;
   G->nseg = (G->nx_ext + G->lx - 1) / G->lx;
-  G->bw_shift = ilog2_ceil_i((G->nz + SW_WARPS - 1) / SW_WARPS);
-  if (G->bw_shift < 1) G->bw_shift = 1;
+  G->rs = bw + 1;
+  G->ps = (ty + 1) * G->rs;
   if (d->ptcl_num >= ((int64_t)1 << 32)) return false;
-  return sweep_smem_bytes(*G) <= 226 * 1024;      // 227 KB per CTA minus the kernel's static shared memory
+  if ((int64_t)G->nx_ext * G->ny * G->nz > ((int64_t)1 << 32)) return false;     // 32-bit sort keys
+  if ((int64_t)G->npencil * G->nband * G->nseg >= ((int64_t)1 << 31)) return false;
+  const size_t avail = 226 * 1024;
+  int nw = (int)(avail / sweep_ring_bytes(ty, bw));
+  if (nw > SW_MAX_WARPS) nw = SW_MAX_WARPS;
+  if (nw < 4) return false;
+  G->nwarps = nw;
+  return true;
 }
 
 }  // namespace pmwd
 
 using namespace pmwd;
 
-// Largest supported pencil height for this mesh (0: the sweep scatter cannot be used).
-extern "C" int pmwd_sweep_pick_ty(const pmwd_cic_desc* d) {
-  if (!d) return 0;
+// Tile shape for this mesh: ty = the largest divisor of ny up to 16, bw = a multiple of 4 dividing nz
+// (32 preferred).  Returns 1 and fills *ty, *bw, or 0 if the sweep kernels do not support the mesh.
+extern "C" int pmwd_sweep_pick(const pmwd_cic_desc* d, int* ty_out, int* bw_out) {
+  if (!d || d->dim != 3) return 0;
+  const int ny = d->wrap_shape[1], nz = d->wrap_shape[2];
+  int ty = 0, bw = 0;
+  for (int t = 16; t >= 2; --t) if (ny % t == 0) { ty = t; break; }
+  for (int b = 32; b >= 4; b -= 4) if (nz % b == 0) { bw = b; break; }
+  if (bw < 16) for (int b = 36; b <= 128; b += 4) if (nz % b == 0) { bw = b; break; }
+  if (!ty || !bw) return 0;
   SweepGeom G;
-  for (int ty = 8; ty >= 2; ty >>= 1)
-    if (sweep_geom(d, ty, 64, &G)) return ty;
-  return 0;
+  if (!sweep_geom(d, ty, bw, 64, &G)) return 0;
+  if (ty_out) *ty_out = ty;
+  if (bw_out) *bw_out = bw;
+  return 1;
 }
 
-extern "C" size_t pmwd_sweep_table_bytes(const pmwd_cic_desc* d, int ty) {
-  if (!d || ty <= 0 || d->mesh_shape[1] % ty) return 0;
-  return (size_t)(d->mesh_shape[1] / ty) * d->mesh_shape[0] * sizeof(uint2);
+extern "C" size_t pmwd_sweep_table_bytes(const pmwd_cic_desc* d, int ty, int bw) {
+  if (!d || ty <= 0 || bw <= 0 || d->wrap_shape[1] % ty || d->wrap_shape[2] % bw) return 0;
+  return (size_t)(d->wrap_shape[1] / ty) * (d->wrap_shape[2] / bw) * d->mesh_shape[0] * sizeof(uint2);
 }
 
 // counters (64 bytes) + straggler list (4 bytes per particle)
@@ -482,27 +460,25 @@ extern "C" size_t pmwd_sweep_scratch_bytes(const pmwd_cic_desc* d) {
   return 64 + (size_t)d->ptcl_num * sizeof(uint32_t);
 }
 
-// Build the (pencil, plane) table.  `keys`: the sorted keys of pmwd_cell_sort_perm in the sweep key
-// layout (ty = the sort's ty), or NULL to derive the segments from pmid (Lagrangian order).
+// Build the (tile, plane) table from the sorted keys of pmwd_cell_sort_perm(..., ty, bw).
 // `status` (device, 16 bytes, zeroed here): [0] = particles outside their segment (unsigned),
 // [8] = total length of all ranges (unsigned long long); the table is valid iff status[0] == 0 and
-// total == ptcl_num.  Enqueue-only; the caller reads `status` after synchronising.
-extern "C" int pmwd_sweep_table(void* stream, const pmwd_cic_desc* d, int ty, const uint32_t* keys,
-                                const void* pmid, uint32_t* table, void* status) {
-  PMWD_REQUIRE(d && table && status && (keys || pmid), "null buffer");
+// total == ptcl_num (true by construction for sorted keys; tests read it back).  Enqueue-only.
+extern "C" int pmwd_sweep_table(void* stream, const pmwd_cic_desc* d, int ty, int bw, const uint32_t* keys,
+                                uint32_t* table, void* status) {
+  PMWD_REQUIRE(d && table && status && keys, "null buffer");
   SweepGeom G;
-  PMWD_REQUIRE(sweep_geom(d, ty, 64, &G), "geometry not supported by the sweep scatter");
+  PMWD_REQUIRE(sweep_geom(d, ty, bw, 64, &G), "geometry not supported by the sweep scatter");
   cudaStream_t st = as_stream(stream);
-  const int64_t nid = (int64_t)G.npencil * G.nx_ext;
+  const int64_t nid = (int64_t)G.npencil * G.nband * G.nx_ext;
   PMWD_CUDA_TRY(cudaMemsetAsync(table, 0, (size_t)nid * sizeof(uint2), st));
   PMWD_CUDA_TRY(cudaMemsetAsync(status, 0, 16, st));
   if (G.n == 0) return PMWD_OK;
-  const uint32_t key_div = (uint32_t)((ty / 2) * G.nz);
+  const uint32_t key_div = (uint32_t)(ty * bw);
   const int grid = grid_for(G.n, 256, 8);
-  sweep_table_kernel<<<grid, 256, 0, st>>>(G.n, keys, key_div, (const short*)pmid, G, (uint2*)table);
+  sweep_table_kernel<<<grid, 256, 0, st>>>(G.n, keys, key_div, (uint2*)table);
   PMWD_LAUNCH_CHECK();
-  sweep_table_check_kernel<<<grid, 256, 0, st>>>(G.n, keys, key_div, (const short*)pmid, G, (const uint2*)table,
-                                                 (unsigned*)status);
+  sweep_table_check_kernel<<<grid, 256, 0, st>>>(G.n, keys, key_div, (const uint2*)table, (unsigned*)status);
   PMWD_LAUNCH_CHECK();
   sweep_table_cover_kernel<<<grid_for(nid, 256, 8), 256, 0, st>>>(nid, (const uint2*)table,
                                                                   (unsigned long long*)((char*)status + 8));
@@ -515,7 +491,7 @@ namespace pmwd {
 bool sweep_usable(const pmwd_cic_desc* d, const pmwd_sweep* sw) {
   if (!sw || !sw->table || !sw->scratch) return false;
   SweepGeom G;
-  if (!sweep_geom(d, sw->ty, sw->lx, &G)) return false;
+  if (!sweep_geom(d, sw->ty, sw->bw, sw->lx, &G)) return false;
   if (sw->nx_ext != G.nx_ext || sw->xoff != G.xoff) return false;      // table built for another slab
   return sw->scratch_bytes >= 64 + (size_t)d->ptcl_num * sizeof(uint32_t);
 }
@@ -526,11 +502,11 @@ int scatter_sweep(cudaStream_t st, const pmwd_cic_desc* d, const pmwd_sweep* sw,
                   const float* disp, const float* val, int vstride, float vscalar, float* mesh,
                   bool reuse_stragglers) {
   SweepGeom G;
-  PMWD_REQUIRE(sweep_geom(d, sw->ty, sw->lx, &G), "geometry not supported by the sweep scatter");
+  PMWD_REQUIRE(sweep_geom(d, sw->ty, sw->bw, sw->lx, &G), "geometry not supported by the sweep scatter");
   unsigned* counters = (unsigned*)sw->scratch;
   uint32_t* strag = (uint32_t*)((char*)sw->scratch + 64);
   static int smem_set = 0;
-  const size_t smem = sweep_smem_bytes(G);
+  const size_t smem = (size_t)G.nwarps * sweep_ring_bytes(G.ty, G.bw);
   if (!smem_set) {
     PMWD_CUDA_TRY(cudaFuncSetAttribute(scatter_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        226 * 1024));
@@ -540,9 +516,10 @@ int scatter_sweep(cudaStream_t st, const pmwd_cic_desc* d, const pmwd_sweep* sw,
   const int64_t rows = (int64_t)G.nx_ext * G.ny;
   sweep_zero_kernel<<<grid_for(rows * 32, 256, 8), 256, 0, st>>>(G, mesh);
   PMWD_LAUNCH_CHECK();
-  const int nitems = G.npencil * G.nseg;
-  const int grid = nitems < sm_count() ? nitems : sm_count();
-  scatter_sweep_kernel<<<grid, SW_THREADS, smem, st>>>(G, (const short*)pmid, disp, val, vstride, vscalar, mesh,
+  const int64_t nitems = (int64_t)G.npencil * G.nband * G.nseg;
+  const int64_t want = (nitems + G.nwarps - 1) / G.nwarps;
+  const int grid = (int)(want < sm_count() ? want : sm_count());
+  scatter_sweep_kernel<<<grid, G.nwarps * 32, smem, st>>>(G, (const short*)pmid, disp, val, vstride, vscalar, mesh,
                                                        (const uint2*)sw->table, counters, strag,
                                                        reuse_stragglers ? 0 : 1);
   PMWD_LAUNCH_CHECK();

@@ -103,18 +103,17 @@ class _Store:
         self.sweep = None          # sweep.SweepState: table + scratch of the tiled deposit
 
     def setup_sweep(self):
-        """Tiled deposit (csrc/scatter_sweep.cu) for the single-device fast path: the table is first
-        derived from pmid (Lagrangian C order), later rebuilt from every re-sort.  An order without
-        one contiguous run per (pencil, plane) leaves the RED kernel in charge until the first sort."""
+        """Tiled deposit (csrc/scatter_sweep.cu) for the single-device fast path: the storage is sorted
+        into the tile order right away (one sort per run) and the table rebuilt from every re-sort."""
         conf, a = self.conf, self.arrays
         if self.desc_fn is not None or not _sweep.enabled(conf) or conf.dim != 3 \
-                or a['pmid'].dtype != torch.int16:
+                or a['pmid'].dtype != torch.int16 or conf.reorder_every <= 0:
             return
         desc = _force_desc(a['pmid'], conf)
         st = _sweep.SweepState(desc, a['disp'].device)
         if st.ty > 0:
-            st.build(desc, pmid=a['pmid'], check=True)
             self.sweep = st
+            self.reorder()
 
     def sweep_arg(self):
         return self.sweep.arg() if self.sweep is not None else None
@@ -160,10 +159,10 @@ class _Store:
             self._scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
-            ty = self.sweep.ty if self.sweep is not None else 0
+            ty, bw = (self.sweep.ty, self.sweep.bw) if self.sweep is not None else (0, 0)
             _lib.check(lib.pmwd_cell_sort_perm(st, C.byref(desc), _lib.ptr(a['pmid']), _lib.ptr(a['disp']),
                                                _lib.ptr(self._perm), _lib.ptr(self._scratch),
-                                               self._scratch.numel(), ty), 'pmwd_cell_sort_perm')
+                                               self._scratch.numel(), ty, bw), 'pmwd_cell_sort_perm')
             names = list(a) + ['lag']
             cur = dict(a, lag=self.lag)
             src = (C.c_void_p * len(names))(*[cur[k].data_ptr() for k in names])
@@ -180,7 +179,7 @@ class _Store:
         if self.sweep is not None:
             # table of the new order from the sort's own keys (valid by construction: no read-back)
             keys = lib.pmwd_cell_sort_sorted_keys(C.byref(desc), _lib.ptr(self._scratch))
-            self.sweep.build(desc, keys_ptr=C.c_void_p(keys), check=False)
+            self.sweep.build(desc, C.c_void_p(keys))
 
     def lagrangian(self, *names):
         """Arrays restored to Lagrangian order (new tensors; storage untouched)."""
@@ -200,7 +199,7 @@ class _Store:
         return outs if len(outs) > 1 else outs[0]
 
 
-def _store_from(ptcl, conf, **extra):
+def _store_from(ptcl, conf, _tiled=True, **extra):
     p = _owned(ptcl, conf)
     # pmid is cloned too: the store ping-pongs between two buffer sets when it re-sorts and
     # must never write into the caller's tensors
@@ -208,7 +207,8 @@ def _store_from(ptcl, conf, **extra):
     arrays = dict(pmid=pmid, disp=p.disp, vel=p.vel, acc=p.acc)
     arrays.update(extra)
     store = _Store(conf, arrays)
-    store.setup_sweep()
+    if _tiled:
+        store.setup_sweep()
     return store
 
 
@@ -494,18 +494,19 @@ def nbody_adj(ptcl, ptcl_cot, obsvbl_cot, cosmo, conf, reverse=False, _slab=None
     lib = _lib.lib()
     pmid_in = ptcl.pmid
     with torch.no_grad():
+        xi = ptcl_cot.disp.detach().to(conf.float_dtype).clone(memory_format=torch.contiguous_format)
         store = _store_from(
-            ptcl, conf,
-            xi=ptcl_cot.disp.detach().to(conf.float_dtype).clone(memory_format=torch.contiguous_format),
-            pi=ptcl_cot.vel.detach().to(conf.float_dtype).clone(memory_format=torch.contiguous_format))
-        store.arrays['alpha'] = torch.empty_like(store.arrays['xi'])
+            ptcl, conf, _tiled=_slab is None, xi=xi,
+            pi=ptcl_cot.vel.detach().to(conf.float_dtype).clone(memory_format=torch.contiguous_format),
+            alpha=torch.empty_like(xi))
         if _slab is not None:
             store.desc_fn = lambda pmid: _slab._desc(pmid, max(_slab.h_alloc, 1))
         n = store.arrays['xi'].numel()
         if conf.reorder_every > 0 and _fast_ok(ptcl, conf) and \
                 float(store.arrays['disp'].abs().max()) >= conf.reorder_min_disp * conf.cell_size:
             store.active = True
-            store.reorder()       # the adjoint starts from the evolved (clustered) state
+            if store.reorders == 0:   # (the tiled deposit has already sorted the storage)
+                store.reorder()       # the adjoint starts from the evolved (clustered) state
         pairs = list(zip(a_nbody[:0:-1], a_nbody[-2::-1]))
         # per kick / drift: float64 dot products kept on the device until the end
         nsplit = len(conf.symp_splits)

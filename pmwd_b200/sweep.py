@@ -2,10 +2,9 @@
 
 The reference's ``_scatter`` (``pmwd/scatter.py:33-83``) is one XLA scatter-add over all particles.
 Inside the integrator the deposit instead goes through shared-memory mesh tiles: the particle
-storage is kept sorted by (y-pencil, x-plane, ...) -- or is still in the reference's Lagrangian C
-order (``pmwd/particles.py:135-139``), which has the same segment structure -- and a small table
-gives the particle range of every (pencil, plane).  This module owns that table and the scratch
-area (work counters + straggler list) and hands them to the C library as a ``pmwd_sweep``.
+storage is kept sorted by (y-tile, z-tile, x-plane, y, z) and a table gives the particle range of
+every (tile, plane).  This module owns that table and the scratch area (work counters + straggler
+list) and hands them to the C library as a ``pmwd_sweep``.
 """
 import ctypes as C
 import os
@@ -27,15 +26,17 @@ class SweepState:
 
     def __init__(self, desc, dev, lx=LX):
         lib = _lib.lib()
-        self.ty = int(lib.pmwd_sweep_pick_ty(C.byref(desc)))
+        ty, bw = C.c_int32(0), C.c_int32(0)
+        ok = lib.pmwd_sweep_pick(C.byref(desc), C.byref(ty), C.byref(bw))
+        self.ty, self.bw = (int(ty.value), int(bw.value)) if ok else (0, 0)
         self.ok = False
         self.dev = dev
         if self.ty <= 0:
             return
         self.lx = lx
         self.nx_ext = int(desc.mesh_shape[0])
-        self.table = torch.zeros(lib.pmwd_sweep_table_bytes(C.byref(desc), self.ty) // 4, dtype=torch.int32,
-                                 device=dev)
+        self.table = torch.zeros(lib.pmwd_sweep_table_bytes(C.byref(desc), self.ty, self.bw) // 4,
+                                 dtype=torch.int32, device=dev)
         self.scratch = torch.empty(lib.pmwd_sweep_scratch_bytes(C.byref(desc)), dtype=torch.uint8, device=dev)
         self.status = torch.zeros(2, dtype=torch.int64, device=dev)
         self._struct = None
@@ -44,7 +45,7 @@ class SweepState:
     def _make_struct(self, desc):
         s = _lib.Sweep()
         s.table = self.table.data_ptr()
-        s.ty, s.lx = self.ty, self.lx
+        s.ty, s.bw, s.lx = self.ty, self.bw, self.lx
         s.nx_ext = int(desc.mesh_shape[0])
         a1 = float(torch.tensor(desc.cell_size, dtype=torch.float32))
         s.xoff = int(desc.offset[0] // a1) % int(desc.wrap_shape[0])
@@ -52,17 +53,15 @@ class SweepState:
         s.scratch_bytes = self.scratch.numel()
         self._struct = s
 
-    def build(self, desc, pmid=None, keys_ptr=None, check=True):
-        """(Re)build the table from the sort's keys (``keys_ptr``) or from ``pmid`` (Lagrangian order).
+    def build(self, desc, keys_ptr, check=False):
+        """(Re)build the table from the keys of the sort that has just ordered the storage.
         With ``check`` the device-side validation is read back (one synchronisation); an invalid
         table leaves the state unusable (``ok`` False) and the RED kernel in charge."""
         if self.ty <= 0:
             return False
         lib = _lib.lib()
         with torch.cuda.device(self.dev):
-            _lib.check(lib.pmwd_sweep_table(_lib.stream_ptr(self.dev), C.byref(desc), self.ty,
-                                            keys_ptr if keys_ptr is not None else None,
-                                            _lib.ptr(pmid) if keys_ptr is None else None,
+            _lib.check(lib.pmwd_sweep_table(_lib.stream_ptr(self.dev), C.byref(desc), self.ty, self.bw, keys_ptr,
                                             _lib.ptr(self.table), _lib.ptr(self.status)), 'pmwd_sweep_table')
         self.ok = True
         if check:

@@ -1,6 +1,6 @@
-"""GPU parity of the tiled ("pencil sweep") CIC deposit (csrc/scatter_sweep.cu) against the oracle's
-scatter (pmwd/scatter.py:60-83) and against the per-particle RED kernel, in Lagrangian order, in
-re-sorted order, with stale sorts (stragglers), 3 channels, anisotropic meshes and slab descriptors.
+"""GPU parity of the tiled ("tile sweep") CIC deposit (csrc/scatter_sweep.cu) against the oracle's
+scatter (pmwd/scatter.py:60-83) and against the per-particle RED kernel: freshly sorted storage,
+stale sorts (stragglers), 3 channels, anisotropic meshes with odd tile shapes.
 Tolerance: per-cell density rel. err <= 1e-5 (of max(density, 1)), the north-star figure."""
 import ctypes as C
 
@@ -52,21 +52,21 @@ def _close(got, want):
 
 
 @pytest.mark.parametrize('shape, sigma', [((32, 32, 32), 0.3), ((32, 32, 32), 3.0), ((12, 10, 18), 0.4),
-                                          ((8, 8, 512), 0.5), ((40, 6, 34), 0.2), ((16, 16, 16), 40.0)],
+                                          ((8, 8, 512), 0.5), ((40, 6, 34), 0.2), ((16, 16, 16), 40.0),
+                                          ((64, 16, 48), 1.0)],
                          ids=lambda v: 'x'.join(str(n) for n in v) if isinstance(v, tuple) else str(v))
-def test_sweep_scatter_lagrangian_order_vs_oracle(shape, sigma):
-    """Storage in the reference's Lagrangian order, table derived from pmid.  Small displacements:
-    (almost) everything goes through the shared-memory tiles; large ones: mostly stragglers."""
+def test_sweep_scatter_fresh_sort_vs_oracle(shape, sigma):
+    """The store sorts its arrays into the tile order when it is set up: every particle goes through
+    the shared-memory tiles (no stragglers), whatever the displacement amplitude and tile shape."""
     from pmwd_b200.nbody import _store_from
     pm, conf, oconf, pmid, disp, ptcl = _setup(shape, sigma)
     store = _store_from(ptcl, conf)
-    assert store.sweep is not None and store.sweep.ok, 'sweep table from pmid must be valid for gen_grid order'
+    assert store.sweep is not None and store.sweep.ok and store.reorders == 1
+    st = store.sweep.status.cpu()
+    assert int(st[0]) & 0xffffffff == 0 and int(st[1]) == conf.ptcl_num      # the table is an exact partition
     dens, = _sweep_scatter(store, conf)
     _close(dens, O.scatter(pmid, disp, oconf))
-    n_strag = store.sweep.stragglers()
-    print('stragglers', n_strag, 'of', conf.ptcl_num)
-    if sigma <= 0.5:
-        assert n_strag < 0.6 * conf.ptcl_num
+    assert store.sweep.stragglers() == 0
 
 
 @pytest.mark.parametrize('shape, sigma', [((32, 32, 32), 2.0), ((24, 16, 64), 5.0), ((8, 8, 512), 6.0)],
@@ -77,7 +77,6 @@ def test_sweep_scatter_sorted_and_stale_order(shape, sigma):
     from pmwd_b200.nbody import _store_from
     pm, conf, oconf, pmid, disp, ptcl = _setup(shape, sigma)
     store = _store_from(ptcl, conf)
-    store.reorder()
     assert store.sweep.ok
     dens, = _sweep_scatter(store, conf)
     _close(dens, O.scatter(pmid, disp, oconf))
@@ -101,7 +100,6 @@ def test_sweep_scatter_three_channels_vs_red_kernel():
     from pmwd_b200.nbody import _store_from
     pm, conf, oconf, pmid, disp, ptcl = _setup((32, 32, 32), 2.0)
     store = _store_from(ptcl, conf)
-    store.reorder()
     a = store.arrays
     g = torch.Generator(device='cuda').manual_seed(1)
     pi = torch.randn(a['disp'].shape, device='cuda', generator=g)
@@ -123,19 +121,18 @@ def test_sweep_scatter_three_channels_vs_red_kernel():
     assert np.abs(V[1].cpu().numpy() - mc).max() <= 2e-6 * np.abs(mc).max()
 
 
-def test_sweep_table_rejects_unordered_storage():
-    """A storage order without one contiguous run per (pencil, plane) must leave the RED kernel in
-    charge (no silent loss of particles): the table check fails and the sweep argument is NULL."""
+def test_sweep_handles_arbitrary_input_order():
+    """The caller's particle order does not matter (the store sorts its private copies): a randomly
+    permuted input gives the same density and the outputs come back in the caller's order."""
     from pmwd_b200.nbody import _store_from
-    pm, conf, oconf, pmid, disp, ptcl = _setup((16, 16, 16), 0.3)
+    pm, conf, oconf, pmid, disp, ptcl = _setup((16, 16, 16), 0.8)
     perm = torch.randperm(conf.ptcl_num, device='cuda', generator=torch.Generator(device='cuda').manual_seed(0))
     shuffled = pm.Particles(conf, ptcl.pmid[perm].contiguous(), ptcl.disp[perm].contiguous(), vel=ptcl.vel)
     store = _store_from(shuffled, conf)
-    assert store.sweep is not None and not store.sweep.ok and store.sweep_arg() is None
-    store.reorder()                        # the first re-sort makes it usable
-    assert store.sweep.ok and store.sweep_arg() is not None
+    assert store.sweep is not None and store.sweep.ok and store.sweep_arg() is not None
     dens, = _sweep_scatter(store, conf)
     _close(dens, O.scatter(pmid, disp, oconf))
+    assert torch.equal(store.lagrangian('disp'), shuffled.disp)
 
 
 @pytest.mark.parametrize('tiled', [True, False])
