@@ -303,6 +303,11 @@ int pmwd_permute_rows(void* stream, int64_t n, const uint32_t* perm, int narr,
  * The caller brackets the call with cross-rank barriers. */
 int pmwd_transpose_p2p(void* stream, int mode, int nranks, int rank, int mx, int my, int nzc,
                        const void* src_c64, const uint64_t* peer_ptrs);
+/* The same transposes on the copy engines (one strided 2-D peer copy per rank, spread over
+ * `nstreams` <= 4 internal streams that `stream` forks and joins): no SM pushes data, so the
+ * transposes do not slow down the kernels they overlap with. */
+int pmwd_transpose_ce(void* stream, int mode, int nranks, int rank, int mx, int my, int nzc,
+                      const void* src_c64, const uint64_t* peer_ptrs, int nstreams);
 
 /* ---- leapfrog updates: pmwd/nbody.py:39-99 ----------------------------------------- */
 /* kick (nbody.py:70-77) then drift (nbody.py:39-46) in one pass over n = N*dim floats:

@@ -112,6 +112,7 @@ _SIGNATURES = {
     'pmwd_cell_sort_sorted_keys': (_vp, [_descp, _vp]),
     'pmwd_permute_rows': (_i, [_vp, _i64, _vp, _i, C.POINTER(_vp), C.POINTER(_vp), _i32p, _i]),
     'pmwd_transpose_p2p': (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, C.POINTER(C.c_uint64)]),
+    'pmwd_transpose_ce': (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, C.POINTER(C.c_uint64), _i]),
     'pmwd_kick_drift': (_i, [_vp, _i64, _vp, _vp, _vp, _f, _f, _i, _i]),
     'pmwd_kick_drift_adj': (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _i, _vp]),
 }

@@ -278,3 +278,69 @@ extern "C" int pmwd_transpose_p2p(void* stream, int mode, int nranks, int rank, 
   PMWD_LAUNCH_CHECK();
   return PMWD_OK;
 }
+
+
+// The same transposes on the COPY ENGINES: per peer one strided 2-D cudaMemcpy (runs of my * nzc
+// complex64 = the peer's y-range of one x plane), so that no SM is busy pushing data over NVLink
+// while the 2-D C2R of the previous component runs (the P2P-store kernel above doubled that C2R's
+// time at N = 8: SCALE_r01 phase table).  The copies are spread over a few internal streams
+// (several copy engines) and start with the next rank so that the ranks do not all target the same
+// destination at once; `stream` waits for all of them.
+namespace pmwd {
+struct CeStreams {
+  cudaStream_t s[4];
+  cudaEvent_t fork, join[4];
+  int device = -1;
+};
+static CeStreams g_ce;
+static int ce_init() {
+  int dev = 0;
+  PMWD_CUDA_TRY(cudaGetDevice(&dev));
+  if (g_ce.device == dev) return PMWD_OK;
+  for (int i = 0; i < 4; ++i) {
+    PMWD_CUDA_TRY(cudaStreamCreateWithFlags(&g_ce.s[i], cudaStreamNonBlocking));
+    PMWD_CUDA_TRY(cudaEventCreateWithFlags(&g_ce.join[i], cudaEventDisableTiming));
+  }
+  PMWD_CUDA_TRY(cudaEventCreateWithFlags(&g_ce.fork, cudaEventDisableTiming));
+  g_ce.device = dev;
+  return PMWD_OK;
+}
+}  // namespace pmwd
+
+extern "C" int pmwd_transpose_ce(void* stream, int mode, int nranks, int rank, int mx, int my, int nzc,
+                                 const void* src, const uint64_t* peer_ptrs, int nstreams) {
+  PMWD_REQUIRE(src && peer_ptrs, "null buffer");
+  PMWD_REQUIRE(nranks >= 1 && nranks <= 8 && rank >= 0 && rank < nranks, "bad rank / world size");
+  PMWD_REQUIRE(mx > 0 && my > 0 && nzc > 0 && (mode == 0 || mode == 1), "bad sizes");
+  if (nstreams < 1) nstreams = 1;
+  if (nstreams > 4) nstreams = 4;
+  int rc = pmwd::ce_init();
+  if (rc) return rc;
+  cudaStream_t st = pmwd::as_stream(stream);
+  pmwd::StageTimer timer(pmwd::ST_OTHER, st);
+  PMWD_CUDA_TRY(cudaEventRecord(pmwd::g_ce.fork, st));
+  for (int i = 0; i < nstreams; ++i) PMWD_CUDA_TRY(cudaStreamWaitEvent(pmwd::g_ce.s[i], pmwd::g_ce.fork, 0));
+  const size_t run = (size_t)my * nzc * sizeof(float2);          // contiguous bytes per (x plane, peer)
+  const size_t My_run = run * nranks;                            // bytes of a full x plane [My][nzc]
+  const char* s8 = (const char*)src;
+  for (int k = 0; k < nranks; ++k) {
+    const int q = (rank + 1 + k) % nranks;                       // own block last
+    char* d8 = reinterpret_cast<char*>(peer_ptrs[q]);
+    PMWD_REQUIRE(d8 != nullptr, "null peer pointer");
+    cudaStream_t cs = pmwd::g_ce.s[k % nstreams];
+    if (mode == 0) {
+      // src[ix][q*my + iy][:] -> dst_q[rank*mx + ix][iy][:]
+      PMWD_CUDA_TRY(cudaMemcpy2DAsync(d8 + (size_t)rank * mx * run, run, s8 + (size_t)q * run, My_run, run,
+                                      (size_t)mx, cudaMemcpyDeviceToDevice, cs));
+    } else {
+      // src[q*mx + ix][iy][:] -> dst_q[ix][rank*my + iy][:]
+      PMWD_CUDA_TRY(cudaMemcpy2DAsync(d8 + (size_t)rank * run, My_run, s8 + (size_t)q * mx * run, run, run,
+                                      (size_t)mx, cudaMemcpyDeviceToDevice, cs));
+    }
+  }
+  for (int i = 0; i < nstreams; ++i) {
+    PMWD_CUDA_TRY(cudaEventRecord(pmwd::g_ce.join[i], pmwd::g_ce.s[i]));
+    PMWD_CUDA_TRY(cudaStreamWaitEvent(st, pmwd::g_ce.join[i], 0));
+  }
+  return PMWD_OK;
+}

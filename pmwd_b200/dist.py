@@ -141,8 +141,7 @@ class SlabComm:
             s = self._rfft2(real)
         nzc = s.shape[-1]
         with TIMERS('p2p_transpose'):
-            _lib.check(_lib.lib().pmwd_transpose_p2p(_lib.stream_ptr(real.device), 0, P, self.rank, mx, My // P,
-                                                     nzc, _lib.ptr(s), self._p2p[slot][2]), 'pmwd_transpose_p2p')
+            self._transpose(real.device, 0, mx, My // P, nzc, s, slot)
         return self._p2p_view(slot, (P * mx, My // P, nzc))
 
     def p2p_inverse(self, spec, slot):
@@ -151,9 +150,21 @@ class SlabComm:
         P = self.size
         Mx, my, nzc = spec.shape
         with TIMERS('p2p_transpose'):
-            _lib.check(_lib.lib().pmwd_transpose_p2p(_lib.stream_ptr(spec.device), 1, P, self.rank, Mx // P, my,
-                                                     nzc, _lib.ptr(spec), self._p2p[slot][2]), 'pmwd_transpose_p2p')
+            self._transpose(spec.device, 1, Mx // P, my, nzc, spec, slot)
         return self._p2p_view(slot, (Mx // P, my * P, nzc))
+
+    def _transpose(self, dev, mode, mx, my, nzc, src, slot):
+        """Slab-FFT transpose into receive buffer ``slot`` of every peer: strided peer copies on the
+        copy engines (default), or the P2P-store kernel (``PMWD_P2P_CE=0``, A/B partner)."""
+        lib = _lib.lib()
+        st = _lib.stream_ptr(dev)
+        if os.environ.get('PMWD_P2P_CE', '1') != '0':
+            _lib.check(lib.pmwd_transpose_ce(st, mode, self.size, self.rank, mx, my, nzc, _lib.ptr(src),
+                                             self._p2p[slot][2], int(os.environ.get('PMWD_P2P_CE_STREAMS', '4'))),
+                       'pmwd_transpose_ce')
+        else:
+            _lib.check(lib.pmwd_transpose_p2p(st, mode, self.size, self.rank, mx, my, nzc, _lib.ptr(src),
+                                              self._p2p[slot][2]), 'pmwd_transpose_p2p')
 
     # ---- particles -----------------------------------------------------------------------
     def local_slice(self):

@@ -13,7 +13,7 @@ for f in sys.argv[1:]:
     for k, v in (d.get('kernels') or {}).items():
         print('   F %-18s ms/launch %-8s frac %-7s share %-7s total %s' % (k, v.get('ms_per_launch'), v.get('frac'), v.get('share_of_step'), v.get('ms_total')))
     if d.get('adjoint'):
-        for k, v in d['adjoint']['kernels'].items():
+        for k, v in d['adjoint'].get('kernels', {}).items():
             print('   A %-18s ms/launch %-8s frac %-7s ms/step %s' % (k, v.get('ms_per_launch'), v.get('frac'), v.get('ms_per_step')))
     if d.get('phase_ms_per_step_rank0'):
         print('   phases', d['phase_ms_per_step_rank0'])
