@@ -190,6 +190,24 @@ int pmwd_powspec_weight(void* stream, const int32_t* shape, const void* f_c64, i
                         double deconv, const double* edges_f64, int nedges, int right,
                         const double* wbin_f64, void* out_c64);
 
+/* ---- fused elementwise passes of LPT: pmwd/lpt.py:40-76, 190-208 ---------------------- */
+/* 2LPT source (m == n) from the six real strain fields s = {s00, s11, s22, s01, s02, s12}[n]:
+ * L = s00 s22 + s00 s11 + s11 s22 - s01^2 - s02^2 - s12^2 in the reference's summation order; and
+ * its VJP s_cot[k] = dL/ds_k * L_cot. */
+int pmwd_lpt_source2(void* stream, int64_t n, const float* const* s, float* L);
+int pmwd_lpt_source2_vjp(void* stream, int64_t n, const float* const* s, const float* L_cot,
+                         float* const* s_cot);
+/* disp[p][a] = (disp0[p][a] + D1 g1[a][p]) + D2 g2[a][p]; vel likewise with V1, V2 (lpt.py:203-208,
+ * order 1 then order 2; g2 == NULL for first-order LPT).  VJP: g1_cot[a] = D1 disp_cot[:, a] +
+ * V1 vel_cot[:, a] (g2 likewise) and sums[4] += (sum disp_cot g1, sum vel_cot g1, sum disp_cot g2,
+ * sum vel_cot g2) in float64 = the cotangents of D1, V1, D2, V2. */
+int pmwd_lpt_displace(void* stream, int64_t n, const float* disp0, const float* vel0,
+                      const float* const* g1, const float* const* g2, float D1, float V1, float D2,
+                      float V2, float* disp, float* vel);
+int pmwd_lpt_displace_vjp(void* stream, int64_t n, const float* disp_cot, const float* vel_cot,
+                          const float* const* g1, const float* const* g2, float D1, float V1, float D2,
+                          float V2, float* const* g1_cot, float* const* g2_cot, double* sums);
+
 /* ---- slab-decomposed (multi-GPU) building blocks ------------------------------------- */
 /* The reference's own (offset, mesh shape) semantics describe a slab: a mesh array holding
  * d->mesh_shape[0] x-planes starting at global plane d->offset[0] / cell_size of the periodic
@@ -308,6 +326,11 @@ int pmwd_transpose_p2p(void* stream, int mode, int nranks, int rank, int mx, int
  * transposes do not slow down the kernels they overlap with. */
 int pmwd_transpose_ce(void* stream, int mode, int nranks, int rank, int mx, int my, int nzc,
                       const void* src_c64, const uint64_t* peer_ptrs, int nstreams);
+/* Generic form for chunk-pipelined transposes: to every rank q one strided 2-D copy of `height` rows
+ * of `width` bytes, src + q * src_peer_stride (pitch spitch) -> peer_ptrs[q] + dst_off (pitch dpitch). */
+int pmwd_peer_copy2d(void* stream, int nranks, int rank, size_t width, size_t height, const void* src,
+                     size_t src_peer_stride, size_t spitch, const uint64_t* peer_ptrs, size_t dst_off,
+                     size_t dpitch, int nstreams);
 
 /* ---- leapfrog updates: pmwd/nbody.py:39-99 ----------------------------------------- */
 /* kick (nbody.py:70-77) then drift (nbody.py:39-46) in one pass over n = N*dim floats:

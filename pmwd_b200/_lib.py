@@ -87,6 +87,11 @@ _SIGNATURES = {
     'pmwd_strain': (_i, [_vp, _i, _i32p, _d, _i, _i, _vp, _vp]),
     'pmwd_powspec_bin': (_i, [_vp, _i32p, _vp, _vp, _i, _d, _vp, _i, _i, _vp]),
     'pmwd_powspec_weight': (_i, [_vp, _i32p, _vp, _i, _d, _vp, _i, _i, _vp, _vp]),
+    'pmwd_lpt_source2': (_i, [_vp, _i64, C.POINTER(_vp), _vp]),
+    'pmwd_lpt_source2_vjp': (_i, [_vp, _i64, C.POINTER(_vp), _vp, C.POINTER(_vp)]),
+    'pmwd_lpt_displace': (_i, [_vp, _i64, _vp, _vp, C.POINTER(_vp), C.POINTER(_vp), _f, _f, _f, _f, _vp, _vp]),
+    'pmwd_lpt_displace_vjp': (_i, [_vp, _i64, _vp, _vp, C.POINTER(_vp), C.POINTER(_vp), _f, _f, _f, _f,
+                                   C.POINTER(_vp), C.POINTER(_vp), _vp]),
     'pmwd_scatter_soa': (_i, [_vp, _descp, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp]),
     'pmwd_gather3': (_i, [_vp, _descp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f]),
     'pmwd_gather3_kdk': (_i, [_vp, _descp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f]),
@@ -113,6 +118,7 @@ _SIGNATURES = {
     'pmwd_permute_rows': (_i, [_vp, _i64, _vp, _i, C.POINTER(_vp), C.POINTER(_vp), _i32p, _i]),
     'pmwd_transpose_p2p': (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, C.POINTER(C.c_uint64)]),
     'pmwd_transpose_ce': (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, C.POINTER(C.c_uint64), _i]),
+    'pmwd_peer_copy2d': (_i, [_vp, _i, _i, _sz, _sz, _vp, _sz, _sz, C.POINTER(C.c_uint64), _sz, _sz, _i]),
     'pmwd_kick_drift': (_i, [_vp, _i64, _vp, _vp, _vp, _f, _f, _i, _i]),
     'pmwd_kick_drift_adj': (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _i, _vp]),
 }

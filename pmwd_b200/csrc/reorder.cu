@@ -344,3 +344,48 @@ extern "C" int pmwd_transpose_ce(void* stream, int mode, int nranks, int rank, i
   }
   return PMWD_OK;
 }
+
+
+// Generic form used by the chunk-pipelined slab FFT (pmwd_b200/dist.py): to every rank q one strided
+// 2-D copy of `height` rows of `width` bytes,
+//   src + q * src_peer_stride (row pitch spitch)  ->  peer_ptrs[q] + dst_off (row pitch dpitch),
+// on the copy engines, spread over `nstreams` internal streams forked from / joined into `stream`.
+extern "C" int pmwd_peer_copy2d(void* stream, int nranks, int rank, size_t width, size_t height, const void* src,
+                                size_t src_peer_stride, size_t spitch, const uint64_t* peer_ptrs, size_t dst_off,
+                                size_t dpitch, int nstreams) {
+  PMWD_REQUIRE(src && peer_ptrs, "null buffer");
+  PMWD_REQUIRE(nranks >= 1 && nranks <= 8 && rank >= 0 && rank < nranks, "bad rank / world size");
+  PMWD_REQUIRE(width > 0 && height > 0 && spitch >= width && dpitch >= width, "bad sizes");
+  if (nstreams < 1) nstreams = 1;
+  if (nstreams > 4) nstreams = 4;
+  int rc = pmwd::ce_init();
+  if (rc) return rc;
+  cudaStream_t st = pmwd::as_stream(stream);
+  pmwd::StageTimer timer(pmwd::ST_OTHER, st);
+  PMWD_CUDA_TRY(cudaEventRecord(pmwd::g_ce.fork, st));
+  for (int i = 0; i < nstreams; ++i) PMWD_CUDA_TRY(cudaStreamWaitEvent(pmwd::g_ce.s[i], pmwd::g_ce.fork, 0));
+  // optionally split every peer's rows over several streams (= copy engines); measured at N = 2
+  // (profiles/r02_slab_ab_n2.txt): no gain, one engine already reaches the ~600 GB/s the pair sustains
+  static const int split_env = [] { const char* e = getenv("PMWD_P2P_CE_SPLIT"); return e ? atoi(e) : 0; }();
+  int nsplit = split_env > 0 ? split_env : 1;
+  if ((size_t)nsplit > height) nsplit = (int)height;
+  if (nsplit < 1) nsplit = 1;
+  int job = 0;
+  for (int k = 0; k < nranks; ++k) {
+    const int q = (rank + 1 + k) % nranks;                       // own block last
+    char* d8 = reinterpret_cast<char*>(peer_ptrs[q]);
+    PMWD_REQUIRE(d8 != nullptr, "null peer pointer");
+    for (int part = 0; part < nsplit; ++part, ++job) {
+      const size_t r0 = height * part / nsplit, r1 = height * (part + 1) / nsplit;
+      if (r1 == r0) continue;
+      PMWD_CUDA_TRY(cudaMemcpy2DAsync(d8 + dst_off + r0 * dpitch, dpitch,
+                                      (const char*)src + (size_t)q * src_peer_stride + r0 * spitch, spitch, width,
+                                      r1 - r0, cudaMemcpyDeviceToDevice, pmwd::g_ce.s[job % nstreams]));
+    }
+  }
+  for (int i = 0; i < nstreams; ++i) {
+    PMWD_CUDA_TRY(cudaEventRecord(pmwd::g_ce.join[i], pmwd::g_ce.s[i]));
+    PMWD_CUDA_TRY(cudaStreamWaitEvent(st, pmwd::g_ce.join[i], 0));
+  }
+  return PMWD_OK;
+}

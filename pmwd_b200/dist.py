@@ -71,6 +71,37 @@ class _Timers:
 TIMERS = _Timers()
 
 
+class _Trace:
+    """Optional event trace of one pipelined force (PMWD_TRACE=1): (label, stream) timestamps relative to
+    the first mark, printed by rank 0 -- the poor man's timeline (no nsys in this image)."""
+
+    def __init__(self):
+        self.marks = []
+
+    @property
+    def on(self):
+        return os.environ.get('PMWD_TRACE') == '1'
+
+    def mark(self, label, stream=None):
+        if not self.on:
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(stream if stream is not None else torch.cuda.current_stream())
+        self.marks.append((label, ev))
+
+    def dump(self, rank):
+        if not self.marks:
+            return
+        torch.cuda.synchronize()
+        t0 = self.marks[0][1]
+        if rank == 0:
+            print('   '.join(f'{lab}@{t0.elapsed_time(ev):.2f}' for lab, ev in self.marks), flush=True)
+        self.marks = []
+
+
+TRACE = _Trace()
+
+
 class SlabComm:
     """Geometry and collectives of one rank of the slab decomposition."""
 
@@ -397,6 +428,13 @@ class SlabForce:
             rho = comm.halo_reduce(ext1, h)
         fused = bool(lib.pmwd_xpass_supported(Mx)) and os.environ.get('PMWD_XPASS', '1') != '0'
         p2p = fused and disp.is_cuda and comm.setup_p2p(dev)
+        npipe = int(os.environ.get('PMWD_PIPE', '1'))
+        if p2p and npipe > 1 and os.environ.get('PMWD_P2P_CE', '1') != '0' and comm.mx % npipe == 0 \
+                and comm.my % npipe == 0 and ((comm.my // npipe) * (Mz // 2 + 1)) % 2 == 0:
+            self._spectral_pipelined(rho, ext3, h, Om, npipe)
+            with TIMERS('halo'):
+                comm.halo_fill(ext3, h)
+            return desc, ext3, val
         if p2p:
             comm.p2p_barrier()                      # peers are done reading their receive buffers
             spec = comm.p2p_forward(rho, 0)
@@ -450,6 +488,164 @@ class SlabForce:
             comm.halo_fill(ext3, h)
         return desc, ext3, val
 
+    def _spectral_pipelined(self, rho, ext3, h, Om, npipe):
+        """rho ``[mx][My][Mz]`` -> the three force meshes in ``ext3[:, h:h+mx]``, with the slab-FFT
+        transposes (copy engines, side stream) hidden under the transforms: the 2-D R2C runs on
+        ``npipe`` chunks of x planes, each chunk's rows leaving for the peers while the next chunk
+        is transformed; the x-pass runs on ``npipe`` y-parts of the y-slab, each part's three
+        spectra leaving while the next part is computed; component i's 2-D C2R starts as soon as
+        its last part has landed everywhere."""
+        conf, comm = self.conf, self.comm
+        lib = _lib.lib()
+        dev = rho.device
+        Mx, My, Mz = conf.mesh_shape
+        P, rank, mx, my = comm.size, comm.rank, comm.mx, comm.my
+        nzc = Mz // 2 + 1
+        myh, mxc = my // npipe, mx // npipe
+        run_h = myh * nzc * 8                       # bytes of one (x plane, y-part) run
+        main = torch.cuda.current_stream(dev)
+        side = self._side_stream(dev)
+        ns = int(os.environ.get('PMWD_P2P_CE_STREAMS', '4'))
+        slot_ptrs = [comm._p2p[k][2] for k in range(4)]
+        scale = float(np.float32(1.5 * Om / conf.mesh_size))
+
+        def copy(src_ptr, width, height, src_peer_stride, spitch, slot, dst_off, dpitch):
+            _lib.check(lib.pmwd_peer_copy2d(_lib.stream_ptr(dev), P, rank, width, height, C.c_void_p(src_ptr),
+                                            src_peer_stride, spitch, slot_ptrs[slot], dst_off, dpitch, ns),
+                       'pmwd_peer_copy2d')
+
+        TRACE.mark('start', main)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            comm.p2p_barrier()                      # peers are done with all their receive buffers
+            TRACE.mark('bar0', side)
+        # ---- forward: R2C per x-chunk (main), rows to the peers' y-part buffers (side)
+        keep = []
+        for c in range(npipe):
+            with TIMERS('fft2d_r2c'):
+                s_c = comm._rfft2(rho[c * mxc:(c + 1) * mxc])
+            ev = torch.cuda.Event(); ev.record(main)
+            TRACE.mark(f'r2c{c}', main)
+            keep.append(s_c)
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                for hh in range(npipe):
+                    copy(s_c.data_ptr() + hh * run_h, run_h, mxc, my * nzc * 8, My * nzc * 8, 0,
+                         hh * Mx * run_h + (rank * mx + c * mxc) * run_h, run_h)
+                TRACE.mark(f'T{c}', side)
+            s_c.record_stream(side)
+        with torch.cuda.stream(side):
+            comm.p2p_barrier()                      # every rank's rows have landed
+            ev_fwd = torch.cuda.Event(); ev_fwd.record(side)
+            TRACE.mark('bar1', side)
+        main.wait_event(ev_fwd)
+        keep = None
+        # ---- x-pass per y-part (main); its three spectra to the owners of the x planes (side)
+        recv0 = comm._p2p[0][0]
+        g = [[torch.empty((Mx, myh, nzc), dtype=torch.complex64, device=dev) for _ in range(3)] for _ in range(npipe)]
+        evx = []
+        for hh in range(npipe):
+            n = Mx * myh * nzc
+            spec_h = torch.view_as_complex(recv0[2 * hh * n:2 * (hh + 1) * n].view(n, 2)).view(Mx, myh, nzc)
+            arr = (C.c_void_p * 3)(*[t.data_ptr() for t in g[hh]])
+            with TIMERS('kspace'):
+                _lib.check(lib.pmwd_xpass_force(_lib.stream_ptr(dev), _lib.shape_arr(conf.mesh_shape), comm.y0 + hh * myh,
+                                                myh, float(conf.cell_size), scale, _lib.ptr(spec_h), arr),
+                           'pmwd_xpass_force')
+            ev = torch.cuda.Event(); ev.record(main)
+            TRACE.mark(f'xp{hh}', main)
+            evx.append(ev)
+        landed = []
+        with torch.cuda.stream(side):
+            # component by component, so that the first 2-D C2R can start as early as possible
+            for i in range(3):
+                for hh in range(npipe):
+                    if i == 0:
+                        side.wait_event(evx[hh])
+                    copy(g[hh][i].data_ptr(), run_h, mx, mx * run_h, run_h, 1 + i,
+                         (rank * my + hh * myh) * nzc * 8, My * nzc * 8)
+                comm.p2p_barrier()                  # component i has landed everywhere
+                ev = torch.cuda.Event(); ev.record(side)
+                TRACE.mark(f'L{i}', side)
+                landed.append(ev)
+        for part in g:
+            for t in part:
+                t.record_stream(side)
+        for i in range(3):
+            main.wait_event(landed[i])
+            with TIMERS('fft2d_c2r'):
+                comm._irfft2(comm._p2p_view(1 + i, (mx, My, nzc)), My, Mz, out=ext3[i, h:h + mx])
+            TRACE.mark(f'c2r{i}', main)
+        TRACE.dump(rank)
+
+    def _spectral_adj_pipelined(self, Vs, rc, h, Om, npipe):
+        """The mesh part of ``force_adj``: the three cotangent meshes ``Vs[i]`` ``[mx][My][Mz]`` -> rho_cot in
+        ``rc[h:h+mx]``.  Component i's rows leave for the peers (copy engines, side stream) while component
+        i+1 is transformed; the x-pass runs on ``npipe`` y-parts whose output leaves while the next part is
+        computed."""
+        conf, comm = self.conf, self.comm
+        lib = _lib.lib()
+        dev = rc.device
+        Mx, My, Mz = conf.mesh_shape
+        P, rank, mx, my = comm.size, comm.rank, comm.mx, comm.my
+        nzc = Mz // 2 + 1
+        myh = my // npipe
+        run_h = myh * nzc * 8
+        main = torch.cuda.current_stream(dev)
+        side = self._side_stream(dev)
+        ns = int(os.environ.get('PMWD_P2P_CE_STREAMS', '4'))
+        slot_ptrs = [comm._p2p[k][2] for k in range(4)]
+        scale = float(np.float32(1.5 * Om / conf.mesh_size))
+
+        def copy(src_ptr, width, height, src_peer_stride, spitch, slot, dst_off, dpitch):
+            _lib.check(lib.pmwd_peer_copy2d(_lib.stream_ptr(dev), P, rank, width, height, C.c_void_p(src_ptr),
+                                            src_peer_stride, spitch, slot_ptrs[slot], dst_off, dpitch, ns),
+                       'pmwd_peer_copy2d')
+
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            comm.p2p_barrier()
+        for i in range(3):
+            with TIMERS('fft2d_r2c'):
+                s_i = comm._rfft2(Vs[i])
+            ev = torch.cuda.Event(); ev.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                for hh in range(npipe):
+                    copy(s_i.data_ptr() + hh * run_h, run_h, mx, my * nzc * 8, My * nzc * 8, i,
+                         hh * Mx * run_h + rank * mx * run_h, run_h)
+            s_i.record_stream(side)
+            del s_i
+        with torch.cuda.stream(side):
+            comm.p2p_barrier()
+            ev_fwd = torch.cuda.Event(); ev_fwd.record(side)
+        main.wait_event(ev_fwd)
+        n = Mx * myh * nzc
+        outs, evx = [], []
+        for hh in range(npipe):
+            parts = [torch.view_as_complex(comm._p2p[i][0][2 * hh * n:2 * (hh + 1) * n].view(n, 2)).view(Mx, myh, nzc)
+                     for i in range(3)]
+            out_h = torch.empty((Mx, myh, nzc), dtype=torch.complex64, device=dev)
+            arr = (C.c_void_p * 3)(*[t.data_ptr() for t in parts])
+            with TIMERS('kspace'):
+                _lib.check(lib.pmwd_xpass_force_adj(_lib.stream_ptr(dev), _lib.shape_arr(conf.mesh_shape),
+                                                    comm.y0 + hh * myh, myh, float(conf.cell_size), scale, arr,
+                                                    _lib.ptr(out_h)), 'pmwd_xpass_force_adj')
+            ev = torch.cuda.Event(); ev.record(main)
+            outs.append(out_h); evx.append(ev)
+        with torch.cuda.stream(side):
+            for hh in range(npipe):
+                side.wait_event(evx[hh])
+                copy(outs[hh].data_ptr(), run_h, mx, mx * run_h, run_h, 3, (rank * my + hh * myh) * nzc * 8,
+                     My * nzc * 8)
+            comm.p2p_barrier()
+            landed = torch.cuda.Event(); landed.record(side)
+        for t in outs:
+            t.record_stream(side)
+        main.wait_event(landed)
+        with TIMERS('fft2d_c2r'):
+            comm._irfft2(comm._p2p_view(3, (mx, My, nzc)), My, Mz, out=rc[h:h + mx])
+
     def force(self, pmid, disp, Om, acc, kick_vel=None, kick_factor=0.0, next_kd=None):
         """``next_kd = (K1_next, D_next)``: also apply the next step's leading half-kick and
         drift in the gather pass (pipelined KDK, cf. ``pmwd_force_kdk``)."""
@@ -485,6 +681,18 @@ class SlabForce:
         Vs = comm.halo_reduce(V, h)
         fused = bool(lib.pmwd_xpass_supported(Mx)) and os.environ.get('PMWD_XPASS', '1') != '0'
         p2p = fused and comm.setup_p2p(dev)
+        npipe = int(os.environ.get('PMWD_PIPE', '1'))
+        if p2p and npipe > 1 and os.environ.get('PMWD_P2P_CE', '1') != '0' and comm.my % npipe == 0 \
+                and ((comm.my // npipe) * (Mz // 2 + 1)) % 2 == 0:
+            rc = torch.empty_like(F[0])
+            self._spectral_adj_pipelined(Vs, rc, h, Om, npipe)
+            del V, Vs
+            with TIMERS('halo'):
+                comm.halo_fill(rc, h)
+            _lib.check(lib.pmwd_force_adj_gather(st, C.byref(desc), _lib.ptr(pmid), _lib.ptr(disp), _lib.ptr(F[0]),
+                                                 _lib.ptr(F[1]), _lib.ptr(F[2]), _lib.ptr(rc), _lib.ptr(pi), val,
+                                                 _lib.ptr(alpha)), 'pmwd_force_adj_gather')
+            return
         if p2p:
             comm.p2p_barrier()
             S = [comm.p2p_forward(Vs[i].contiguous(), i) for i in range(3)]

@@ -15,21 +15,22 @@ def _free_port():
     s = socket.socket(); s.bind(('127.0.0.1', 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-@pytest.mark.timeout(900)
+@pytest.mark.timeout(450)
 @pytest.mark.parametrize('world', [2, 4, 8])
-@pytest.mark.parametrize('ce', ['1', '0'], ids=['copy_engine', 'store_kernel'])
+@pytest.mark.parametrize('ce', ['1', '0', 'pipe2'], ids=['copy_engine', 'store_kernel', 'pipelined'])
 def test_slab_matches_single_gpu(world, ce):
     """LPT, force, force_adj, N-body and the adjoint on `world` slabs against the single-GPU path;
-    slab-FFT transposes on the copy engines (default) and with the P2P-store kernel."""
+    slab-FFT transposes on the copy engines (default), with the P2P-store kernel, and chunk-pipelined."""
     n = torch.cuda.device_count()
     if n < world:
         pytest.skip(f'needs >= {world} GPUs')
-    if ce == '0' and world != 2:
-        pytest.skip('the store-kernel transposes are exercised at world 2 only')
+    if ce != '1' and world != 2:
+        pytest.skip('the store-kernel and pipelined transposes are exercised at world 2 only')
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(world),
            '--master-addr', '127.0.0.1', '--master-port', str(_free_port()),
            os.path.join(ROOT, 'tests', 'dist_gpu_worker.py')]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=850, env=dict(os.environ, PMWD_P2P_CE=ce))
+    env = dict(os.environ, PMWD_P2P_CE='0' if ce == '0' else '1', PMWD_PIPE='2' if ce == 'pipe2' else '1')
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=420, env=env)
     errs = [l for l in (r.stdout + r.stderr).splitlines() if 'rank' in l and ('Error' in l or 'assert' in l)]
     assert r.returncode == 0, '\n'.join(errs[:20]) + r.stderr[-1500:]
     assert r.stdout.count(' ok: ') == 2 * world
