@@ -344,6 +344,13 @@ int pmwd_kick_drift(void* stream, int64_t n, float* disp, float* vel, const floa
 int pmwd_kick_drift_adj(void* stream, int64_t n, float* disp, float* vel, const float* acc,
                         float* xi, float* pi, const float* alpha, float K, float D,
                         int do_kick, int do_drift, double* sums);
+/* kick_adj(K0), then kick_adj(K) + drift_adj(D) in one pass (the trailing half-kick of one adjoint step
+ * and the leading half-kick + drift of the next, between which acc and alpha do not change); float32
+ * sequence identical to two pmwd_kick_drift_adj calls.  sums_pre[0] and sums[0] += sum(pi . acc),
+ * sums[1] += sum(xi . vel). */
+int pmwd_kick_kick_drift_adj(void* stream, int64_t n, float* disp, float* vel, const float* acc,
+                             float* xi, float* pi, const float* alpha, float K0, float K, float D,
+                             double* sums_pre, double* sums);
 
 #ifdef __cplusplus
 }

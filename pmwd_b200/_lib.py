@@ -121,6 +121,7 @@ _SIGNATURES = {
     'pmwd_peer_copy2d': (_i, [_vp, _i, _i, _sz, _sz, _vp, _sz, _sz, C.POINTER(C.c_uint64), _sz, _sz, _i]),
     'pmwd_kick_drift': (_i, [_vp, _i64, _vp, _vp, _vp, _f, _f, _i, _i]),
     'pmwd_kick_drift_adj': (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _i, _vp]),
+    'pmwd_kick_kick_drift_adj': (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _vp, _vp]),
 }
 
 EXPORTS = tuple(sorted(_SIGNATURES))

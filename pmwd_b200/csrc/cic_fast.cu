@@ -223,7 +223,8 @@ __global__ void __launch_bounds__(256)
 force_adj_gather_kernel(FastParams P, const short* __restrict__ pmid, const float* __restrict__ disp,
                         const float* __restrict__ f0, const float* __restrict__ f1,
                         const float* __restrict__ f2, const float* __restrict__ rho_cot,
-                        const float* __restrict__ pi, float val, float* __restrict__ alpha) {
+                        const float* __restrict__ pi, float val, float* __restrict__ alpha,
+                        float* __restrict__ acc) {
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P.n;
        p += (int64_t)gridDim.x * blockDim.x) {
     Stencil3G<true> s;
@@ -233,6 +234,7 @@ force_adj_gather_kernel(FastParams P, const short* __restrict__ pmid, const floa
     localize_x(P, s.ix);
     const float p0 = pi[3 * p + 0], p1 = pi[3 * p + 1], p2 = pi[3 * p + 2];
     float d[4][3];
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;     // acc = gather3 of the same force values (same arithmetic as gather3_kernel)
 #pragma unroll
     for (int q = 0; q < 4; ++q) d[q][0] = d[q][1] = d[q][2] = 0.f;
 #pragma unroll
@@ -244,10 +246,17 @@ force_adj_gather_kernel(FastParams P, const short* __restrict__ pmid, const floa
       float gz = __fmul_rn(s.sz[bz], __fmul_rn(s.wx[bx], s.wy[by]));
       const bool ok = s.ix[bx] >= 0;
       int64_t lin = ((int64_t)(ok ? s.ix[bx] : 0) * P.ny + s.iy[by]) * P.nz + s.iz[bz];
+      const float F0 = ok ? __ldg(f0 + lin) : 0.f, F1 = ok ? __ldg(f1 + lin) : 0.f, F2 = ok ? __ldg(f2 + lin) : 0.f;
+      if (acc) {
+        const float w = __fmul_rn(__fmul_rn(s.wx[bx], s.wy[by]), s.wz[bz]);
+        a0 = __fadd_rn(a0, __fmul_rn(F0, w));
+        a1 = __fadd_rn(a1, __fmul_rn(F1, w));
+        a2 = __fadd_rn(a2, __fmul_rn(F2, w));
+      }
       float t[4];
-      t[0] = __fmul_rn(p0, ok ? __ldg(f0 + lin) : 0.f);
-      t[1] = __fmul_rn(p1, ok ? __ldg(f1 + lin) : 0.f);
-      t[2] = __fmul_rn(p2, ok ? __ldg(f2 + lin) : 0.f);
+      t[0] = __fmul_rn(p0, F0);
+      t[1] = __fmul_rn(p1, F1);
+      t[2] = __fmul_rn(p2, F2);
       t[3] = __fmul_rn(ok ? __ldg(rho_cot + lin) : 0.f, val);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -263,6 +272,11 @@ force_adj_gather_kernel(FastParams P, const short* __restrict__ pmid, const floa
       a = __fadd_rn(a, __fdiv_rn(d[2][j], P.cell));
       a = __fadd_rn(a, __fdiv_rn(d[3][j], P.cell));
       alpha[3 * p + j] = a;
+    }
+    if (acc) {
+      acc[3 * p + 0] = a0;
+      acc[3 * p + 1] = a1;
+      acc[3 * p + 2] = a2;
     }
   }
 }
@@ -351,7 +365,7 @@ int gather3_fast(cudaStream_t st, const pmwd_cic_desc* d, const void* pmid, cons
 
 int force_adj_gather(cudaStream_t st, const pmwd_cic_desc* d, const void* pmid, const float* disp,
                      const float* f0, const float* f1, const float* f2, const float* rho_cot,
-                     const float* pi, float val, float* alpha) {
+                     const float* pi, float val, float* alpha, float* acc) {
   FastParams P;
   int rc = fast_params(d, &P);
   if (rc) return rc;
@@ -359,7 +373,7 @@ int force_adj_gather(cudaStream_t st, const pmwd_cic_desc* d, const void* pmid, 
   const int block = 256;
   int grid = grid_for(P.n, block, 8);
   force_adj_gather_kernel<<<grid, block, 0, st>>>(P, (const short*)pmid, disp, f0, f1, f2, rho_cot,
-                                                  pi, val, alpha);
+                                                  pi, val, alpha, acc);
   PMWD_LAUNCH_CHECK();
   return PMWD_OK;
 }

@@ -34,7 +34,7 @@ int gather3_fast(cudaStream_t st, const pmwd_cic_desc* d, const void* pmid, cons
                  const float* next_kd, float* disp_rw);
 int force_adj_gather(cudaStream_t st, const pmwd_cic_desc* d, const void* pmid, const float* disp,
                      const float* f0, const float* f1, const float* f2, const float* rho_cot,
-                     const float* pi, float val, float* alpha);
+                     const float* pi, float val, float* alpha, float* acc);
 // scatter_sweep.cu
 bool sweep_usable(const pmwd_cic_desc* d, const pmwd_sweep* sw);
 int scatter_sweep(cudaStream_t st, const pmwd_cic_desc* d, const pmwd_sweep* sw, const void* pmid,
@@ -248,7 +248,7 @@ extern "C" int pmwd_force_adj_gather(void* stream, const pmwd_cic_desc* d, const
   PMWD_REQUIRE(d && f0 && f1 && f2 && rho_cot && (d->ptcl_num == 0 || (pmid && disp && pi && alpha)),
                "null buffer");
   StageTimer t(ST_GATHER_ADJ, as_stream(stream));
-  return force_adj_gather(as_stream(stream), d, pmid, disp, f0, f1, f2, rho_cot, pi, val, alpha);
+  return force_adj_gather(as_stream(stream), d, pmid, disp, f0, f1, f2, rho_cot, pi, val, alpha, nullptr);
 }
 
 extern "C" size_t pmwd_force_workspace_bytes(const pmwd_cic_desc* d, int adjoint, int mode) {
@@ -332,12 +332,9 @@ extern "C" int pmwd_force_adj(pmwd_ctx* ctx, void* stream, const pmwd_cic_desc* 
   float val = 0.f;
   rc = force_forward(ctx, st, d, pmid, disp, Omega_m, mode, ws, L, &val, sweep);
   if (rc) return rc;
+  // acc = gather3(F) is evaluated in the weight-gradient gather at the end (same force values, same
+  // float32 arithmetic): one pass over the particles and the three force meshes instead of two
   float* F[3] = {(float*)(ws + L.rho_f0), (float*)(ws + L.f1), (float*)(ws + L.f2)};
-  {
-    StageTimer t(ST_GATHER, st);
-    rc = gather3_fast(st, d, pmid, disp, F[0], F[1], F[2], acc, nullptr, 0.f, nullptr, nullptr);
-  }
-  if (rc) return rc;
 
   // V_i = scatter(pi_i): the mesh_cot of _gather_bwd (gather.py:113), SoA, in the (now free)
   // gradient-spectrum buffers
@@ -382,5 +379,5 @@ extern "C" int pmwd_force_adj(pmwd_ctx* ctx, void* stream, const pmwd_cic_desc* 
   }
   if (rc) return rc;
   StageTimer t(ST_GATHER_ADJ, st);
-  return force_adj_gather(st, d, pmid, disp, F[0], F[1], F[2], rho_cot, pi, val, alpha);
+  return force_adj_gather(st, d, pmid, disp, F[0], F[1], F[2], rho_cot, pi, val, alpha, acc);
 }

@@ -54,12 +54,14 @@ __device__ __forceinline__ double dot4(float4 a, float4 b) {
   return (double)a.x * b.x + (double)a.y * b.y + (double)a.z * b.z + (double)a.w * b.w;
 }
 
-template <bool KICK, bool DRIFT>
+// PRE: a kick_adj with factor K0 (the previous step's trailing half-kick, same acc / alpha) is applied
+// first in the same pass; its sum(pi . acc) equals this kick's and is added to sums_pre[0] as well.
+template <bool KICK, bool DRIFT, bool PRE = false>
 __global__ void __launch_bounds__(256)
 kick_drift_adj_kernel(int64_t n, float* __restrict__ disp, float* __restrict__ vel,
                       const float* __restrict__ acc, float* __restrict__ xi,
                       float* __restrict__ pi, const float* __restrict__ alpha, float K, float D,
-                      double* __restrict__ sums) {
+                      double* __restrict__ sums, float K0 = 0.f, double* __restrict__ sums_pre = nullptr) {
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t n4 = n >> 2;
@@ -70,8 +72,13 @@ kick_drift_adj_kernel(int64_t n, float* __restrict__ disp, float* __restrict__ v
     float4 p = reinterpret_cast<float4*>(pi)[i];
     if (KICK) {
       float4 a = reinterpret_cast<const float4*>(acc)[i];
+      const float4 al = reinterpret_cast<const float4*>(alpha)[i];
+      if (PRE) {
+        v = axpy4(v, a, K0);
+        x = axmy4(x, al, K0);
+      }
       v = axpy4(v, a, K);                                              // nbody.py:87
-      x = axmy4(x, reinterpret_cast<const float4*>(alpha)[i], K);      // nbody.py:91
+      x = axmy4(x, al, K);                                             // nbody.py:91
       s_pa += dot4(p, a);                                              // nbody.py:95
       reinterpret_cast<float4*>(vel)[i] = v;
       reinterpret_cast<float4*>(xi)[i] = x;
@@ -88,6 +95,10 @@ kick_drift_adj_kernel(int64_t n, float* __restrict__ disp, float* __restrict__ v
     float v = vel[i], x = xi[i], p = pi[i];
     if (KICK) {
       float a = acc[i];
+      if (PRE) {
+        v = __fadd_rn(v, __fmul_rn(a, K0));
+        x = __fsub_rn(x, __fmul_rn(alpha[i], K0));
+      }
       v = __fadd_rn(v, __fmul_rn(a, K));
       x = __fsub_rn(x, __fmul_rn(alpha[i], K));
       s_pa += (double)p * a;
@@ -120,6 +131,7 @@ kick_drift_adj_kernel(int64_t n, float* __restrict__ disp, float* __restrict__ v
     }
     if (l == 0) {
       if (KICK) atomicAdd(sums + 0, a);
+      if (PRE) atomicAdd(sums_pre + 0, a);
       if (DRIFT) atomicAdd(sums + 1, b);
     }
   }
@@ -168,6 +180,27 @@ extern "C" int pmwd_kick_drift_adj(void* stream, int64_t n, float* disp, float* 
     kick_drift_adj_kernel<true, false><<<grid, 256, 0, st>>>(n, disp, vel, acc, xi, pi, alpha, K, D, sums);
   else
     kick_drift_adj_kernel<false, true><<<grid, 256, 0, st>>>(n, disp, vel, acc, xi, pi, alpha, K, D, sums);
+  PMWD_LAUNCH_CHECK();
+  return PMWD_OK;
+}
+
+// Two consecutive adjoint updates in one pass: kick_adj(K0) [the trailing half-kick of one step], then
+// kick_adj(K) + drift_adj(D) [the leading half-kick and drift of the next step, pmwd/nbody.py:143-162];
+// same float32 operation sequence as the two separate calls.  sums_pre[0] += sum(pi . acc) (of the first
+// kick), sums[0] += the same sum (second kick), sums[1] += sum(xi . vel).
+extern "C" int pmwd_kick_kick_drift_adj(void* stream, int64_t n, float* disp, float* vel, const float* acc,
+                                        float* xi, float* pi, const float* alpha, float K0, float K, float D,
+                                        double* sums_pre, double* sums) {
+  PMWD_REQUIRE(n >= 0, "negative length");
+  PMWD_REQUIRE(disp && vel && xi && pi && acc && alpha && sums && sums_pre, "null buffer");
+  PMWD_REQUIRE(aligned16(disp) && aligned16(vel) && aligned16(acc) && aligned16(xi) &&
+               aligned16(pi) && aligned16(alpha), "arrays must be 16-byte aligned");
+  if (n == 0) return PMWD_OK;
+  cudaStream_t st = as_stream(stream);
+  StageTimer timer(ST_KICK_DRIFT_ADJ, st);
+  int grid = grid_for((n + 3) / 4, 256, 8);
+  kick_drift_adj_kernel<true, true, true><<<grid, 256, 0, st>>>(n, disp, vel, acc, xi, pi, alpha, K, D, sums, K0,
+                                                               sums_pre);
   PMWD_LAUNCH_CHECK();
   return PMWD_OK;
 }

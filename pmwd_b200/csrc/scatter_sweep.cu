@@ -29,6 +29,8 @@
 //    after this one (so that it can never race with the plain stores).
 //
 // Correctness never depends on how fresh the sort is; only the straggler fraction does.
+#include <stdlib.h>
+
 #include "cic.cuh"
 
 namespace pmwd {
@@ -47,7 +49,7 @@ struct SweepGeom {
   int ty, npencil;    // tile rows, ny / ty
   int bw, nband;      // tile cells along z (multiple of 4), nz / bw
   int lx, nseg;       // planes per x segment, ceil(nx_ext / lx)
-  int rs, ps;         // ring row stride (bw + 1) and plane size (ty + 1) * rs, in floats
+  int rs, ps;         // ring row stride (bw + 4: float4-aligned rows, halo column at bw) and plane size (ty + 1) * rs
   int nwarps;         // warps per CTA (each with its own ring)
 };
 
@@ -100,7 +102,7 @@ scatter_sweep_kernel(SweepGeom G, const short* __restrict__ pmid, const float* _
   extern __shared__ __align__(16) float smf[];
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* ring = smf + (size_t)warp * 4 * G.ps;          // [4][ty+1][bw+1], private to this warp
+  float* ring = smf + (size_t)warp * 4 * G.ps;          // [4][ty+1][bw+4], private to this warp
   uint32_t* sbuf = reinterpret_cast<uint32_t*>(smf + (size_t)G.nwarps * 4 * G.ps) + warp * 64;   // straggler staging
   int scount = 0;
   const int nitems = G.npencil * G.nband * G.nseg;
@@ -117,7 +119,7 @@ scatter_sweep_kernel(SweepGeom G, const short* __restrict__ pmid, const float* _
     const int xa = sgi * G.lx, xb = min(xa + G.lx, G.nx_ext);
     const int y0 = pencil * G.ty, z0 = band * G.bw;
     const uint2* tab = table + ((int64_t)pencil * G.nband + band) * G.nx_ext;
-    for (int i = lane; i < 4 * G.ps; i += 32) ring[i] = 0.f;
+    for (int i = lane; i < G.ps; i += 32) reinterpret_cast<float4*>(ring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncwarp();
 
     // ---- flush one ring plane of this warp to the mesh and clear it
@@ -137,8 +139,7 @@ scatter_sweep_kernel(SweepGeom G, const short* __restrict__ pmid, const float* _
         const int ntot = (G.ty + 1) * ngr;
         for (int i = lane; i < ntot; i += 32) {
           const int row = i / ngr, gq = i - row * ngr;
-          const float* sp = src + row * G.rs + 4 * gq;
-          const float4 v = make_float4(sp[0], sp[1], sp[2], sp[3]);
+          const float4 v = *reinterpret_cast<const float4*>(src + row * G.rs + 4 * gq);
           int gy = y0 + row;
           if (gy == G.ny) gy = 0;
           float* dst = mesh + ((int64_t)gpl * G.ny + gy) * G.nz + z0 + 4 * gq;
@@ -160,7 +161,7 @@ scatter_sweep_kernel(SweepGeom G, const short* __restrict__ pmid, const float* _
         }
       }
       __syncwarp();
-      for (int i = lane; i < G.ps; i += 32) src[i] = 0.f;
+      for (int i = lane; i < (G.ps >> 2); i += 32) reinterpret_cast<float4*>(src)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       __syncwarp();
     };
 
@@ -396,7 +397,7 @@ sweep_table_cover_kernel(int64_t nid, const uint2* __restrict__ table, unsigned 
 
 // ---------------------------------------------------------------------------------------------
 // per warp: the ring + 64 words of straggler staging
-static size_t sweep_ring_bytes(int ty, int bw) { return (size_t)4 * (ty + 1) * (bw + 1) * sizeof(float) + 256; }
+static size_t sweep_ring_bytes(int ty, int bw) { return (size_t)4 * (ty + 1) * (bw + 4) * sizeof(float) + 256; }
 
 // Fills G for (d, ty, bw, lx); returns false if the geometry is not supported by the sweep kernels.
 static bool sweep_geom(const pmwd_cic_desc* d, int ty, int bw, int lx, SweepGeom* G) {
@@ -415,7 +416,7 @@ static bool sweep_geom(const pmwd_cic_desc* d, int ty, int bw, int lx, SweepGeom
   G->bw = bw; G->nband = G->nz / bw;
   G->lx = lx < G->nx_ext ? lx : G->nx_ext;
   G->nseg = (G->nx_ext + G->lx - 1) / G->lx;
-  G->rs = bw + 1;
+  G->rs = bw + 4;
   G->ps = (ty + 1) * G->rs;
   if (d->ptcl_num >= ((int64_t)1 << 32)) return false;
   if ((int64_t)G->nx_ext * G->ny * G->nz > ((int64_t)1 << 32)) return false;     // 32-bit sort keys
@@ -441,6 +442,8 @@ extern "C" int pmwd_sweep_pick(const pmwd_cic_desc* d, int* ty_out, int* bw_out)
   for (int t = 16; t >= 2; --t) if (ny % t == 0) { ty = t; break; }
   for (int b = 32; b >= 4; b -= 4) if (nz % b == 0) { bw = b; break; }
   if (bw < 16) for (int b = 36; b <= 128; b += 4) if (nz % b == 0) { bw = b; break; }
+  { const char* e = getenv("PMWD_SWEEP_TY"); if (e && atoi(e) > 0 && ny % atoi(e) == 0) ty = atoi(e); }
+  { const char* e = getenv("PMWD_SWEEP_BW"); if (e && atoi(e) > 0 && nz % atoi(e) == 0 && atoi(e) % 4 == 0) bw = atoi(e); }
   if (!ty || !bw) return 0;
   SweepGeom G;
   if (!sweep_geom(d, ty, bw, 64, &G)) return 0;

@@ -322,6 +322,19 @@ def nbody_step(a_prev, a_next, ptcl, obsvbl, cosmo, conf):
 
 
 _host_streams = {}
+_pmid_resident = {}        # (host data_ptr, shape, version, device) -> device copy of a host pmid array
+
+
+def _resident_pmid(host_pmid, dev):
+    """pmid never changes during a run (``pmwd/particles.py:52-59``): a host pmid array that has been
+    uploaded before (same storage, same version counter) is not uploaded again."""
+    key = (host_pmid.data_ptr(), tuple(host_pmid.shape), host_pmid._version, str(dev))
+    t = _pmid_resident.get(key)
+    if t is None:
+        if len(_pmid_resident) >= 4:
+            _pmid_resident.clear()
+        t = _pmid_resident[key] = host_pmid.to(dev, non_blocking=True)
+    return t
 
 
 def nbody_step_host(a_prev, a_next, host, cosmo, conf, out=None):
@@ -329,7 +342,8 @@ def nbody_step_host(a_prev, a_next, host, cosmo, conf, out=None):
     dict map ``'pmid'`` (int16), ``'disp'``, ``'vel'``, ``'acc'`` (float32) to CPU tensors of
     shape ``(N, 3)``; ``out`` may supply the output buffers (``pmid`` is passed through).
 
-    Same arithmetic as ``nbody_step`` (``nbody.py:204-212``).  The copies are part of the call:
+    Same arithmetic as ``nbody_step`` (``nbody.py:204-212``).  The copies are part of the call
+    (``pmid``, which never changes, is uploaded once per host array and kept resident):
     the three dynamic arrays go up first, the leading half-kick + drift run as soon as they are
     there, and the new displacements -- final after the drift -- are copied back on a second
     stream WHILE the force is computed; velocities and accelerations follow the fused
@@ -352,7 +366,7 @@ def nbody_step_host(a_prev, a_next, host, cosmo, conf, out=None):
         acc = host['acc'].to(dev, non_blocking=True)
         vel = host['vel'].to(dev, non_blocking=True)
         disp = host['disp'].to(dev, non_blocking=True)
-        pmid = host['pmid'].to(dev, non_blocking=True)
+        pmid = _resident_pmid(host['pmid'], dev)
         p = Particles(conf, pmid, disp, vel=vel, acc=acc)
         default = tuple(tuple(x) for x in conf.symp_splits) == ((0, 0.5), (1, 0.5))
         if not (default and _fast_ok(p, conf)):
@@ -513,7 +527,9 @@ def nbody_adj(ptcl, ptcl_cot, obsvbl_cot, cosmo, conf, reverse=False, _slab=None
         sums = torch.zeros((len(pairs) * nsplit + 1, 2), dtype=torch.float64, device=dev)
         records = []   # (kind, slot, column, factor, grads)
 
-        def kd_adj(K, D, do_kick, do_drift, slot):
+        pending = []     # a trailing kick-only update waiting to share its pass with the next kick+drift
+
+        def _kd_call(K, D, do_kick, do_drift, slot):
             a = store.arrays
             with torch.cuda.device(dev):
                 _lib.check(lib.pmwd_kick_drift_adj(
@@ -522,7 +538,31 @@ def nbody_adj(ptcl, ptcl_cot, obsvbl_cot, cosmo, conf, reverse=False, _slab=None
                     int(do_kick), int(do_drift), C.c_void_p(sums[slot].data_ptr())),
                     'pmwd_kick_drift_adj')
 
+        def flush_pending():
+            if pending:
+                K0, slot0 = pending.pop()
+                _kd_call(K0, 0.0, True, False, slot0)
+
+        def kd_adj(K, D, do_kick, do_drift, slot):
+            if do_kick and not do_drift:
+                flush_pending()
+                pending.append((K, slot))      # acc / alpha stay as they are until the next force_adj
+                return
+            if pending and do_kick and do_drift:
+                K0, slot0 = pending.pop()
+                a = store.arrays
+                with torch.cuda.device(dev):
+                    _lib.check(lib.pmwd_kick_kick_drift_adj(
+                        _lib.stream_ptr(dev), n, _lib.ptr(a['disp']), _lib.ptr(a['vel']), _lib.ptr(a['acc']),
+                        _lib.ptr(a['xi']), _lib.ptr(a['pi']), _lib.ptr(a['alpha']), K0, K, D,
+                        C.c_void_p(sums[slot0].data_ptr()), C.c_void_p(sums[slot].data_ptr())),
+                        'pmwd_kick_kick_drift_adj')
+                return
+            flush_pending()
+            _kd_call(K, D, do_kick, do_drift, slot)
+
         def f_adj():
+            flush_pending()
             a = store.arrays
             if _slab is not None:
                 _slab.force_adj(a['pmid'], a['disp'], Om, a['pi'], a['acc'], a['alpha'])
@@ -561,6 +601,7 @@ def nbody_adj(ptcl, ptcl_cot, obsvbl_cot, cosmo, conf, reverse=False, _slab=None
                     a_acc = a_disp
             store.maybe_reorder()
 
+        flush_pending()
         if _slab is not None:
             _slab.comm.allreduce_sum_(sums)
         sums_h = sums.cpu()
