@@ -433,15 +433,17 @@ static bool sweep_geom(const pmwd_cic_desc* d, int ty, int bw, int lx, SweepGeom
 
 using namespace pmwd;
 
-// Tile shape for this mesh: ty = the largest divisor of ny up to 16, bw = a multiple of 4 dividing nz
-// (32 preferred).  Returns 1 and fills *ty, *bw, or 0 if the sweep kernels do not support the mesh.
+// Tile shape for this mesh: ty = the largest divisor of ny up to 8, bw = a multiple of 4 dividing nz
+// (64 preferred).  Returns 1 and fills *ty, *bw, or 0 if the sweep kernels do not support the mesh.
 extern "C" int pmwd_sweep_pick(const pmwd_cic_desc* d, int* ty_out, int* bw_out) {
   if (!d || d->dim != 3) return 0;
   const int ny = d->wrap_shape[1], nz = d->wrap_shape[2];
   int ty = 0, bw = 0;
-  for (int t = 16; t >= 2; --t) if (ny % t == 0) { ty = t; break; }
-  for (int b = 32; b >= 4; b -= 4) if (nz % b == 0) { bw = b; break; }
-  if (bw < 16) for (int b = 36; b <= 128; b += 4) if (nz % b == 0) { bw = b; break; }
+  // measured at 512^3 / 1024^3 over the whole 63-step run (profiles/r02_sweep_tiles.txt): 8 x 64 tiles
+  // 33.85 ms/step, 16 x 32: 34.42; 8 x 32 and 16 x 64 are slower (more RED rows / fewer warps per SM)
+  for (int t = 8; t >= 2; --t) if (ny % t == 0) { ty = t; break; }
+  for (int b = 64; b >= 4; b -= 4) if (nz % b == 0) { bw = b; break; }
+  if (bw < 16) for (int b = 68; b <= 128; b += 4) if (nz % b == 0) { bw = b; break; }
   { const char* e = getenv("PMWD_SWEEP_TY"); if (e && atoi(e) > 0 && ny % atoi(e) == 0) ty = atoi(e); }
   { const char* e = getenv("PMWD_SWEEP_BW"); if (e && atoi(e) > 0 && nz % atoi(e) == 0 && atoi(e) % 4 == 0) bw = atoi(e); }
   if (!ty || !bw) return 0;
