@@ -313,6 +313,11 @@ int pmwd_permute_rows(void* stream, int64_t n, const uint32_t* perm, int narr,
                       const void* const* src, void* const* dst, const int32_t* row_bytes,
                       int inverse);
 
+/* Slab bookkeeping in one pass (int16 pmid, 3-D): owner[p] = rank whose x-slab holds particle p's base plane
+ * (may be NULL), *need = halo planes the slab [x0, x0 + mx) needs for these particles (device int32, reset here). */
+int pmwd_slab_owner(void* stream, int64_t n, const void* pmid, const float* disp, double cell_size,
+                    int Mx, int nranks, int x0, int mx, uint8_t* owner, int32_t* need);
+
 /* Slab-FFT transpose as one kernel over NVLink peer memory: every rank stores the rows of its
  * local array straight into the peers' receive buffers (peer-mapped device pointers, one per
  * rank, e.g. from torch symmetric memory) at their final position.

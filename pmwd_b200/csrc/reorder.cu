@@ -389,3 +389,45 @@ extern "C" int pmwd_peer_copy2d(void* stream, int nranks, int rank, size_t width
   }
   return PMWD_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// Slab bookkeeping in one pass over the particles: the rank that owns each particle's base plane
+// (Eulerian ownership, pmwd_b200/migrate.py) and how many halo planes the slab [x0, x0 + mx) needs for
+// the particles it holds (max over particles, atomicMax into *need).  Same float32 cell arithmetic as
+// the CIC kernels (pm_util.py:129-136).
+namespace pmwd {
+__global__ void __launch_bounds__(256)
+slab_owner_kernel(int64_t n, const short* __restrict__ pmid, const float* __restrict__ disp, float cell, int Mx,
+                  int planes_per_rank, int x0, int mx, uint8_t* __restrict__ owner, int* __restrict__ need) {
+  int local = 0;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    const float t = __fdiv_rn(disp[3 * p], cell);
+    const int plane = wrap_index((int)pmid[3 * p] + (int)floorf(t), Mx);
+    if (owner) owner[p] = (uint8_t)(plane / planes_per_rank);
+    int d = plane - x0;
+    if (d < 0) d += Mx;
+    const int right = d + 2 - mx;
+    const int nd = d < mx ? (right > 0 ? right : 0) : (right < Mx - d ? right : Mx - d);
+    local = nd > local ? nd : local;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const int t = __shfl_xor_sync(0xffffffffu, local, o);
+    local = t > local ? t : local;
+  }
+  if ((threadIdx.x & 31) == 0 && local > 0) atomicMax(need, local);
+}
+}  // namespace pmwd
+
+extern "C" int pmwd_slab_owner(void* stream, int64_t n, const void* pmid, const float* disp, double cell_size,
+                               int Mx, int nranks, int x0, int mx, uint8_t* owner, int32_t* need) {
+  PMWD_REQUIRE(need && (n == 0 || (pmid && disp)), "null buffer");
+  PMWD_REQUIRE(Mx > 0 && nranks >= 1 && nranks <= 255 && Mx % nranks == 0 && mx > 0, "bad slab geometry");
+  cudaStream_t st = pmwd::as_stream(stream);
+  PMWD_CUDA_TRY(cudaMemsetAsync(need, 0, sizeof(int32_t), st));
+  if (n == 0) return PMWD_OK;
+  pmwd::slab_owner_kernel<<<pmwd::grid_for(n, 256, 8), 256, 0, st>>>(n, (const short*)pmid, disp, (float)cell_size, Mx,
+                                                                    Mx / nranks, x0, mx, owner, need);
+  PMWD_LAUNCH_CHECK();
+  return PMWD_OK;
+}

@@ -381,10 +381,28 @@ class SlabForce:
             self._side = torch.cuda.Stream(device=dev)
         return self._side
 
-    def _halo(self, disp):
+    def _halo(self, pmid, disp):
+        """Halo planes needed on either side of the slab: how far the base plane of any local particle
+        (``pmid_x + floor(disp_x / cell)``, float32 arithmetic of ``pmwd/pm_util.py:129-136``) lies
+        outside the owned planes, + the stencil's second plane.  With Lagrangian ownership this grows
+        with the largest displacement; with Eulerian ownership (``nbody._Store.migrator``) it stays at
+        the drift accumulated since the last migration."""
         conf, comm = self.conf, self.comm
-        m = comm.allreduce_max(disp[:, 0].abs().max())
-        h = int(math.ceil(m / conf.cell_size)) + 1
+        Mx, mx = conf.mesh_shape[0], comm.mx
+        if disp.is_cuda and pmid.dtype == torch.int16:
+            m = torch.empty(1, dtype=torch.int32, device=disp.device)
+            with torch.cuda.device(disp.device):
+                _lib.check(_lib.lib().pmwd_slab_owner(_lib.stream_ptr(disp.device), pmid.shape[0], _lib.ptr(pmid),
+                                                      _lib.ptr(disp), float(conf.cell_size), Mx, comm.size, comm.x0, mx,
+                                                      None, _lib.ptr(m)), 'pmwd_slab_owner')
+        else:
+            cell32 = float(np.float32(conf.cell_size))
+            plane = pmid[:, 0].to(torch.int32) + torch.floor(disp[:, 0] / cell32).to(torch.int32)
+            d = torch.remainder(plane - comm.x0, Mx)                 # 0 .. Mx-1; owned if d < mx
+            right = d + (2 - mx)                                     # planes needed above the slab
+            need = torch.where(d < mx, right.clamp(min=0), torch.minimum(right, Mx - d))
+            m = need.max() if need.numel() else torch.zeros((), dtype=torch.int32, device=disp.device)
+        h = max(int(comm.allreduce_max(m.to(torch.float32))), 1)
         if h > comm.mx:
             raise RuntimeError(f'halo of {h} planes exceeds the slab width {comm.mx}: use fewer ranks')
         if h > self.h_alloc:
@@ -650,7 +668,7 @@ class SlabForce:
         """``next_kd = (K1_next, D_next)``: also apply the next step's leading half-kick and
         drift in the gather pass (pipelined KDK, cf. ``pmwd_force_kdk``)."""
         with TIMERS('halo_width'):
-            h = self._halo(disp)
+            h = self._halo(pmid, disp)
         desc, F, _ = self._mesh_forces(pmid, disp, Om, h)
         with TIMERS('gather'):
             st = _lib.stream_ptr(disp.device)
@@ -669,7 +687,7 @@ class SlabForce:
         lib = _lib.lib()
         dev = disp.device
         Mx, My, Mz = conf.mesh_shape
-        h = self._halo(disp)
+        h = self._halo(pmid, disp)
         desc, F, val = self._mesh_forces(pmid, disp, Om, h)
         st = _lib.stream_ptr(dev)
         _lib.check(lib.pmwd_gather3(st, C.byref(desc), _lib.ptr(pmid), _lib.ptr(disp), _lib.ptr(F[0]),
@@ -847,6 +865,8 @@ class SlabStepper:
         self.i = 0
         self.pre = False
         store.desc_fn = lambda pmid: force._desc(pmid, max(force.h_alloc, 1))
+        if os.environ.get('PMWD_MIGRATE', '1') != '0' and comm.size > 1:
+            store.migrator = comm              # Eulerian ownership: re-assigned at every storage re-sort
 
     @property
     def nsteps(self):

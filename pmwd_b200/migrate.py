@@ -1,11 +1,10 @@
-"""Eulerian particle ownership for the slab decomposition: groundwork, NOT wired into the
-stepping yet.
+"""Eulerian particle ownership for the slab decomposition (wired into the slab integrator's storage
+re-sort, ``nbody._Store.reorder``; ``PMWD_MIGRATE=0`` keeps Lagrangian ownership).
 
-Today particles stay on the rank that owns their Lagrangian x-slab and the mesh halo has to cover
-the largest displacement (70 planes of 2048^2 late in the 8-GPU run: 9.7 GB of halo traffic per
-step).  If a particle instead lives on the rank that owns its CURRENT base cell, the halo is the
-one plane the CIC stencil reaches into, at the price of moving the few particles that crossed a
-slab boundary after every drift.  This module holds that exchange as plain tensor code -- rank
+With Lagrangian ownership the mesh halo has to cover the largest displacement (56 planes at N = 2,
+88 planes of 2048^2 at N = 8 late in a run).  If a particle instead lives on the rank that owns its
+CURRENT base plane, the halo only covers the drift since the last migration (8 planes), at the price of
+moving the particles that crossed a slab boundary.  This module holds that exchange as plain tensor code -- rank
 assignment with the kernels' own float32 cell arithmetic (``pmwd/pm_util.py:129-136``), a stable
 partition, one count exchange and one variable-size all-to-all per array, and the inverse that
 restores the reference's Lagrangian order -- so that it runs under gloo on the CPU
@@ -61,6 +60,51 @@ def to_eulerian(arrays, conf, group=None):
     nranks = dist.get_world_size(group)
     dest = owner_rank(arrays['pmid'][:, 0], arrays['disp'][:, 0], conf, nranks)
     return exchange(arrays, dest, group)
+
+
+def to_eulerian_movers(arrays, conf, group=None):
+    """Same result set as :func:`to_eulerian` (order differs: the particles that stay come first, in
+    their old order, then the arrivals by source rank), but only the particles that change rank travel:
+    the owner comes from one fused pass (``pmwd_slab_owner``), the movers (a few per cent) are compacted and
+    exchanged, the stayers are compacted with one gather per array."""
+    from . import _lib
+    import ctypes as C
+    nranks, rank = dist.get_world_size(group), dist.get_rank(group)
+    pmid, disp = arrays['pmid'], arrays['disp']
+    n = pmid.shape[0]
+    dev = disp.device
+    Mx = conf.mesh_shape[0]
+    if disp.is_cuda and pmid.dtype == torch.int16:
+        owner = torch.empty(n, dtype=torch.uint8, device=dev)
+        need = torch.empty(1, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().pmwd_slab_owner(_lib.stream_ptr(dev), n, _lib.ptr(pmid), _lib.ptr(disp),
+                                                  float(conf.cell_size), Mx, nranks, 0, Mx // nranks,
+                                                  _lib.ptr(owner), _lib.ptr(need)), 'pmwd_slab_owner')
+    else:
+        owner = owner_rank(pmid[:, 0], disp[:, 0], conf, nranks).to(torch.uint8)
+    stay = owner == rank
+    idx_stay = stay.nonzero(as_tuple=False).squeeze(1)
+    idx_move = (~stay).nonzero(as_tuple=False).squeeze(1)
+    dest = owner.index_select(0, idx_move).to(torch.int64)
+    order = torch.sort(dest, stable=True).indices
+    idx_move = idx_move.index_select(0, order)                  # movers grouped by destination rank
+    send, recv = _counts(dest, nranks, group)
+    ssz, rsz = send.tolist(), recv.tolist()
+    nstay, nrecv = int(idx_stay.numel()), int(sum(rsz))
+    out = {}
+    for name, a in arrays.items():
+        res = torch.empty((nstay + nrecv,) + tuple(a.shape[1:]), dtype=a.dtype, device=a.device)
+        torch.index_select(a, 0, idx_stay, out=res[:nstay])    # stayers: one gather straight into place
+        rows = a.index_select(0, idx_move).contiguous()
+        row_bytes = a.element_size()
+        for d in a.shape[1:]:
+            row_bytes *= int(d)
+        src = rows.view(torch.uint8).reshape(rows.shape[0], row_bytes)
+        got = res[nstay:].view(torch.uint8).reshape(nrecv, row_bytes)      # arrivals land behind the stayers
+        dist.all_to_all_single(got, src, output_split_sizes=rsz, input_split_sizes=ssz, group=group)
+        out[name] = res
+    return out, (send, recv)
 
 
 def to_lagrangian(arrays, ptcl_num, group=None):

@@ -101,6 +101,8 @@ class _Store:
         self.reorders = 0
         self.desc_fn = None        # pmid -> pmwd_cic_desc used for the sort keys (slab runs)
         self.sweep = None          # sweep.SweepState: table + scratch of the tiled deposit
+        self.migrator = None       # dist.SlabComm: particles move to the rank that owns their current x plane
+        self.migrations = 0
 
     def setup_sweep(self):
         """Tiled deposit (csrc/scatter_sweep.cu) for the single-device fast path: the storage is sorted
@@ -146,9 +148,24 @@ class _Store:
         dev = a['disp'].device
         n = a['disp'].shape[0]
         lib = _lib.lib()
+        if self.migrator is not None:
+            # Eulerian ownership (slab runs): every particle moves to the rank that owns its current base
+            # plane (one variable-size all-to-all per array, pmwd_b200/migrate.py); `lag` then carries the
+            # GLOBAL Lagrangian index so that lagrangian() can send everything home again
+            from . import migrate
+            comm = self.migrator
+            if self.lag is None:
+                self.lag = comm.rank * n + torch.arange(n, dtype=torch.int32, device=dev)
+            got, _ = migrate.to_eulerian_movers(dict(a, lag=self.lag), conf, comm.group)
+            self.lag = got.pop('lag')
+            self.arrays = a = got
+            n = a['disp'].shape[0]
+            self._alt = self._perm = None
+            self.migrations += 1
         desc = self.desc_fn(a['pmid']) if self.desc_fn is not None else _force_desc(a['pmid'], conf)
         if self.lag is None:
             self.lag = torch.arange(n, dtype=torch.int32, device=dev)   # bit pattern of uint32
+        if self._perm is None or self._perm.numel() != n:
             self._perm = torch.empty(n, dtype=torch.int32, device=dev)
             self._alt = {k: torch.empty_like(v) for k, v in a.items()}
             self._alt['lag'] = torch.empty_like(self.lag)
@@ -184,6 +201,14 @@ class _Store:
     def lagrangian(self, *names):
         """Arrays restored to Lagrangian order (new tensors; storage untouched)."""
         a = self.arrays
+        if self.migrator is not None and self.migrations > 0:
+            # collective: every rank sends its particles back to their Lagrangian owner (sorted by `lag`)
+            from . import migrate
+            comm = self.migrator
+            home = migrate.to_lagrangian(dict({k: a[k] for k in names}, lag=self.lag.to(torch.int64)),
+                                         self.conf.ptcl_num, comm.group)
+            outs = [home[k].contiguous() for k in names]
+            return outs if len(outs) > 1 else outs[0]
         if self.lag is None:
             out = [a[k].clone() for k in names]
             return out if len(out) > 1 else out[0]
@@ -515,9 +540,13 @@ def nbody_adj(ptcl, ptcl_cot, obsvbl_cot, cosmo, conf, reverse=False, _slab=None
             alpha=torch.empty_like(xi))
         if _slab is not None:
             store.desc_fn = lambda pmid: _slab._desc(pmid, max(_slab.h_alloc, 1))
-        n = store.arrays['xi'].numel()
-        if conf.reorder_every > 0 and _fast_ok(ptcl, conf) and \
-                float(store.arrays['disp'].abs().max()) >= conf.reorder_min_disp * conf.cell_size:
+            import os
+            if os.environ.get('PMWD_MIGRATE', '1') != '0' and _slab.comm.size > 1:
+                store.migrator = _slab.comm
+        sync_max = _slab.comm.allreduce_max if _slab is not None else None
+        m0 = store.arrays['disp'].abs().max()
+        m0 = sync_max(m0) if sync_max is not None else float(m0)     # one decision for all ranks
+        if conf.reorder_every > 0 and _fast_ok(ptcl, conf) and m0 >= conf.reorder_min_disp * conf.cell_size:
             store.active = True
             if store.reorders == 0:   # (the tiled deposit has already sorted the storage)
                 store.reorder()       # the adjoint starts from the evolved (clustered) state
@@ -533,7 +562,7 @@ def nbody_adj(ptcl, ptcl_cot, obsvbl_cot, cosmo, conf, reverse=False, _slab=None
             a = store.arrays
             with torch.cuda.device(dev):
                 _lib.check(lib.pmwd_kick_drift_adj(
-                    _lib.stream_ptr(dev), n, _lib.ptr(a['disp']), _lib.ptr(a['vel']),
+                    _lib.stream_ptr(dev), a['xi'].numel(), _lib.ptr(a['disp']), _lib.ptr(a['vel']),
                     _lib.ptr(a['acc']), _lib.ptr(a['xi']), _lib.ptr(a['pi']), _lib.ptr(a['alpha']), K, D,
                     int(do_kick), int(do_drift), C.c_void_p(sums[slot].data_ptr())),
                     'pmwd_kick_drift_adj')
@@ -553,7 +582,7 @@ def nbody_adj(ptcl, ptcl_cot, obsvbl_cot, cosmo, conf, reverse=False, _slab=None
                 a = store.arrays
                 with torch.cuda.device(dev):
                     _lib.check(lib.pmwd_kick_kick_drift_adj(
-                        _lib.stream_ptr(dev), n, _lib.ptr(a['disp']), _lib.ptr(a['vel']), _lib.ptr(a['acc']),
+                        _lib.stream_ptr(dev), a['xi'].numel(), _lib.ptr(a['disp']), _lib.ptr(a['vel']), _lib.ptr(a['acc']),
                         _lib.ptr(a['xi']), _lib.ptr(a['pi']), _lib.ptr(a['alpha']), K0, K, D,
                         C.c_void_p(sums[slot0].data_ptr()), C.c_void_p(sums[slot].data_ptr())),
                         'pmwd_kick_kick_drift_adj')
@@ -599,7 +628,7 @@ def nbody_adj(ptcl, ptcl_cot, obsvbl_cot, cosmo, conf, reverse=False, _slab=None
                 if d != 0:
                     f_adj()
                     a_acc = a_disp
-            store.maybe_reorder()
+            store.maybe_reorder(sync_max=sync_max)
 
         flush_pending()
         if _slab is not None:

@@ -89,6 +89,13 @@ WORKER = textwrap.dedent('''
     back = migrate.to_lagrangian(eul, n_all)
     for k in ('pmid', 'disp', 'vel', 'lag'):
         assert torch.equal(back[k], mine[k]), k
+    # the movers-only exchange the integrator uses: same particle set per rank (stayers first), same way home
+    eul2, _ = migrate.to_eulerian_movers(arrs, conf)
+    assert sorted(eul2['lag'].tolist()) == sorted(eul['lag'].tolist())
+    np.testing.assert_array_equal(eul2['vel'].numpy(), vel_all[eul2['lag'].numpy()])
+    back2 = migrate.to_lagrangian(eul2, n_all)
+    for k in ('pmid', 'disp', 'vel', 'lag'):
+        assert torch.equal(back2[k], mine[k]), k
     print('rank', r, 'ok')
 ''')
 
