@@ -435,9 +435,10 @@ def run_ours(args):
         host[k].copy_(getattr(p0, k))
     del p0
     torch.cuda.empty_cache()
-    # nbody_step_host keeps pmid (constant during a run) resident after its first upload
-    h2d = sum(host[k].numel() * host[k].element_size() for k in ('disp', 'vel', 'acc'))
-    h2d_plain = h2d + host['pmid'].numel() * host['pmid'].element_size()
+    # nbody_step_host keeps pmid (constant during a run) resident after its first upload, and does not
+    # re-upload the accelerations it wrote itself on the previous step (the device keeps that array)
+    h2d = sum(host[k].numel() * host[k].element_size() for k in ('disp', 'vel'))
+    h2d_plain = sum(host[k].numel() * host[k].element_size() for k in ('pmid', 'disp', 'vel', 'acc'))
     d2h = sum(host[k].numel() * host[k].element_size() for k in ('disp', 'vel', 'acc'))
 
     def e2e_plain(j, src, dst):
@@ -467,8 +468,10 @@ def run_ours(args):
             same = same and (chk[k] - host[k]).abs().max().item() <= 1e-4 * scale
         if same:
             e2e_step = e2e_host
-            api = ('pmwd_b200.nbody_step_host: pinned host arrays in and out, displacement download '
-                   'overlapped with the force (checked against nbody_step + explicit copies on the warm-up step)')
+            api = ('pmwd_b200.nbody_step_host: pinned host arrays in and out every step (disp, vel up; disp, vel, acc '
+                   'down); acc is not re-uploaded (device mirror of the array the previous step wrote); disp download '
+                   'under the force, acc download under the next step\'s uploads (full-duplex link); checked against '
+                   'nbody_step + explicit copies on the warm-up step')
         else:
             print('[bench] nbody_step_host differs from the plain route; timing the plain route', file=sys.stderr)
     except Exception as e:                         # noqa: BLE001 -- the plain route is always available
@@ -476,9 +479,10 @@ def run_ours(args):
         torch.cuda.synchronize()
         e2e_plain(0, host, host)
     del chk
+    e2e_step(1 % nsched, host, host)               # second warm-up: from here on acc is the array the API wrote
     torch.cuda.synchronize()
     e0.record()
-    for j in range(1, 1 + ke):
+    for j in range(2, 2 + ke):
         e2e_step(j % nsched, host, host)
     e1.record()
     torch.cuda.synchronize()
@@ -487,6 +491,7 @@ def run_ours(args):
            'ms_per_step': ems / ke, 'h2d_bytes_per_step': h2d if e2e_step is e2e_host else h2d_plain,
            'd2h_bytes_per_step': d2h, 'api': api}
     del host
+    pm.nbody_host_release()
     torch.cuda.empty_cache()
 
     # ---- CPU baseline on a bounded sample (rank 0, N=1)

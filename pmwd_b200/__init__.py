@@ -10,7 +10,7 @@ from .gather import gather
 from .gravity import laplace, neg_grad, gravity
 from .modes import white_noise, linear_modes
 from .lpt import lpt
-from .nbody import nbody, nbody_init, nbody_step, nbody_step_host, nbody_adj
+from .nbody import nbody, nbody_init, nbody_step, nbody_step_host, nbody_host_release, nbody_adj
 from .pm_util import fftfreq, fftfwd, fftinv
 from .spec_util import powspec
 from . import _lib

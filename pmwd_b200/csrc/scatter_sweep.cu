@@ -29,6 +29,7 @@
 //    after this one (so that it can never race with the plain stores).
 //
 // Correctness never depends on how fresh the sort is; only the straggler fraction does.
+#include <math.h>
 #include <stdlib.h>
 
 #include "cic.cuh"
@@ -46,6 +47,7 @@ struct SweepGeom {
   int nx_ext, xoff;   // planes held by the mesh array, global index of plane 0
   int periodic;       // the array spans the whole periodic x axis
   float cell;
+  float inv_cell;     // 1 / cell when that is exact (cell a power of two), else 0: multiply instead of divide
   int ty, npencil;    // tile rows, ny / ty
   int bw, nband;      // tile cells along z (multiple of 4), nz / bw
   int lx, nseg;       // planes per x segment, ceil(nx_ext / lx)
@@ -94,6 +96,14 @@ __device__ __forceinline__ int wrap_fast(int i, int n) {
   return i;
 }
 
+// disp / cell in float32 (pm_util.py:133): for a power-of-two cell the product with the exact reciprocal is the
+// same correctly rounded number, without the division's ~10 instructions (and its slow path for zero numerators)
+__device__ __forceinline__ float cell_units(float d, const SweepGeom& G) {
+  return G.inv_cell != 0.f ? __fmul_rn(d, G.inv_cell) : __fdiv_rn(d, G.cell);
+}
+
+// TY, BW > 0: tile shape known at compile time (the flush loop's index arithmetic folds away); 0, 0: G.ty, G.bw.
+template <int TY, int BW>
 __global__ void __launch_bounds__(SW_MAX_WARPS * 32, 1)
 scatter_sweep_kernel(SweepGeom G, const short* __restrict__ pmid, const float* __restrict__ disp,
                      const float* __restrict__ val, int vstride, float vscalar, float* __restrict__ mesh,
@@ -102,11 +112,15 @@ scatter_sweep_kernel(SweepGeom G, const short* __restrict__ pmid, const float* _
   extern __shared__ __align__(16) float smf[];
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* ring = smf + (size_t)warp * 4 * G.ps;          // [4][ty+1][bw+4], private to this warp
-  uint32_t* sbuf = reinterpret_cast<uint32_t*>(smf + (size_t)G.nwarps * 4 * G.ps) + warp * 64;   // straggler staging
+  const int ty = TY ? TY : G.ty, bw = BW ? BW : G.bw;
+  const int rs = bw + 4, ps = (ty + 1) * rs;            // ring row stride (halo column at bw), plane size
+  const int ngr = bw >> 2;                              // float4 groups per tile row
+  float* ring = smf + (size_t)warp * 4 * ps;            // [4][ty+1][bw+4], private to this warp
+  uint32_t* sbuf = reinterpret_cast<uint32_t*>(smf + (size_t)G.nwarps * 4 * ps) + warp * 64;   // straggler staging
   int scount = 0;
   const int nitems = G.npencil * G.nband * G.nseg;
-  const int ngr = G.bw >> 2;                            // float4 groups per tile row
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int64_t plane_elems = (int64_t)G.ny * G.nz;
 
   for (;;) {
     int item = 0;
@@ -117,15 +131,17 @@ scatter_sweep_kernel(SweepGeom G, const short* __restrict__ pmid, const float* _
     const int t1 = item / G.nband;
     const int pencil = t1 % G.npencil, sgi = t1 / G.npencil;
     const int xa = sgi * G.lx, xb = min(xa + G.lx, G.nx_ext);
-    const int y0 = pencil * G.ty, z0 = band * G.bw;
+    const int y0 = pencil * ty, z0 = band * bw;
+    const int wrap_row = (y0 + ty == G.ny) ? ty : -1;   // the halo row of the last y-tile is row 0 of the mesh
+    const int zh = (z0 + bw == G.nz) ? 0 : z0 + bw;     // halo column: the first cell of the next tile along z
     const uint2* tab = table + ((int64_t)pencil * G.nband + band) * G.nx_ext;
-    for (int i = lane; i < G.ps; i += 32) reinterpret_cast<float4*>(ring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = lane; i < ps; i += 32) reinterpret_cast<float4*>(ring)[i] = zero4;
     __syncwarp();
 
-    // ---- flush one ring plane of this warp to the mesh and clear it
+    // ---- flush one ring plane of this warp to the mesh, clearing it on the way
     auto flush = [&](int pl) {
       const int slot = (pl - (xa - 1)) & 3;
-      float* src = ring + slot * G.ps;
+      float* src = ring + slot * ps;
       bool valid = true;
       int gpl = pl;
       if (G.periodic) {
@@ -134,55 +150,65 @@ scatter_sweep_kernel(SweepGeom G, const short* __restrict__ pmid, const float* _
       } else {
         valid = pl >= 0 && pl < G.nx_ext;
       }
-      if (valid) {
-        const bool all_red = (pl <= xa + 1) || (pl >= xb - 1);
-        const int ntot = (G.ty + 1) * ngr;
-        for (int i = lane; i < ntot; i += 32) {
+      float* mpl = mesh + (int64_t)gpl * plane_elems;
+      const bool all_red = (pl <= xa + 1) || (pl >= xb - 1);
+      const int ntot = (ty + 1) * ngr;
+#pragma unroll
+      for (int i0 = 0; i0 < ntot; i0 += 32) {
+        const int i = i0 + lane;
+        if (i < ntot) {
           const int row = i / ngr, gq = i - row * ngr;
-          const float4 v = *reinterpret_cast<const float4*>(src + row * G.rs + 4 * gq);
-          int gy = y0 + row;
-          if (gy == G.ny) gy = 0;
-          float* dst = mesh + ((int64_t)gpl * G.ny + gy) * G.nz + z0 + 4 * gq;
-          if (all_red || row == 0 || row == G.ty || gq == 0) {
-            if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) red_add4(dst, v);
-          } else {
-            __stcs(reinterpret_cast<float4*>(dst), v);
-          }
-        }
-        // halo column: the first cell of the next tile along z
-        const int zh = (z0 + G.bw == G.nz) ? 0 : z0 + G.bw;
-        for (int row = lane; row <= G.ty; row += 32) {
-          const float v = src[row * G.rs + G.bw];
-          if (v != 0.f) {
-            int gy = y0 + row;
-            if (gy == G.ny) gy = 0;
-            atomicAdd(mesh + ((int64_t)gpl * G.ny + gy) * G.nz + zh, v);
+          float4* sp = reinterpret_cast<float4*>(src + row * rs + 4 * gq);
+          const float4 v = *sp;
+          *sp = zero4;
+          if (valid) {
+            const int gy = row == wrap_row ? 0 : y0 + row;
+            float* dst = mpl + (unsigned)(gy * G.nz + z0 + 4 * gq);
+            if (all_red || row == 0 || row == ty || gq == 0) {
+              if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) red_add4(dst, v);
+            } else {
+              __stcs(reinterpret_cast<float4*>(dst), v);
+            }
           }
         }
       }
-      __syncwarp();
-      for (int i = lane; i < (G.ps >> 2); i += 32) reinterpret_cast<float4*>(src)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int row = lane; row <= ty; row += 32) {
+        const float v = src[row * rs + bw];
+        src[row * rs + bw] = 0.f;
+        if (valid && v != 0.f) {
+          const int gy = row == wrap_row ? 0 : y0 + row;
+          atomicAdd(mpl + (unsigned)(gy * G.nz + zh), v);
+        }
+      }
       __syncwarp();
     };
 
-    // ---- chunk iterator over the item's (plane, particle range) list; uniform across the warp
+    // ---- chunk iterator over the item's (plane, particle range) list; uniform across the warp.
+    // The table entry of the next plane is always in flight while the current plane is worked on.
     int xs = xa;
     unsigned b0 = 0, bend = 0;
+    uint2 ahead;
+    { const uint2 s = __ldg(tab + xa); b0 = s.x; bend = s.y; }
+    ahead = __ldg(tab + min(xa + 1, xb - 1));
     auto seek = [&]() {      // make (xs, b0, bend) point at a non-empty chunk or xs == xb
       while (xs < xb) {
         if (b0 < bend) return;
         ++xs;
-        if (xs < xb) { const uint2 s = __ldg(tab + xs); b0 = s.x; bend = s.y; }
+        if (xs < xb) {
+          b0 = ahead.x; bend = ahead.y;
+          ahead = __ldg(tab + min(xs + 1, xb - 1));
+        }
       }
     };
-    { const uint2 s = __ldg(tab + xa); b0 = s.x; bend = s.y; }
     seek();
     auto load = [&](int lxs, unsigned lb0, unsigned lbend, PtclRegs& R) -> bool {
       const unsigned p = lb0 + lane;
       const bool act = lxs < xb && p < lbend;
       if (act) {
-        R.pm[0] = pmid[3 * (int64_t)p + 0]; R.pm[1] = pmid[3 * (int64_t)p + 1]; R.pm[2] = pmid[3 * (int64_t)p + 2];
-        R.dp[0] = disp[3 * (int64_t)p + 0]; R.dp[1] = disp[3 * (int64_t)p + 1]; R.dp[2] = disp[3 * (int64_t)p + 2];
+        const short* pm = pmid + 3 * (int64_t)p;
+        const float* dp = disp + 3 * (int64_t)p;
+        R.pm[0] = pm[0]; R.pm[1] = pm[1]; R.pm[2] = pm[2];
+        R.dp[0] = dp[0]; R.dp[1] = dp[1]; R.dp[2] = dp[2];
         R.v = val ? val[(int64_t)vstride * p] : vscalar;
       }
       return act;
@@ -208,7 +234,8 @@ scatter_sweep_kernel(SweepGeom G, const short* __restrict__ pmid, const float* _
       const int nn[3] = {G.nx, G.ny, G.nz};
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
-        const float t = __fdiv_rn(cur_act ? cur.dp[a] : 0.f, G.cell);
+        // idle lanes: a numerator the division's fast path accepts (a zero sends the whole warp down its slow path)
+        const float t = cell_units(cur_act ? cur.dp[a] : G.cell, G);
         const float fl = floorf(t);
         d0[a] = __fsub_rn(t, fl);
         g[a] = wrap_fast((cur_act ? (int)cur.pm[a] : 0) + (int)fl, nn[a]);
@@ -221,7 +248,10 @@ scatter_sweep_kernel(SweepGeom G, const short* __restrict__ pmid, const float* _
         else if (dxs < -(G.nx >> 1)) dxs += G.nx;
       }
       const int dy = g[1] - y0, dz = g[2] - z0;
-      const bool inwin = cur_act && dxs >= -1 && dxs <= 1 && dy >= 0 && dy < G.ty && dz >= 0 && dz < G.bw;
+      const bool inwin = cur_act && dxs >= -1 && dxs <= 1 && dy >= 0 && dy < ty && dz >= 0 && dz < bw;
+      // lanes with the same base cell (issued early: its latency hides behind the weights)
+      const unsigned key = inwin ? (unsigned)(((dxs + 1) * ty + dy) * bw + dz) : (0x80000000u | (unsigned)lane);
+      unsigned peers = __match_any_sync(full, key);
       if (record_strag) {
         // stragglers are staged in a per-warp buffer and appended to the global list 32 at a time
         // (one global atomic per chunk on a single counter stalled half of all issue slots)
@@ -243,11 +273,11 @@ scatter_sweep_kernel(SweepGeom G, const short* __restrict__ pmid, const float* _
         }
       }
       // ---- contributions, merged over lanes with the same base cell
-      const unsigned key = inwin ? (unsigned)(((dxs + 1) * G.ty + dy) * G.bw + dz) : (0x80000000u | (unsigned)lane);
       float wx[2], wy[2], wz[2];
       wx[0] = __fsub_rn(1.f, fabsf(d0[0])); wx[1] = __fsub_rn(1.f, fabsf(__fsub_rn(d0[0], 1.f)));
       wy[0] = __fsub_rn(1.f, fabsf(d0[1])); wy[1] = __fsub_rn(1.f, fabsf(__fsub_rn(d0[1], 1.f)));
       wz[0] = __fsub_rn(1.f, fabsf(d0[2])); wz[1] = __fsub_rn(1.f, fabsf(__fsub_rn(d0[2], 1.f)));
+      const float v = inwin ? cur.v : 0.f;
       float c8[8];
 #pragma unroll
       for (int bx = 0; bx < 2; ++bx)
@@ -256,20 +286,25 @@ scatter_sweep_kernel(SweepGeom G, const short* __restrict__ pmid, const float* _
           const float wxy = __fmul_rn(wx[bx], wy[by]);
 #pragma unroll
           for (int bz = 0; bz < 2; ++bz)
-            c8[(bx * 2 + by) * 2 + bz] = inwin ? __fmul_rn(cur.v, __fmul_rn(wxy, wz[bz])) : 0.f;
+            c8[(bx * 2 + by) * 2 + bz] = __fmul_rn(v, __fmul_rn(wxy, wz[bz]));
         }
-      const unsigned peers = __match_any_sync(full, key);
       const bool first = sweep_reduce_peers<8>(peers, c8);
       if (__any_sync(full, inwin)) {
         const bool push = inwin && first;
         const int slot = (cxs + dxs - (xa - 1)) & 3;
-        const int off = dy * G.rs + dz;
-        float* p0 = ring + slot * G.ps + off;
-        float* p1 = ring + ((slot + 1) & 3) * G.ps + off;
+        const int off = dy * rs + dz;
+        float* p0 = ring + slot * ps + off;
+        float* p1 = ring + ((slot + 1) & 3) * ps + off;
+        // the two x-planes of a stencil are different ring planes: their read-modify-writes cannot alias
+        // across lanes, so each of the four (y, z) phases handles both (two independent LDS/FADD/STS chains)
 #pragma unroll
-        for (int n = 0; n < 8; ++n) {
-          float* cellp = ((n & 4) ? p1 : p0) + ((n & 2) ? G.rs : 0) + (n & 1);
-          if (push) *cellp = *cellp + c8[n];
+        for (int n = 0; n < 4; ++n) {
+          const int o = ((n & 2) ? rs : 0) + (n & 1);
+          if (push) {
+            const float a0 = p0[o], a1 = p1[o];
+            p0[o] = a0 + c8[n];
+            p1[o] = a1 + c8[4 + n];
+          }
           __syncwarp();
         }
       }
@@ -409,6 +444,13 @@ static bool sweep_geom(const pmwd_cic_desc* d, int ty, int bw, int lx, SweepGeom
   G->periodic = (G->nx_ext == G->nx && G->xoff == 0) ? 1 : 0;
   if (!G->periodic && G->nx_ext > G->nx) return false;      // halos wider than the box: RED kernel
   G->cell = (float)d->cell_size;
+  {
+    int e = 0;
+    const float m = frexpf(G->cell, &e);
+    G->inv_cell = (m == 0.5f && e > -100 && e < 100) ? 1.f / G->cell : 0.f;
+    const char* env = getenv("PMWD_SWEEP_DIV");
+    if (env && atoi(env) > 0) G->inv_cell = 0.f;
+  }
   if (ty < 2 || ty > 64 || G->ny % ty != 0) return false;
   if (bw < 4 || bw > 256 || (bw & 3) != 0 || G->nz % bw != 0) return false;
   if (lx < 1 || G->nx_ext < 4) return false;
@@ -512,9 +554,15 @@ int scatter_sweep(cudaStream_t st, const pmwd_cic_desc* d, const pmwd_sweep* sw,
   uint32_t* strag = (uint32_t*)((char*)sw->scratch + 64);
   static int smem_set = 0;
   const size_t smem = (size_t)G.nwarps * sweep_ring_bytes(G.ty, G.bw);
+  auto kernel = scatter_sweep_kernel<0, 0>;
+  if (G.ty == 8 && G.bw == 64) kernel = scatter_sweep_kernel<8, 64>;
+  else if (G.ty == 8 && G.bw == 32) kernel = scatter_sweep_kernel<8, 32>;
+  else if (G.ty == 16 && G.bw == 32) kernel = scatter_sweep_kernel<16, 32>;
   if (!smem_set) {
-    PMWD_CUDA_TRY(cudaFuncSetAttribute(scatter_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       226 * 1024));
+    PMWD_CUDA_TRY(cudaFuncSetAttribute(scatter_sweep_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    PMWD_CUDA_TRY(cudaFuncSetAttribute(scatter_sweep_kernel<8, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    PMWD_CUDA_TRY(cudaFuncSetAttribute(scatter_sweep_kernel<8, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    PMWD_CUDA_TRY(cudaFuncSetAttribute(scatter_sweep_kernel<16, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     smem_set = 1;
   }
   PMWD_CUDA_TRY(cudaMemsetAsync(counters, 0, reuse_stragglers ? 4 : 8, st));
@@ -524,9 +572,8 @@ int scatter_sweep(cudaStream_t st, const pmwd_cic_desc* d, const pmwd_sweep* sw,
   const int64_t nitems = (int64_t)G.npencil * G.nband * G.nseg;
   const int64_t want = (nitems + G.nwarps - 1) / G.nwarps;
   const int grid = (int)(want < sm_count() ? want : sm_count());
-  scatter_sweep_kernel<<<grid, G.nwarps * 32, smem, st>>>(G, (const short*)pmid, disp, val, vstride, vscalar, mesh,
-                                                       (const uint2*)sw->table, counters, strag,
-                                                       reuse_stragglers ? 0 : 1);
+  kernel<<<grid, G.nwarps * 32, smem, st>>>(G, (const short*)pmid, disp, val, vstride, vscalar, mesh,
+                                            (const uint2*)sw->table, counters, strag, reuse_stragglers ? 0 : 1);
   PMWD_LAUNCH_CHECK();
   sweep_straggler_kernel<<<sm_count() * 4, 256, 0, st>>>(G, (const short*)pmid, disp, val, vstride, vscalar, mesh,
                                                          counters, strag);

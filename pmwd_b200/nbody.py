@@ -346,7 +346,6 @@ def nbody_step(a_prev, a_next, ptcl, obsvbl, cosmo, conf):
     return ptcl, obsvbl
 
 
-_host_streams = {}
 _pmid_resident = {}        # (host data_ptr, shape, version, device) -> device copy of a host pmid array
 
 
@@ -362,19 +361,54 @@ def _resident_pmid(host_pmid, dev):
     return t
 
 
-def nbody_step_host(a_prev, a_next, host, cosmo, conf, out=None):
+class _HostMirror:
+    """Device-side working set of ``nbody_step_host`` on one device: the three dynamic arrays, two
+    copy streams and what is known about the host array that mirrors the device accelerations."""
+
+    def __init__(self, dev, shape):
+        self.shape = tuple(shape)
+        self.disp = torch.empty(shape, dtype=torch.float32, device=dev)
+        self.vel = torch.empty(shape, dtype=torch.float32, device=dev)
+        self.acc = torch.empty(shape, dtype=torch.float32, device=dev)
+        self.side = torch.cuda.Stream(dev)       # displacement download, under the force
+        self.side2 = torch.cuda.Stream(dev)      # acceleration download, under the next call's uploads
+        self.acc_tag = None                      # (data_ptr, shape, version) of the host array written from self.acc
+        self.acc_event = None                    # end of that download
+
+
+_host_mirrors = {}
+
+
+def nbody_host_release(dev=None):
+    """Drop the device buffers ``nbody_step_host`` keeps between calls (all devices by default)."""
+    for k in list(_host_mirrors):
+        if dev is None or k == str(torch.device(dev)):
+            del _host_mirrors[k]
+    _pmid_resident.clear()
+
+
+def nbody_step_host(a_prev, a_next, host, cosmo, conf, out=None, acc_resident=True):
     """``nbody_step`` for a state that lives in (pinned) HOST memory: ``host`` and the returned
     dict map ``'pmid'`` (int16), ``'disp'``, ``'vel'``, ``'acc'`` (float32) to CPU tensors of
     shape ``(N, 3)``; ``out`` may supply the output buffers (``pmid`` is passed through).
 
-    Same arithmetic as ``nbody_step`` (``nbody.py:204-212``).  The copies are part of the call
-    (``pmid``, which never changes, is uploaded once per host array and kept resident):
-    the three dynamic arrays go up first, the leading half-kick + drift run as soon as they are
-    there, and the new displacements -- final after the drift -- are copied back on a second
-    stream WHILE the force is computed; velocities and accelerations follow the fused
-    force + trailing half-kick.  Everything is enqueued asynchronously: synchronise the device
-    (or the current stream) before reading the outputs.  Default KDK splitting on the 3-D fast
-    path; other configurations take the plain copy -> ``integrate`` -> copy route.
+    Same arithmetic as ``nbody_step`` (``nbody.py:204-212``).  The copies are part of the call:
+
+    * ``disp`` and ``vel`` go up every call; ``pmid`` never changes (``pmwd/particles.py:52-59``) and is
+      uploaded once per host array;
+    * ``acc`` is the force at the displacements the previous call produced: the device keeps the array
+      it computed, and a host ``acc`` that is the very array the previous call wrote (same storage,
+      unchanged torch version counter) is not sent back up.  Any other ``acc`` array is uploaded;
+      ``acc_resident=False`` always uploads (needed if the host array was modified behind torch's back,
+      e.g. through a NumPy view);
+    * the new displacements -- final after the drift -- come back on a second stream WHILE the force is
+      computed, the velocities after the fused force + trailing half-kick, and the accelerations after
+      those on a third stream, so that their download shares the (full-duplex) link with the NEXT call's
+      uploads instead of delaying them.
+
+    Everything is enqueued asynchronously: ``torch.cuda.synchronize(device)`` before reading the outputs
+    (synchronising the current stream covers ``disp`` and ``vel`` only).  Default KDK splitting on the 3-D
+    fast path; other configurations take the plain copy -> ``integrate`` -> copy route.
     """
     dev = torch.device(conf.device if getattr(conf, 'device', None) is not None else 'cuda')
     if dev.type != 'cuda' or not torch.cuda.is_available():
@@ -387,34 +421,48 @@ def nbody_step_host(a_prev, a_next, host, cosmo, conf, out=None):
     out['pmid'] = host['pmid']
     a_prev, a_next = _f(a_prev), _f(a_next)
     with torch.no_grad(), torch.cuda.device(dev):
+        dev = torch.device('cuda', torch.cuda.current_device())
         cur = torch.cuda.current_stream(dev)
-        acc = host['acc'].to(dev, non_blocking=True)
-        vel = host['vel'].to(dev, non_blocking=True)
-        disp = host['disp'].to(dev, non_blocking=True)
+        m = _host_mirrors.get(str(dev))
+        if m is None or m.shape != tuple(host['disp'].shape):
+            _host_mirrors.pop(str(dev), None)
+            m = _host_mirrors[str(dev)] = _HostMirror(dev, host['disp'].shape)
+        if m.acc_event is not None:
+            cur.wait_event(m.acc_event)          # the previous call's acc download reads m.acc
+            m.acc_event = None
+        tag = (host['acc'].data_ptr(), tuple(host['acc'].shape), host['acc']._version)
+        if not (acc_resident and m.acc_tag == tag):
+            m.acc.copy_(host['acc'], non_blocking=True)
+        m.acc_tag = None
+        m.vel.copy_(host['vel'], non_blocking=True)
+        m.disp.copy_(host['disp'], non_blocking=True)
         pmid = _resident_pmid(host['pmid'], dev)
-        p = Particles(conf, pmid, disp, vel=vel, acc=acc)
+        p = Particles(conf, pmid, m.disp, vel=m.vel, acc=m.acc)
         default = tuple(tuple(x) for x in conf.symp_splits) == ((0, 0.5), (1, 0.5))
         if not (default and _fast_ok(p, conf)):
             q = _integrate_inplace(a_prev, a_next, p, cosmo, conf)
             for k in ('disp', 'vel', 'acc'):
                 out[k].copy_(getattr(q, k), non_blocking=True)
+            if q.acc is not m.acc:
+                m.acc.copy_(q.acc)
+            m.acc_tag = (out['acc'].data_ptr(), tuple(out['acc'].shape), out['acc']._version)
             return out
         am = a_prev * 0.5 + a_next * 0.5
         K1 = _f32(kick_factor(a_prev, a_prev, am, cosmo, conf))
         D = _f32(drift_factor(am, a_prev, a_next, cosmo, conf))
         K2 = _f32(kick_factor(a_next, am, a_next, cosmo, conf))
         _kick_drift(p, K1, D, True, True)
-        side = _host_streams.get(dev)
-        if side is None:
-            side = _host_streams[dev] = torch.cuda.Stream(dev)
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            out['disp'].copy_(p.disp, non_blocking=True)
-        p.disp.record_stream(side)
+        m.side.wait_stream(cur)
+        with torch.cuda.stream(m.side):
+            out['disp'].copy_(m.disp, non_blocking=True)
         force_into(p.pmid, p.disp, float(cosmo.Omega_m), conf, p.acc, p.vel, K2)
-        out['vel'].copy_(p.vel, non_blocking=True)
-        out['acc'].copy_(p.acc, non_blocking=True)
-        cur.wait_stream(side)
+        out['vel'].copy_(m.vel, non_blocking=True)
+        m.side2.wait_stream(cur)                 # after the velocities: same direction, same link
+        with torch.cuda.stream(m.side2):
+            out['acc'].copy_(m.acc, non_blocking=True)
+            m.acc_event = m.side2.record_event()
+        m.acc_tag = (out['acc'].data_ptr(), tuple(out['acc'].shape), out['acc']._version)
+        cur.wait_stream(m.side)                  # the next call may overwrite m.disp / read out['disp']
     return out
 
 

@@ -716,3 +716,44 @@ def test_nbody_step_host_matches_nbody_step(splits):
             assert (host[k] - r).abs().max().item() <= 1e-5 * r.abs().max().item(), (i, k)
     with pytest.raises(ValueError):
         pm.nbody_step_host(a[0], a[1], dict(host, disp=host['disp'].cuda()), cosmo, conf)
+
+
+def test_nbody_step_host_acc_mirror():
+    """The device keeps the accelerations it computed: a host acc array that is the one the previous call
+    wrote is not uploaded again, one that was modified through torch (version counter) or replaced is,
+    and acc_resident=False always uploads.  All routes give the result of a call with explicit uploads."""
+    from pmwd_b200 import nbody as nb
+    pm, conf, oconf, cosmo, ocosmo, ic, ptcl = _ic(32, a_nbody_maxstep=1 / 16)
+    a = conf.a_nbody
+    p0, _ = pm.nbody_init(a[0], ptcl, None, cosmo, conf)
+    first = {k: getattr(p0, k).cpu().pin_memory() for k in ('pmid', 'disp', 'vel', 'acc')}
+    nb.nbody_host_release()
+    s1 = pm.nbody_step_host(a[0], a[1], first, cosmo, conf)
+    torch.cuda.synchronize()
+    state = {k: s1[k].clone().pin_memory() for k in s1}
+
+    def step2(src, **kw):
+        o = pm.nbody_step_host(a[1], a[2], src, cosmo, conf, **kw)
+        torch.cuda.synchronize()
+        return {k: o[k].clone() for k in ('disp', 'vel', 'acc')}
+
+    def same(x, y):       # two runs of step 1 differ by the atomic deposit's summation order
+        for k in ('disp', 'vel', 'acc'):
+            assert (x[k] - y[k]).abs().max().item() <= 1e-5 * y[k].abs().max().item(), k
+
+    want = step2(state, acc_resident=False)              # explicit upload of everything
+    # (a) the array the previous call wrote: acc comes from the device mirror
+    nb.nbody_host_release()
+    s1 = pm.nbody_step_host(a[0], a[1], first, cosmo, conf)
+    m = nb._host_mirrors[str(torch.device('cuda', torch.cuda.current_device()))]
+    assert m.acc_tag == (s1['acc'].data_ptr(), tuple(s1['acc'].shape), s1['acc']._version)
+    same(step2(s1), want)
+    # (b) acc modified on the host through torch: the tag no longer matches, the modified array goes up
+    nb.nbody_host_release()
+    s1 = pm.nbody_step_host(a[0], a[1], first, cosmo, conf)
+    torch.cuda.synchronize()
+    s1['acc'].mul_(2.0)
+    mod = dict(state, acc=(state['acc'] * 2.0).pin_memory())
+    same(step2(s1), step2(mod, acc_resident=False))
+    # (c) a stale mirror must not leak into a call with another acc array
+    same(step2(state), want)

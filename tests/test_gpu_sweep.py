@@ -13,10 +13,10 @@ import oracle as O
 pytestmark = pytest.mark.gpu
 
 
-def _setup(shape, sigma, seed=0, **kw):
+def _setup(shape, sigma, seed=0, spacing=1., **kw):
     import pmwd_b200 as pm
-    conf = pm.Configuration(1., shape, mesh_shape=2, **kw)
-    oconf = O.Conf(1., shape, mesh_shape=2)
+    conf = pm.Configuration(spacing, shape, mesh_shape=2, **kw)
+    oconf = O.Conf(spacing, shape, mesh_shape=2)
     pmid, disp, _, _ = O.gen_grid(oconf)
     rng = np.random.default_rng(seed)
     disp = (disp + sigma * conf.cell_size * rng.standard_normal(disp.shape)).astype(np.float32)
@@ -67,6 +67,25 @@ def test_sweep_scatter_fresh_sort_vs_oracle(shape, sigma):
     dens, = _sweep_scatter(store, conf)
     _close(dens, O.scatter(pmid, disp, oconf))
     assert store.sweep.stragglers() == 0
+
+
+@pytest.mark.parametrize('spacing, force_div', [(0.7, False), (1.0, True), (0.1, False)])
+def test_sweep_scatter_cell_size_paths(spacing, force_div, monkeypatch):
+    """disp / cell (pm_util.py:133): cells that are not a power of two take the IEEE division, powers of two
+    the exact reciprocal; both must give the oracle's deposit, also with partly filled warps (fresh and stale)."""
+    from pmwd_b200.nbody import _store_from
+    if force_div:
+        monkeypatch.setenv('PMWD_SWEEP_DIV', '1')
+    pm, conf, oconf, pmid, disp, ptcl = _setup((32, 16, 32), 1.5, spacing=spacing)
+    store = _store_from(ptcl, conf)
+    assert store.sweep is not None and store.sweep.ok
+    dens, = _sweep_scatter(store, conf)
+    _close(dens, O.scatter(pmid, disp, oconf))
+    assert store.sweep.stragglers() == 0
+    g = torch.Generator(device='cuda').manual_seed(5)
+    store.arrays['disp'] += 0.5 * conf.cell_size * torch.randn(store.arrays['disp'].shape, device='cuda', generator=g)
+    dens, = _sweep_scatter(store, conf)
+    _close(dens, O.scatter(pmid, store.lagrangian('disp').cpu().numpy(), oconf))
 
 
 @pytest.mark.parametrize('shape, sigma', [((32, 32, 32), 2.0), ((24, 16, 64), 5.0), ((8, 8, 512), 6.0)],
