@@ -40,6 +40,9 @@ int slab_xoff(const pmwd_cic_desc* d);
 bool cic_is_fast(const pmwd_cic_desc* d);
 
 constexpr int SW_MAX_WARPS = 24;
+constexpr int SW_STRAG_BLOCK = 256;               // straggler-list slots a warp reserves per global atomic
+constexpr uint32_t SW_STRAG_EMPTY = 0xffffffffu;  // unused slot of a reserved block
+constexpr int64_t SW_STRAG_SLACK = (int64_t)SW_STRAG_BLOCK * SW_MAX_WARPS * 256;   // one open block per warp, <= 256 CTAs
 
 struct SweepGeom {
   int64_t n;
@@ -117,7 +120,9 @@ scatter_sweep_kernel(SweepGeom G, const short* __restrict__ pmid, const float* _
   const int ngr = bw >> 2;                              // float4 groups per tile row
   float* ring = smf + (size_t)warp * 4 * ps;            // [4][ty+1][bw+4], private to this warp
   uint32_t* sbuf = reinterpret_cast<uint32_t*>(smf + (size_t)G.nwarps * 4 * ps) + warp * 64;   // straggler staging
-  int scount = 0;
+  int scount = 0;                                       // staged stragglers (< 32 between chunks)
+  unsigned sres_pos = 0, stotal = 0;                    // next reserved slot of the global list, stragglers so far
+  int sres_left = 0;                                    // reserved slots left
   const int nitems = G.npencil * G.nband * G.nseg;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   const int64_t plane_elems = (int64_t)G.ny * G.nz;
@@ -213,17 +218,28 @@ scatter_sweep_kernel(SweepGeom G, const short* __restrict__ pmid, const float* _
       }
       return act;
     };
-    PtclRegs cur, nxt;
-    bool cur_act = load(xs, b0, bend, cur);
+    // two chunks in flight behind the one being worked on (the loads' latency is several chunk times)
+    struct Chunk { PtclRegs R; int xs; unsigned b0; bool act; };
+    // Take the chunk the iterator points at, advance the iterator, THEN issue the chunk's loads: seek()
+    // consumes the prefetched table entry, and a scoreboard wait right behind freshly issued particle
+    // loads would wait for those as well (11 % of all stall samples before this order)
+    auto fetch = [&](Chunk& c) {
+      c.xs = xs; c.b0 = b0;
+      const unsigned cbend = bend;
+      if (xs < xb) { b0 += 32; seek(); }
+      c.act = load(c.xs, c.b0, cbend, c.R);
+    };
+    Chunk c0, c1, c2;
+    fetch(c0);
+    fetch(c1);
     int next_flush = xa - 1;
 
-    while (xs < xb) {
-      const int cxs = xs;
-      const unsigned cb0 = b0;
-      // advance the iterator and prefetch the next chunk before working on this one
-      b0 += 32;
-      seek();
-      const bool nxt_act = load(xs, b0, bend, nxt);
+    while (c0.xs < xb) {
+      fetch(c2);
+      const int cxs = c0.xs;
+      const unsigned cb0 = c0.b0;
+      const bool cur_act = c0.act;
+      const PtclRegs& cur = c0.R;
 
       while (next_flush <= cxs - 2) { flush(next_flush); ++next_flush; }   // planes out of reach
 
@@ -252,27 +268,9 @@ scatter_sweep_kernel(SweepGeom G, const short* __restrict__ pmid, const float* _
       // lanes with the same base cell (issued early: its latency hides behind the weights)
       const unsigned key = inwin ? (unsigned)(((dxs + 1) * ty + dy) * bw + dz) : (0x80000000u | (unsigned)lane);
       unsigned peers = __match_any_sync(full, key);
-      if (record_strag) {
-        // stragglers are staged in a per-warp buffer and appended to the global list 32 at a time
-        // (one global atomic per chunk on a single counter stalled half of all issue slots)
-        const unsigned sm = __ballot_sync(full, cur_act && !inwin);
-        if (sm) {
-          if (cur_act && !inwin) sbuf[scount + __popc(sm & ((1u << lane) - 1u))] = p;
-          scount += __popc(sm);
-          __syncwarp();
-          if (scount >= 32) {
-            unsigned base = 0;
-            if (lane == 0) base = atomicAdd(&counters[1], 32u);
-            base = __shfl_sync(full, base, 0);
-            strag[base + lane] = sbuf[lane];
-            __syncwarp();
-            if (lane < scount - 32) sbuf[lane] = sbuf[32 + lane];
-            scount -= 32;
-            __syncwarp();
-          }
-        }
-      }
-      // ---- contributions, merged over lanes with the same base cell
+      // ---- contributions: independent work placed behind the match (~150 cycles of latency); the empty
+      // volatile asm keeps the compiler from hoisting it above
+      asm volatile("" : "+f"(d0[0]), "+f"(d0[1]), "+f"(d0[2]));
       float wx[2], wy[2], wz[2];
       wx[0] = __fsub_rn(1.f, fabsf(d0[0])); wx[1] = __fsub_rn(1.f, fabsf(__fsub_rn(d0[0], 1.f)));
       wy[0] = __fsub_rn(1.f, fabsf(d0[1])); wy[1] = __fsub_rn(1.f, fabsf(__fsub_rn(d0[1], 1.f)));
@@ -288,6 +286,32 @@ scatter_sweep_kernel(SweepGeom G, const short* __restrict__ pmid, const float* _
           for (int bz = 0; bz < 2; ++bz)
             c8[(bx * 2 + by) * 2 + bz] = __fmul_rn(v, __fmul_rn(wxy, wz[bz]));
         }
+      if (record_strag) {
+        // stragglers are staged in a per-warp buffer and appended to the global list 32 at a time, into
+        // slots reserved SW_STRAG_BLOCK at a time (one global atomic per chunk on a single counter
+        // stalled half of all issue slots; one per 32 stragglers still cost 5 % of the kernel)
+        const unsigned sm = __ballot_sync(full, cur_act && !inwin);
+        if (sm) {
+          if (cur_act && !inwin) sbuf[scount + __popc(sm & ((1u << lane) - 1u))] = p;
+          scount += __popc(sm);
+          __syncwarp();
+          if (scount >= 32) {
+            if (sres_left == 0) {
+              unsigned base = 0;
+              if (lane == 0) base = atomicAdd(&counters[1], (unsigned)SW_STRAG_BLOCK);
+              sres_pos = __shfl_sync(full, base, 0);
+              sres_left = SW_STRAG_BLOCK;
+            }
+            strag[sres_pos + lane] = sbuf[lane];
+            sres_pos += 32; sres_left -= 32; stotal += 32;
+            __syncwarp();
+            if (lane < scount - 32) sbuf[lane] = sbuf[32 + lane];
+            scount -= 32;
+            __syncwarp();
+          }
+        }
+      }
+      // ---- merged over lanes with the same base cell
       const bool first = sweep_reduce_peers<8>(peers, c8);
       if (__any_sync(full, inwin)) {
         const bool push = inwin && first;
@@ -295,30 +319,48 @@ scatter_sweep_kernel(SweepGeom G, const short* __restrict__ pmid, const float* _
         const int off = dy * rs + dz;
         float* p0 = ring + slot * ps + off;
         float* p1 = ring + ((slot + 1) & 3) * ps + off;
-        // the two x-planes of a stencil are different ring planes: their read-modify-writes cannot alias
-        // across lanes, so each of the four (y, z) phases handles both (two independent LDS/FADD/STS chains)
+        // Lane A's upper x-plane can be lane B's lower one (different base planes, hence different keys, same
+        // (y, z) cell), so in general the eight neighbours go one per phase.  If all base planes of the chunk
+        // have the same parity that cannot happen, and the two x-planes of a stencil -- different ring planes
+        // -- go together: four phases of two independent LDS/FADD/STS chains.
+        const bool mixed = __any_sync(full, inwin && (dxs & 1)) && __any_sync(full, inwin && !(dxs & 1));
+        if (!mixed) {
 #pragma unroll
-        for (int n = 0; n < 4; ++n) {
-          const int o = ((n & 2) ? rs : 0) + (n & 1);
-          if (push) {
-            const float a0 = p0[o], a1 = p1[o];
-            p0[o] = a0 + c8[n];
-            p1[o] = a1 + c8[4 + n];
+          for (int n = 0; n < 4; ++n) {
+            const int o = ((n & 2) ? rs : 0) + (n & 1);
+            if (push) {
+              const float a0 = p0[o], a1 = p1[o];
+              p0[o] = a0 + c8[n];
+              p1[o] = a1 + c8[4 + n];
+            }
+            __syncwarp();
           }
-          __syncwarp();
+        } else {
+#pragma unroll
+          for (int n = 0; n < 8; ++n) {
+            float* cellp = ((n & 4) ? p1 : p0) + ((n & 2) ? rs : 0) + (n & 1);
+            if (push) *cellp = *cellp + c8[n];
+            __syncwarp();
+          }
         }
       }
-      cur = nxt;
-      cur_act = nxt_act;
+      c0 = c1;
+      c1 = c2;
     }
     // ---- the rest of the ring: planes up to xb + 1
     while (next_flush <= xb + 1) { flush(next_flush); ++next_flush; }
   }
-  if (scount > 0) {
-    unsigned base = 0;
-    if (lane == 0) base = atomicAdd(&counters[1], (unsigned)scount);
-    base = __shfl_sync(full, base, 0);
-    if (lane < scount) strag[base + lane] = sbuf[lane];
+  if (record_strag) {
+    // the staged rest, then the unused slots of this warp's last block are marked empty
+    if (scount > 0 && sres_left == 0) {
+      unsigned base = 0;
+      if (lane == 0) base = atomicAdd(&counters[1], (unsigned)SW_STRAG_BLOCK);
+      sres_pos = __shfl_sync(full, base, 0);
+      sres_left = SW_STRAG_BLOCK;
+    }
+    for (int i = lane; i < sres_left; i += 32) strag[sres_pos + i] = i < scount ? sbuf[i] : SW_STRAG_EMPTY;
+    stotal += scount;
+    if (lane == 0 && stotal) atomicAdd(&counters[2], stotal);
   }
 }
 
@@ -352,6 +394,7 @@ sweep_straggler_kernel(SweepGeom G, const short* __restrict__ pmid, const float*
                        const unsigned* __restrict__ counters, const uint32_t* __restrict__ strag) {
   const unsigned n = counters[1];
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (strag[i] == SW_STRAG_EMPTY) continue;
     const int64_t p = strag[i];
     int ix[2], iy[2], iz[2];
     float wx[2], wy[2], wz[2];
@@ -501,10 +544,13 @@ extern "C" size_t pmwd_sweep_table_bytes(const pmwd_cic_desc* d, int ty, int bw)
   return (size_t)(d->wrap_shape[1] / ty) * (d->wrap_shape[2] / bw) * d->mesh_shape[0] * sizeof(uint2);
 }
 
-// counters (64 bytes) + straggler list (4 bytes per particle)
+// counters (64 bytes: [0] work items, [1] length of the straggler list, [2] stragglers) + straggler list
+// (4 bytes per particle + one open block of reserved slots per warp)
+static size_t sweep_scratch_bytes(int64_t n) { return 64 + (size_t)(n + SW_STRAG_SLACK) * sizeof(uint32_t); }
+
 extern "C" size_t pmwd_sweep_scratch_bytes(const pmwd_cic_desc* d) {
   if (!d) return 0;
-  return 64 + (size_t)d->ptcl_num * sizeof(uint32_t);
+  return sweep_scratch_bytes(d->ptcl_num);
 }
 
 // Build the (tile, plane) table from the sorted keys of pmwd_cell_sort_perm(..., ty, bw).
@@ -540,7 +586,7 @@ bool sweep_usable(const pmwd_cic_desc* d, const pmwd_sweep* sw) {
   SweepGeom G;
   if (!sweep_geom(d, sw->ty, sw->bw, sw->lx, &G)) return false;
   if (sw->nx_ext != G.nx_ext || sw->xoff != G.xoff) return false;      // table built for another slab
-  return sw->scratch_bytes >= 64 + (size_t)d->ptcl_num * sizeof(uint32_t);
+  return sw->scratch_bytes >= sweep_scratch_bytes(d->ptcl_num);
 }
 
 // One channel: mesh (NOT pre-zeroed by the caller) <- deposit of val[p * vstride] (or vscalar).
@@ -565,13 +611,14 @@ int scatter_sweep(cudaStream_t st, const pmwd_cic_desc* d, const pmwd_sweep* sw,
     PMWD_CUDA_TRY(cudaFuncSetAttribute(scatter_sweep_kernel<16, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     smem_set = 1;
   }
-  PMWD_CUDA_TRY(cudaMemsetAsync(counters, 0, reuse_stragglers ? 4 : 8, st));
+  PMWD_CUDA_TRY(cudaMemsetAsync(counters, 0, reuse_stragglers ? 4 : 12, st));
   const int64_t rows = (int64_t)G.nx_ext * G.ny;
   sweep_zero_kernel<<<grid_for(rows * 32, 256, 8), 256, 0, st>>>(G, mesh);
   PMWD_LAUNCH_CHECK();
   const int64_t nitems = (int64_t)G.npencil * G.nband * G.nseg;
   const int64_t want = (nitems + G.nwarps - 1) / G.nwarps;
   const int grid = (int)(want < sm_count() ? want : sm_count());
+  PMWD_REQUIRE((int64_t)grid * G.nwarps * SW_STRAG_BLOCK <= SW_STRAG_SLACK, "straggler list slack too small for this grid");
   kernel<<<grid, G.nwarps * 32, smem, st>>>(G, (const short*)pmid, disp, val, vstride, vscalar, mesh,
                                             (const uint2*)sw->table, counters, strag, reuse_stragglers ? 0 : 1);
   PMWD_LAUNCH_CHECK();
@@ -605,8 +652,8 @@ extern "C" int pmwd_scatter_sweep(void* stream, const pmwd_cic_desc* d, const pm
 // The number of stragglers of the last sweep that recorded them (reads device memory: synchronises).
 extern "C" long long pmwd_sweep_last_stragglers(void* stream, const pmwd_sweep* sweep) {
   if (!sweep || !sweep->scratch) return -1;
-  unsigned c[2] = {0, 0};
+  unsigned c[3] = {0, 0, 0};
   if (cudaStreamSynchronize(as_stream(stream)) != cudaSuccess) return -1;
   if (cudaMemcpy(c, sweep->scratch, sizeof(c), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-  return (long long)c[1];
+  return (long long)c[2];
 }

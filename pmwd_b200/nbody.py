@@ -9,6 +9,7 @@ to float32 before touching particles.  ``jax.custom_vjp`` becomes a
 ``torch.autograd.Function`` whose residual is only the final state (``nbody.py:263-265``).
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -374,6 +375,13 @@ class _HostMirror:
         self.side2 = torch.cuda.Stream(dev)      # acceleration download, under the next call's uploads
         self.acc_tag = None                      # (data_ptr, shape, version) of the host array written from self.acc
         self.acc_event = None                    # end of that download
+        self.trace = [] if os.environ.get('PMWD_HOST_TRACE') else None    # (label, event) per stage, tools/time_host_step.py
+
+    def mark(self, label, stream):
+        if self.trace is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(stream)
+            self.trace.append((label, ev))
 
 
 _host_mirrors = {}
@@ -427,19 +435,24 @@ def nbody_step_host(a_prev, a_next, host, cosmo, conf, out=None, acc_resident=Tr
         if m is None or m.shape != tuple(host['disp'].shape):
             _host_mirrors.pop(str(dev), None)
             m = _host_mirrors[str(dev)] = _HostMirror(dev, host['disp'].shape)
-        if m.acc_event is not None:
-            cur.wait_event(m.acc_event)          # the previous call's acc download reads m.acc
-            m.acc_event = None
+        m.mark('start', cur)
         tag = (host['acc'].data_ptr(), tuple(host['acc'].shape), host['acc']._version)
         if not (acc_resident and m.acc_tag == tag):
+            if m.acc_event is not None:
+                cur.wait_event(m.acc_event)      # the previous call's acc download still reads m.acc
+                m.acc_event = None
             m.acc.copy_(host['acc'], non_blocking=True)
         m.acc_tag = None
         m.vel.copy_(host['vel'], non_blocking=True)
         m.disp.copy_(host['disp'], non_blocking=True)
+        m.mark('uploaded', cur)
         pmid = _resident_pmid(host['pmid'], dev)
         p = Particles(conf, pmid, m.disp, vel=m.vel, acc=m.acc)
         default = tuple(tuple(x) for x in conf.symp_splits) == ((0, 0.5), (1, 0.5))
         if not (default and _fast_ok(p, conf)):
+            if m.acc_event is not None:
+                cur.wait_event(m.acc_event)
+                m.acc_event = None
             q = _integrate_inplace(a_prev, a_next, p, cosmo, conf)
             for k in ('disp', 'vel', 'acc'):
                 out[k].copy_(getattr(q, k), non_blocking=True)
@@ -455,12 +468,20 @@ def nbody_step_host(a_prev, a_next, host, cosmo, conf, out=None, acc_resident=Tr
         m.side.wait_stream(cur)
         with torch.cuda.stream(m.side):
             out['disp'].copy_(m.disp, non_blocking=True)
+            m.mark('disp_down', m.side)
+        m.mark('kick_drift', cur)
+        if m.acc_event is not None:
+            cur.wait_event(m.acc_event)          # the force overwrites m.acc: the previous call's download of it
+            m.acc_event = None                   # (running under this call's uploads) must have finished
         force_into(p.pmid, p.disp, float(cosmo.Omega_m), conf, p.acc, p.vel, K2)
+        m.mark('force', cur)
         out['vel'].copy_(m.vel, non_blocking=True)
+        m.mark('vel_down', cur)
         m.side2.wait_stream(cur)                 # after the velocities: same direction, same link
         with torch.cuda.stream(m.side2):
             out['acc'].copy_(m.acc, non_blocking=True)
             m.acc_event = m.side2.record_event()
+            m.mark('acc_down', m.side2)
         m.acc_tag = (out['acc'].data_ptr(), tuple(out['acc'].shape), out['acc']._version)
         cur.wait_stream(m.side)                  # the next call may overwrite m.disp / read out['disp']
     return out

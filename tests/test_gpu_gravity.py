@@ -722,7 +722,8 @@ def test_nbody_step_host_acc_mirror():
     """The device keeps the accelerations it computed: a host acc array that is the one the previous call
     wrote is not uploaded again, one that was modified through torch (version counter) or replaced is,
     and acc_resident=False always uploads.  All routes give the result of a call with explicit uploads."""
-    from pmwd_b200 import nbody as nb
+    import importlib
+    nb = importlib.import_module('pmwd_b200.nbody')      # (pmwd_b200.nbody is also the function)
     pm, conf, oconf, cosmo, ocosmo, ic, ptcl = _ic(32, a_nbody_maxstep=1 / 16)
     a = conf.a_nbody
     p0, _ = pm.nbody_init(a[0], ptcl, None, cosmo, conf)
