@@ -32,5 +32,9 @@ def test_slab_matches_single_gpu(world, ce):
     env = dict(os.environ, PMWD_P2P_CE='0' if ce == '0' else '1', PMWD_PIPE='2' if ce == 'pipe2' else '1')
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=420, env=env)
     errs = [l for l in (r.stdout + r.stderr).splitlines() if 'rank' in l and ('Error' in l or 'assert' in l)]
+    if r.returncode != 0:           # keep the whole log where a gpurun call brings it back
+        os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+        with open(os.path.join(ROOT, 'gpurun_out', f'dist_worker_fail_w{world}_{ce}.log'), 'w') as f:
+            f.write(r.stdout + '\n=== stderr ===\n' + r.stderr)
     assert r.returncode == 0, '\n'.join(errs[:20]) + r.stderr[-1500:]
     assert r.stdout.count(' ok: ') == 2 * world
