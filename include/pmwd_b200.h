@@ -96,6 +96,11 @@ int pmwd_ctx_create(pmwd_ctx** ctx, int device);
 int pmwd_ctx_destroy(pmwd_ctx* ctx);
 /* Create R2C + C2R plans for a real field of `rank` dims `shape` (float). */
 int pmwd_ctx_reserve(pmwd_ctx* ctx, int rank, const int32_t* shape);
+/* The (y, z) 2-D transforms (pmwd_fft2d_*, and inside pmwd_force*) can be issued `planes` x planes per cuFFT
+ * call (so that the second pass of a 2-D transform may find the first pass's output in L2).  Applies to
+ * plans reserved after the call; 0 = one call for the whole batch, -1 (default) = the PMWD_FFT2D_CHUNK
+ * environment variable, else 0 (measured on B200: chunking is slower, profiles/r02_fft2d_chunks.txt). */
+int pmwd_ctx_set_fft2d_chunk(pmwd_ctx* ctx, int planes);
 
 /* ---- instrumentation (no reference counterpart; used by bench.py) -------------------- */
 /* Number of hand-written kernels launched by this process so far. */

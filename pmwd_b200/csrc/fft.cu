@@ -5,6 +5,8 @@
 // on the caller's stream (cufftSetStream per call).  The 1/N of numpy's 'backward' norm is a
 // separate fused scale pass here only when a caller asks for it outside the force pipeline
 // (the force pipeline folds it into the k-space kernel's `scale`).
+#include <stdlib.h>
+
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -17,6 +19,7 @@ namespace pmwd {
 struct PlanPair {
   cufftHandle r2c = 0, c2r = 0;
   size_t work = 0;
+  int chunk = 0;     // 2-D plans only: planes per cuFFT call (0 = the whole batch in one call)
 };
 
 }  // namespace pmwd
@@ -28,6 +31,7 @@ struct pmwd_ctx {
   std::map<std::tuple<int, long long, long long>, cufftHandle> xplans;   // strided 1-D C2C
   void* work = nullptr;
   size_t work_bytes = 0;
+  int fft2d_chunk = -1;    // planes per call of the (y, z) transforms; -1 = PMWD_FFT2D_CHUNK or the default
 };
 
 namespace pmwd {
@@ -94,13 +98,20 @@ static int find_plans2d(pmwd_ctx* ctx, const int32_t* shape, PlanPair* out) {
   return PMWD_OK;
 }
 
-// in[nx][ny][nz] real -> out[nx][ny][nz/2+1]: R2C over (y, z) for every x plane
+// in[nx][ny][nz] real -> out[nx][ny][nz/2+1]: R2C over (y, z) for every x plane.
+// cuFFT runs a 2-D transform as two passes over the whole batch, i.e. the intermediate array (8.6 GB at
+// 1024^3) goes out to DRAM and comes back.  The plans can be issued `chunk` planes at a time so that the second
+// pass could find the first one's output in the 126 MB L2 -- measured: no gain (profiles/r02_fft2d_chunks.txt),
+// so chunk = 0 (one call) unless pmwd_ctx_set_fft2d_chunk / PMWD_FFT2D_CHUNK says otherwise.
 int fft2d_r2c(pmwd_ctx* ctx, cudaStream_t st, const int32_t* shape, const float* in, void* out) {
   PlanPair pp;
   int rc = find_plans2d(ctx, shape, &pp);
   if (rc) return rc;
   PMWD_CUFFT_TRY(cufftSetStream(pp.r2c, st));
-  PMWD_CUFFT_TRY(cufftExecR2C(pp.r2c, const_cast<float*>(in), (cufftComplex*)out));
+  const int64_t pin = (int64_t)shape[1] * shape[2], pout = (int64_t)shape[1] * (shape[2] / 2 + 1);
+  const int step = pp.chunk > 0 ? pp.chunk : shape[0];
+  for (int x = 0; x < shape[0]; x += step)
+    PMWD_CUFFT_TRY(cufftExecR2C(pp.r2c, const_cast<float*>(in) + x * pin, (cufftComplex*)out + x * pout));
   return PMWD_OK;
 }
 
@@ -109,7 +120,10 @@ int fft2d_c2r(pmwd_ctx* ctx, cudaStream_t st, const int32_t* shape, void* in, fl
   int rc = find_plans2d(ctx, shape, &pp);
   if (rc) return rc;
   PMWD_CUFFT_TRY(cufftSetStream(pp.c2r, st));
-  PMWD_CUFFT_TRY(cufftExecC2R(pp.c2r, (cufftComplex*)in, out));
+  const int64_t pin = (int64_t)shape[1] * (shape[2] / 2 + 1), pout = (int64_t)shape[1] * shape[2];
+  const int step = pp.chunk > 0 ? pp.chunk : shape[0];
+  for (int x = 0; x < shape[0]; x += step)
+    PMWD_CUFFT_TRY(cufftExecC2R(pp.c2r, (cufftComplex*)in + x * pin, out + x * pout));
   return PMWD_OK;
 }
 
@@ -141,6 +155,15 @@ extern "C" int pmwd_ctx_destroy(pmwd_ctx* ctx) {
   if (ctx->work) cudaFree(ctx->work);
   cudaSetDevice(prev);
   delete ctx;
+  return PMWD_OK;
+}
+
+// Planes per cuFFT call of the (y, z) transforms for plans reserved AFTER this call: 0 = whole batch in one
+// call, -1 = PMWD_FFT2D_CHUNK or the L2-sized default.
+extern "C" int pmwd_ctx_set_fft2d_chunk(pmwd_ctx* ctx, int planes) {
+  PMWD_REQUIRE(ctx != nullptr, "null context");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->fft2d_chunk = planes;
   return PMWD_OK;
 }
 
@@ -189,14 +212,30 @@ extern "C" int pmwd_ctx_reserve(pmwd_ctx* ctx, int rank, const int32_t* shape) {
     long long n2[2] = {shape[1], shape[2]};
     long long nzc = shape[2] / 2 + 1;
     size_t v1 = 0, v2 = 0;
+    // planes per call: the largest divisor of the batch that keeps one chunk's intermediate array
+    // (chunk * ny * nzc complex64) within the L2-resident budget
+    int want = ctx->fft2d_chunk;
+    if (want < 0) {
+      const char* e = getenv("PMWD_FFT2D_CHUNK");
+      want = e ? atoi(e) : -1;
+    }
+    // measured at 1024^3 (profiles/r02_fft2d_chunks.txt): every chunk size is SLOWER than one call for the
+    // whole batch (3.74 ms; 64 planes per call 3.95, 8 planes 4.96): cuFFT's small-batch launches do not fill
+    // the GPU and nothing is gained from L2.  Default = one call; the knob stays for other shapes / parts.
+    if (want < 0) want = 0;
+    int chunk = 0;
+    if (want > 0 && want < shape[0])
+      for (int c = want; c >= 1; --c) if (shape[0] % c == 0) { chunk = c; break; }
+    p2.chunk = chunk;
+    const long long batch = chunk > 0 ? chunk : shape[0];
     PMWD_CUFFT_TRY(cufftCreate(&p2.r2c));
     PMWD_CUFFT_TRY(cufftSetAutoAllocation(p2.r2c, 0));
     PMWD_CUFFT_TRY(cufftMakePlanMany64(p2.r2c, 2, n2, nullptr, 1, (long long)shape[1] * shape[2], nullptr, 1,
-                                       (long long)shape[1] * nzc, CUFFT_R2C, shape[0], &v1));
+                                       (long long)shape[1] * nzc, CUFFT_R2C, batch, &v1));
     PMWD_CUFFT_TRY(cufftCreate(&p2.c2r));
     PMWD_CUFFT_TRY(cufftSetAutoAllocation(p2.c2r, 0));
     PMWD_CUFFT_TRY(cufftMakePlanMany64(p2.c2r, 2, n2, nullptr, 1, (long long)shape[1] * nzc, nullptr, 1,
-                                       (long long)shape[1] * shape[2], CUFFT_C2R, shape[0], &v2));
+                                       (long long)shape[1] * shape[2], CUFFT_C2R, batch, &v2));
     p2.work = v1 > v2 ? v1 : v2;
     if (p2.work > ctx->work_bytes) {
       PMWD_CUDA_TRY(cudaDeviceSynchronize());
