@@ -235,6 +235,8 @@ size_t pmwd_sweep_scratch_bytes(const pmwd_cic_desc* d);
  * valid table (true by construction for sorted keys). */
 int pmwd_sweep_table(void* stream, const pmwd_cic_desc* d, int ty, int bw, const uint32_t* keys,
                      uint32_t* table, void* status);
+/* 1 if `sweep` matches the descriptor (same slab planes, scratch large enough): the tiled kernels would run. */
+int pmwd_sweep_usable(const pmwd_cic_desc* d, const pmwd_sweep* sweep);
 /* Stragglers (particles outside their tile's window) of the last recording sweep; synchronises. */
 long long pmwd_sweep_last_stragglers(void* stream, const pmwd_sweep* sweep);
 /* acc[N][3] = (gather(f0), gather(f1), gather(f2)) in one pass (gravity.py:61-70), optionally

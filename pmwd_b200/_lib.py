@@ -113,6 +113,7 @@ _SIGNATURES = {
     'pmwd_sweep_scratch_bytes': (_sz, [_descp]),
     'pmwd_sweep_table': (_i, [_vp, _descp, _i, _i, _vp, _vp, _vp]),
     'pmwd_sweep_last_stragglers': (C.c_longlong, [_vp, _vp]),
+    'pmwd_sweep_usable': (_i, [_descp, _vp]),
     'pmwd_cell_sort_scratch_bytes': (_sz, [_descp]),
     'pmwd_cell_sort_perm': (_i, [_vp, _descp, _vp, _vp, _vp, _vp, _sz, _i, _i]),
     'pmwd_cell_sort_sorted_keys': (_vp, [_descp, _vp]),

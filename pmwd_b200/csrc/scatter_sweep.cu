@@ -589,6 +589,16 @@ bool sweep_usable(const pmwd_cic_desc* d, const pmwd_sweep* sw) {
   return sw->scratch_bytes >= sweep_scratch_bytes(d->ptcl_num);
 }
 
+}  // namespace pmwd
+
+// 1 if `sweep` (table + scratch) matches the mesh descriptor, i.e. pmwd_scatter_sweep / the sweep argument of
+// pmwd_force* would use the tiled kernels; 0: the per-particle RED kernel is the one to call.
+extern "C" int pmwd_sweep_usable(const pmwd_cic_desc* d, const pmwd_sweep* sweep) {
+  return (d && sweep && pmwd::sweep_usable(d, sweep)) ? 1 : 0;
+}
+
+namespace pmwd {
+
 // One channel: mesh (NOT pre-zeroed by the caller) <- deposit of val[p * vstride] (or vscalar).
 // reuse_stragglers: the list recorded by an earlier call with the same particles is used again.
 int scatter_sweep(cudaStream_t st, const pmwd_cic_desc* d, const pmwd_sweep* sw, const void* pmid,

@@ -428,8 +428,10 @@ class SlabForce:
             self._ext3 = torch.empty((3,) + shape, dtype=conf.float_dtype, device=dev)
         return self._ext1, self._ext3
 
-    def _mesh_forces(self, pmid, disp, Om, h):
-        """Particles -> the three force meshes with halos, ``[3][mx+2h][My][Mz]``."""
+    def _mesh_forces(self, pmid, disp, Om, h, sweep=None):
+        """Particles -> the three force meshes with halos, ``[3][mx+2h][My][Mz]``.  ``sweep``: the store's
+        ``sweep.SweepState``; if its table was built for this very slab + halo the deposit goes through the
+        tiled kernels (csrc/scatter_sweep.cu), else through the per-particle RED kernel."""
         conf, comm = self.conf, self.comm
         lib = _lib.lib()
         dev = disp.device
@@ -438,10 +440,15 @@ class SlabForce:
         desc = self._desc(pmid, h)
         st = _lib.stream_ptr(dev)
         val = float(np.float32(conf.mesh_size / conf.ptcl_num))       # scatter.py:37-39
+        self._swept = sweep is not None and sweep.usable(desc)
         with TIMERS('scatter'):
-            ext1.zero_()
-            _lib.check(lib.pmwd_scatter_soa(st, C.byref(desc), _lib.ptr(pmid), _lib.ptr(disp), None, val, 1,
-                                            _lib.ptr(ext1), None, None), 'pmwd_scatter_soa')
+            if self._swept:
+                _lib.check(lib.pmwd_scatter_sweep(st, C.byref(desc), sweep.arg(), _lib.ptr(pmid), _lib.ptr(disp), None,
+                                                  val, 1, _lib.ptr(ext1), None, None), 'pmwd_scatter_sweep')
+            else:
+                ext1.zero_()
+                _lib.check(lib.pmwd_scatter_soa(st, C.byref(desc), _lib.ptr(pmid), _lib.ptr(disp), None, val, 1,
+                                                _lib.ptr(ext1), None, None), 'pmwd_scatter_soa')
         with TIMERS('halo'):
             rho = comm.halo_reduce(ext1, h)
         fused = bool(lib.pmwd_xpass_supported(Mx)) and os.environ.get('PMWD_XPASS', '1') != '0'
@@ -664,12 +671,12 @@ class SlabForce:
         with TIMERS('fft2d_c2r'):
             comm._irfft2(comm._p2p_view(3, (mx, My, nzc)), My, Mz, out=rc[h:h + mx])
 
-    def force(self, pmid, disp, Om, acc, kick_vel=None, kick_factor=0.0, next_kd=None):
+    def force(self, pmid, disp, Om, acc, kick_vel=None, kick_factor=0.0, next_kd=None, sweep=None):
         """``next_kd = (K1_next, D_next)``: also apply the next step's leading half-kick and
         drift in the gather pass (pipelined KDK, cf. ``pmwd_force_kdk``)."""
         with TIMERS('halo_width'):
             h = self._halo(pmid, disp)
-        desc, F, _ = self._mesh_forces(pmid, disp, Om, h)
+        desc, F, _ = self._mesh_forces(pmid, disp, Om, h, sweep)
         with TIMERS('gather'):
             st = _lib.stream_ptr(disp.device)
             if next_kd is not None:
@@ -682,20 +689,28 @@ class SlabForce:
                     st, C.byref(desc), _lib.ptr(pmid), _lib.ptr(disp), _lib.ptr(F[0]), _lib.ptr(F[1]),
                     _lib.ptr(F[2]), _lib.ptr(acc), _lib.ptr(kick_vel), float(kick_factor)), 'pmwd_gather3')
 
-    def force_adj(self, pmid, disp, Om, pi, acc, alpha):
+    def force_adj(self, pmid, disp, Om, pi, acc, alpha, sweep=None):
         conf, comm = self.conf, self.comm
         lib = _lib.lib()
         dev = disp.device
         Mx, My, Mz = conf.mesh_shape
         h = self._halo(pmid, disp)
-        desc, F, val = self._mesh_forces(pmid, disp, Om, h)
+        desc, F, val = self._mesh_forces(pmid, disp, Om, h, sweep)
         st = _lib.stream_ptr(dev)
         _lib.check(lib.pmwd_gather3(st, C.byref(desc), _lib.ptr(pmid), _lib.ptr(disp), _lib.ptr(F[0]),
                                     _lib.ptr(F[1]), _lib.ptr(F[2]), _lib.ptr(acc), None, 0.0), 'pmwd_gather3')
         # V_i = scatter(pi_i) (gather.py:113), halos reduced
-        V = torch.zeros_like(F)
-        _lib.check(lib.pmwd_scatter_soa(st, C.byref(desc), _lib.ptr(pmid), _lib.ptr(disp), _lib.ptr(pi), 0.0, 3,
-                                        _lib.ptr(V[0]), _lib.ptr(V[1]), _lib.ptr(V[2])), 'pmwd_scatter_soa')
+        if self._swept:
+            # three tiled deposits (they overwrite V; the straggler list of the density deposit is re-recorded
+            # by the first one and reused by the other two)
+            V = torch.empty_like(F)
+            _lib.check(lib.pmwd_scatter_sweep(st, C.byref(desc), sweep.arg(), _lib.ptr(pmid), _lib.ptr(disp),
+                                              _lib.ptr(pi), 0.0, 3, _lib.ptr(V[0]), _lib.ptr(V[1]), _lib.ptr(V[2])),
+                       'pmwd_scatter_sweep')
+        else:
+            V = torch.zeros_like(F)
+            _lib.check(lib.pmwd_scatter_soa(st, C.byref(desc), _lib.ptr(pmid), _lib.ptr(disp), _lib.ptr(pi), 0.0, 3,
+                                            _lib.ptr(V[0]), _lib.ptr(V[1]), _lib.ptr(V[2])), 'pmwd_scatter_soa')
         Vs = comm.halo_reduce(V, h)
         fused = bool(lib.pmwd_xpass_supported(Mx)) and os.environ.get('PMWD_XPASS', '1') != '0'
         p2p = fused and comm.setup_p2p(dev)
@@ -867,6 +882,8 @@ class SlabStepper:
         store.desc_fn = lambda pmid: force._desc(pmid, max(force.h_alloc, 1))
         if os.environ.get('PMWD_MIGRATE', '1') != '0' and comm.size > 1:
             store.migrator = comm              # Eulerian ownership: re-assigned at every storage re-sort
+            # ... which keeps the halos narrow and stable: the tiled deposit's table stays valid between re-sorts
+            store.slab_sweep = os.environ.get('PMWD_SLAB_SWEEP', '1') != '0'
 
     @property
     def nsteps(self):
@@ -888,7 +905,8 @@ class SlabStepper:
         if i + 1 < self.nsteps:
             k1n, dn, _ = self.inner.factors(i + 1)
             nxt = (k1n, dn)
-        self.force.force(a['pmid'], a['disp'], float(self.cosmo.Omega_m), a['acc'], a['vel'], k2, next_kd=nxt)
+        self.force.force(a['pmid'], a['disp'], float(self.cosmo.Omega_m), a['acc'], a['vel'], k2, next_kd=nxt,
+                         sweep=self.store.sweep)
         self.pre = nxt is not None
         self.i += 1
         self.store.maybe_reorder(sync_max=self.comm.allreduce_max)

@@ -104,6 +104,7 @@ class _Store:
         self.sweep = None          # sweep.SweepState: table + scratch of the tiled deposit
         self.migrator = None       # dist.SlabComm: particles move to the rank that owns their current x plane
         self.migrations = 0
+        self.slab_sweep = False    # slab runs: keep the storage in the tiled deposit's order as well
 
     def setup_sweep(self):
         """Tiled deposit (csrc/scatter_sweep.cu) for the single-device fast path: the storage is sorted
@@ -164,6 +165,16 @@ class _Store:
             self._alt = self._perm = None
             self.migrations += 1
         desc = self.desc_fn(a['pmid']) if self.desc_fn is not None else _force_desc(a['pmid'], conf)
+        if self.slab_sweep and self.desc_fn is not None and _sweep.enabled(conf):
+            # slab + halo planes: the table follows the descriptor of THIS re-sort (a later change of the
+            # halo width makes it unusable until the next one; the RED kernel takes over meanwhile)
+            if self.sweep is None:
+                st = _sweep.SweepState(desc, dev)
+                self.sweep = st if st.ty > 0 else None
+                self.slab_sweep = self.sweep is not None
+            else:
+                self.sweep.ok = False
+                self.sweep.fit(desc)
         if self.lag is None:
             self.lag = torch.arange(n, dtype=torch.int32, device=dev)   # bit pattern of uint32
         if self._perm is None or self._perm.numel() != n:
@@ -612,6 +623,7 @@ def nbody_adj(ptcl, ptcl_cot, obsvbl_cot, cosmo, conf, reverse=False, _slab=None
             import os
             if os.environ.get('PMWD_MIGRATE', '1') != '0' and _slab.comm.size > 1:
                 store.migrator = _slab.comm
+                store.slab_sweep = os.environ.get('PMWD_SLAB_SWEEP', '1') != '0'
         sync_max = _slab.comm.allreduce_max if _slab is not None else None
         m0 = store.arrays['disp'].abs().max()
         m0 = sync_max(m0) if sync_max is not None else float(m0)     # one decision for all ranks
@@ -663,7 +675,7 @@ def nbody_adj(ptcl, ptcl_cot, obsvbl_cot, cosmo, conf, reverse=False, _slab=None
             flush_pending()
             a = store.arrays
             if _slab is not None:
-                _slab.force_adj(a['pmid'], a['disp'], Om, a['pi'], a['acc'], a['alpha'])
+                _slab.force_adj(a['pmid'], a['disp'], Om, a['pi'], a['acc'], a['alpha'], sweep=store.sweep)
             else:
                 force_adj_into(a['pmid'], a['disp'], Om, conf, a['pi'], a['acc'], a['alpha'],
                                sweep=store.sweep_arg())

@@ -34,13 +34,26 @@ class SweepState:
         if self.ty <= 0:
             return
         self.lx = lx
-        self.nx_ext = int(desc.mesh_shape[0])
-        self.table = torch.zeros(lib.pmwd_sweep_table_bytes(C.byref(desc), self.ty, self.bw) // 4,
-                                 dtype=torch.int32, device=dev)
-        self.scratch = torch.empty(lib.pmwd_sweep_scratch_bytes(C.byref(desc)), dtype=torch.uint8, device=dev)
+        self.table = self.scratch = None
         self.status = torch.zeros(2, dtype=torch.int64, device=dev)
         self._struct = None
+        self.fit(desc)
+
+    def fit(self, desc):
+        """Size the table / scratch for this descriptor (slab runs: the planes held change with the halo
+        width, the particle count with every migration); anything that has to be re-allocated invalidates
+        the state until the next :meth:`build`."""
+        lib = _lib.lib()
+        self.nx_ext = int(desc.mesh_shape[0])
         self.n = int(desc.ptcl_num)
+        tb = lib.pmwd_sweep_table_bytes(C.byref(desc), self.ty, self.bw) // 4
+        if self.table is None or self.table.numel() != tb:
+            self.table = torch.zeros(tb, dtype=torch.int32, device=self.dev)
+            self.ok = False
+        sb = lib.pmwd_sweep_scratch_bytes(C.byref(desc))
+        if self.scratch is None or self.scratch.numel() < sb:
+            self.scratch = torch.empty(sb + sb // 8, dtype=torch.uint8, device=self.dev)    # room to grow
+            self.ok = False
 
     def _make_struct(self, desc):
         s = _lib.Sweep()
@@ -60,6 +73,7 @@ class SweepState:
         if self.ty <= 0:
             return False
         lib = _lib.lib()
+        self.fit(desc)
         with torch.cuda.device(self.dev):
             _lib.check(lib.pmwd_sweep_table(_lib.stream_ptr(self.dev), C.byref(desc), self.ty, self.bw, keys_ptr,
                                             _lib.ptr(self.table), _lib.ptr(self.status)), 'pmwd_sweep_table')
@@ -78,6 +92,12 @@ class SweepState:
         if not self.ok or self._struct is None:
             return None
         return C.byref(self._struct)
+
+    def usable(self, desc):
+        """True if the C library would run the tiled kernels for this descriptor (slab runs: the table
+        was built for the same planes)."""
+        a = self.arg()
+        return a is not None and bool(_lib.lib().pmwd_sweep_usable(C.byref(desc), a))
 
     def stragglers(self):
         if not self.ok:

@@ -172,3 +172,55 @@ def test_nbody_same_result_with_and_without_tiles(tiled):
     ref = O.nbody(dict(ic), ocosmo, oconf)
     err = np.abs(out.disp.cpu().numpy() - ref['disp']) / conf.cell_size
     assert np.sqrt(np.mean(err ** 2)) <= 1e-4 and np.quantile(err, 0.999) <= 1e-4
+
+
+@pytest.mark.parametrize('x0, mx, h', [(16, 32, 8), (48, 16, 8), (0, 32, 4)])
+def test_sweep_scatter_on_a_slab_descriptor(x0, mx, h):
+    """Multi-GPU composition on one GPU: the mesh array is an x-slab of `mx` planes + `h` halo planes on either
+    side (possibly wrapping around the box), particles whose stencil leaves it are dropped plane by plane
+    (enmesh's rule for a smaller target mesh, pm_util.py:147-154).  With the storage sorted for THAT descriptor
+    the tiled deposit must equal the per-particle RED kernel on the same descriptor -- freshly sorted, after a
+    drift, and for three channels -- and must refuse a descriptor with another halo width."""
+    from pmwd_b200 import _lib
+    from pmwd_b200.nbody import _Store
+    from pmwd_b200.scatter import make_desc
+    pm, conf, oconf, pmid, disp, ptcl = _setup((32, 16, 32), 1.0)
+    Mx, My, Mz = conf.mesh_shape
+    cell32 = float(np.float32(conf.cell_size))
+
+    def desc_fn(pmid_, hh=h):
+        return make_desc(conf, pmid_, (mx + 2 * hh, My, Mz), 1, ((x0 - hh) * cell32, 0.0, 0.0), None)
+
+    store = _Store(conf, dict(pmid=ptcl.pmid.clone(), disp=ptcl.disp.clone(), vel=torch.zeros_like(ptcl.disp),
+                              acc=torch.zeros_like(ptcl.disp)))
+    store.desc_fn = desc_fn
+    store.slab_sweep = True
+    store.reorder()
+    assert store.sweep is not None and store.sweep.ok
+    lib, st = _lib.lib(), _lib.stream_ptr()
+    g = torch.Generator(device='cuda').manual_seed(2)
+
+    def both(nch):
+        a = store.arrays
+        desc = desc_fn(a['pmid'])
+        assert store.sweep.usable(desc)
+        assert not store.sweep.usable(desc_fn(a['pmid'], h + 4))
+        shape = (mx + 2 * h, My, Mz)
+        val = torch.randn(a['disp'].shape, device='cuda', generator=g) if nch == 3 else None
+        got = [torch.full(shape, -3.25, device='cuda') for _ in range(nch)]
+        ref = [torch.zeros(shape, device='cuda') for _ in range(nch)]
+        extra = lambda m: [_lib.ptr(m[1]) if nch == 3 else None, _lib.ptr(m[2]) if nch == 3 else None]
+        _lib.check(lib.pmwd_scatter_sweep(st, C.byref(desc), store.sweep.arg(), _lib.ptr(a['pmid']), _lib.ptr(a['disp']),
+                                          _lib.ptr(val), 0.125, nch, _lib.ptr(got[0]), *extra(got)), 'pmwd_scatter_sweep')
+        _lib.check(lib.pmwd_scatter_soa(st, C.byref(desc), _lib.ptr(a['pmid']), _lib.ptr(a['disp']), _lib.ptr(val), 0.125,
+                                        nch, _lib.ptr(ref[0]), *extra(ref)), 'pmwd_scatter_soa')
+        torch.cuda.synchronize()
+        for c in range(nch):
+            scale = max(ref[c].abs().max().item(), 1.0)
+            assert (got[c] - ref[c]).abs().max().item() <= 2e-6 * scale, (nch, c)
+        assert ref[0].abs().sum().item() > 0
+
+    both(1)
+    store.arrays['disp'] += 0.6 * conf.cell_size * torch.randn(store.arrays['disp'].shape, device='cuda', generator=g)
+    both(1)
+    both(3)
