@@ -314,11 +314,21 @@ size_t pmwd_cell_sort_scratch_bytes(const pmwd_cic_desc* d);
 int pmwd_cell_sort_perm(void* stream, const pmwd_cic_desc* d, const void* pmid, const float* disp,
                         uint32_t* perm, void* scratch, size_t scratch_bytes, int ty, int bw);
 const uint32_t* pmwd_cell_sort_sorted_keys(const pmwd_cic_desc* d, const void* scratch);
+/* Two-source variant for slab runs with Eulerian ownership: sorts the virtual concatenation of
+ * A = (pmid, disp)[0, nA) -- rows with ownerA[i] != rank (pmwd_slab_owner) have left for another rank and sort
+ * behind everything -- and the arrivals B = (pmidB, dispB)[0, ptcl_num - nA).  d->ptcl_num = nA + nB.  The
+ * first ptcl_num - (rows gone) entries of perm are the new storage order (indices >= nA refer to B). */
+int pmwd_cell_sort_perm2(void* stream, const pmwd_cic_desc* d, const void* pmid, const float* disp, int64_t nA,
+                         const uint8_t* ownerA, int rank, const void* pmidB, const float* dispB, uint32_t* perm,
+                         void* scratch, size_t scratch_bytes, int ty, int bw);
 /* For each of `narr` row-major arrays (row_bytes[a] bytes per particle, even):
  * inverse == 0: dst[i] = src[perm[i]];  inverse != 0: dst[perm[i]] = src[i]. */
 int pmwd_permute_rows(void* stream, int64_t n, const uint32_t* perm, int narr,
                       const void* const* src, void* const* dst, const int32_t* row_bytes,
                       int inverse);
+/* dst[i] = (srcA ++ srcB)[perm[i]], i < n: rows [0, nA) of the concatenation are srcA's, the rest srcB's. */
+int pmwd_permute_rows2(void* stream, int64_t n, const uint32_t* perm, int narr, const void* const* srcA,
+                       int64_t nA, const void* const* srcB, void* const* dst, const int32_t* row_bytes);
 
 /* Slab bookkeeping in one pass (int16 pmid, 3-D): owner[p] = rank whose x-slab holds particle p's base plane
  * (may be NULL), *need = halo planes the slab [x0, x0 + mx) needs for these particles (device int32, reset here). */

@@ -30,19 +30,32 @@ struct SortParams {
   int nyc;          // ceil(ny >> shift)
   int ty, bw;       // > 0: sweep layout (y / ty, z / bw, x, y % ty, z % bw) -- scatter_sweep.cu
   float cell;
+  // two sources (slab runs, pmwd_cell_sort_perm2): rows [0, nA) come from (pmid, disp), rows [nA, n) from
+  // (pmidB, dispB); a row of A whose owner is another rank gets the largest key and sorts behind everything
+  int64_t nA;
+  const uint8_t* ownerA;
+  int rank;
 };
+
+constexpr uint32_t SORT_KEY_GONE = 0xffffffffu;
 
 __global__ void __launch_bounds__(256)
 sort_keys_kernel(SortParams P, const short* __restrict__ pmid, const float* __restrict__ disp,
+                 const short* __restrict__ pmidB, const float* __restrict__ dispB,
                  uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P.n;
        p += (int64_t)gridDim.x * blockDim.x) {
+    vals[p] = (uint32_t)p;
+    const bool fromA = p < P.nA;
+    if (fromA && P.ownerA && P.ownerA[p] != (uint8_t)P.rank) { keys[p] = SORT_KEY_GONE; continue; }
+    const short* pm = fromA ? pmid + 3 * p : pmidB + 3 * (p - P.nA);
+    const float* dp = fromA ? disp + 3 * p : dispB + 3 * (p - P.nA);
     int c[3];
     const int nn[3] = {P.nx, P.ny, P.nz};
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      float t = __fdiv_rn(disp[3 * p + a], P.cell);
-      c[a] = wrap_index((int)pmid[3 * p + a] + (int)floorf(t), nn[a]);
+      float t = __fdiv_rn(dp[a], P.cell);
+      c[a] = wrap_index((int)pm[a] + (int)floorf(t), nn[a]);
     }
     int lx = c[0] - P.xoff;           // slab-local plane keeps the key below 2^32 on big meshes
     if (lx < 0) lx += P.nx;
@@ -58,13 +71,14 @@ sort_keys_kernel(SortParams P, const short* __restrict__ pmid, const float* __re
     } else {
       keys[p] = (uint32_t)(((int64_t)(lx >> P.shift) * P.nyc + (c[1] >> P.shift)) * P.nz + c[2]);
     }
-    vals[p] = (uint32_t)p;
   }
 }
 
 struct RowArgs {
   int narr;
   const void* src[8];
+  const void* srcB[8];   // second source (gather only): rows nA .. of the virtual concatenation; may be null
+  int64_t nA;
   void* dst[8];
   int words[8];     // row size in 2-byte words (3 for int16[3], 6 for float[3], 2 for uint32)
 };
@@ -75,15 +89,19 @@ permute_rows_kernel(int64_t n, const uint32_t* __restrict__ perm, RowArgs A) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t j = perm[i];
-    const int64_t from = INVERSE ? i : j, to = INVERSE ? j : i;
+    int64_t from = INVERSE ? i : j;
+    const int64_t to = INVERSE ? j : i;
+    const bool second = !INVERSE && from >= A.nA;
+    if (second) from -= A.nA;
     for (int a = 0; a < A.narr; ++a) {
       const int w = A.words[a];
+      const void* base = second ? A.srcB[a] : A.src[a];
       if ((w & 1) == 0) {   // rows of 4-byte words
-        const uint32_t* s = reinterpret_cast<const uint32_t*>(A.src[a]) + from * (w >> 1);
+        const uint32_t* s = reinterpret_cast<const uint32_t*>(base) + from * (w >> 1);
         uint32_t* d = reinterpret_cast<uint32_t*>(A.dst[a]) + to * (w >> 1);
         for (int k = 0; k < (w >> 1); ++k) d[k] = __ldg(s + k);
       } else {
-        const uint16_t* s = reinterpret_cast<const uint16_t*>(A.src[a]) + from * w;
+        const uint16_t* s = reinterpret_cast<const uint16_t*>(base) + from * w;
         uint16_t* d = reinterpret_cast<uint16_t*>(A.dst[a]) + to * w;
         for (int k = 0; k < w; ++k) d[k] = __ldg(s + k);
       }
@@ -120,7 +138,8 @@ extern "C" size_t pmwd_cell_sort_scratch_bytes(const pmwd_cic_desc* d) {
   if (!d || d->dim != 3) return 0;
   int64_t ncell = (int64_t)d->mesh_shape[0] * d->mesh_shape[1] * d->mesh_shape[2];
   SortLayout L;
-  if (sort_layout(d->ptcl_num, ilog2_ceil(ncell) < 1 ? 1 : ilog2_ceil(ncell), &L)) return 0;
+  (void)ncell;
+  if (sort_layout(d->ptcl_num, 32, &L)) return 0;      // sized for full-width keys (pmwd_cell_sort_perm2's mask)
   return L.total;
 }
 
@@ -129,14 +148,25 @@ extern "C" const uint32_t* pmwd_cell_sort_sorted_keys(const pmwd_cic_desc* d, co
   return (const uint32_t*)((const char*)scratch + 2 * align_up((size_t)d->ptcl_num * 4));
 }
 
-extern "C" int pmwd_cell_sort_perm(void* stream, const pmwd_cic_desc* d, const void* pmid,
-                                   const float* disp, uint32_t* perm, void* scratch,
-                                   size_t scratch_bytes, int ty, int bw) {
+// Two sources (slab runs with Eulerian ownership): the rows to sort are the virtual concatenation of
+// A = (pmid, disp)[0, nA) -- of which the rows with ownerA[i] != rank have left for another rank -- and the
+// arrivals B = (pmidB, dispB)[0, nB).  d->ptcl_num must be nA + nB (it sizes the scratch layout).  perm has
+// nA + nB entries; the rows that left sort to the end, i.e. the first nA + nB - (number gone) entries are the
+// new storage order.  ownerA == NULL: nobody left; nB == 0: no arrivals.
+extern "C" int pmwd_cell_sort_perm2(void* stream, const pmwd_cic_desc* d, const void* pmid, const float* disp,
+                                    int64_t nA, const uint8_t* ownerA, int rank, const void* pmidB,
+                                    const float* dispB, uint32_t* perm, void* scratch, size_t scratch_bytes,
+                                    int ty, int bw) {
   PMWD_REQUIRE(d && d->dim == 3 && d->pmid_bytes == 2 && !d->general,
                "cell sort supports the 3-D int16 fast path");
   PMWD_REQUIRE(perm && scratch, "null buffer");
   SortParams P;
   P.n = d->ptcl_num;
+  PMWD_REQUIRE(nA >= 0 && nA <= P.n, "nA must lie in [0, ptcl_num]");
+  PMWD_REQUIRE(nA == P.n || (pmidB && dispB), "null second source");
+  P.nA = nA;
+  P.ownerA = ownerA;
+  P.rank = rank;
   P.nx = d->wrap_shape[0]; P.ny = d->wrap_shape[1]; P.nz = d->wrap_shape[2];
   P.nx_ext = d->mesh_shape[0];
   P.xoff = slab_xoff(d);
@@ -155,12 +185,13 @@ extern "C" int pmwd_cell_sort_perm(void* stream, const pmwd_cic_desc* d, const v
   int64_t ncell = (int64_t)P.nx_ext * P.ny * P.nz;
   PMWD_REQUIRE(ncell <= ((int64_t)1 << 32) && P.n < ((int64_t)1 << 32),
                "cell sort needs mesh_size <= 2^32 and ptcl_num < 2^32 per device");
+  PMWD_REQUIRE(!ownerA || ncell < ((int64_t)1 << 32), "the ownership mask needs mesh_size < 2^32 (one spare key)");
   if (P.n == 0) return PMWD_OK;
-  PMWD_REQUIRE(pmid && disp, "null buffer");
-  int end_bit = ilog2_ceil(ncell);
+  PMWD_REQUIRE(nA == 0 || (pmid && disp), "null buffer");
+  int end_bit = ownerA ? 32 : ilog2_ceil(ncell);
   if (end_bit < 1) end_bit = 1;
   SortLayout L;
-  int rc = sort_layout(P.n, end_bit, &L);
+  int rc = sort_layout(P.n, 32, &L);     // as pmwd_cell_sort_scratch_bytes
   if (rc) return rc;
   if (scratch_bytes < L.total) {
     set_error("cell sort needs %zu bytes of scratch, got %zu", L.total, scratch_bytes);
@@ -172,11 +203,45 @@ extern "C" int pmwd_cell_sort_perm(void* stream, const pmwd_cic_desc* d, const v
   uint32_t* keys_in = (uint32_t*)(base + L.keys_in);
   uint32_t* vals_in = (uint32_t*)(base + L.vals_in);
   uint32_t* keys_out = (uint32_t*)(base + L.keys_out);
-  sort_keys_kernel<<<grid_for(P.n, 256, 8), 256, 0, st>>>(P, (const short*)pmid, disp, keys_in, vals_in);
+  sort_keys_kernel<<<grid_for(P.n, 256, 8), 256, 0, st>>>(P, (const short*)pmid, disp, (const short*)pmidB, dispB,
+                                                          keys_in, vals_in);
   PMWD_LAUNCH_CHECK();
   size_t cub_bytes = L.cub_bytes;
   PMWD_CUDA_TRY(cub::DeviceRadixSort::SortPairs(base + L.cub, cub_bytes, keys_in, keys_out, vals_in,
                                                 perm, P.n, 0, end_bit, st));
+  return PMWD_OK;
+}
+
+extern "C" int pmwd_cell_sort_perm(void* stream, const pmwd_cic_desc* d, const void* pmid,
+                                   const float* disp, uint32_t* perm, void* scratch,
+                                   size_t scratch_bytes, int ty, int bw) {
+  PMWD_REQUIRE(d != nullptr, "null descriptor");
+  return pmwd_cell_sort_perm2(stream, d, pmid, disp, d->ptcl_num, nullptr, 0, nullptr, nullptr, perm, scratch,
+                              scratch_bytes, ty, bw);
+}
+
+// dst[i] = (srcA ++ srcB)[perm[i]] for i < n: gather from the virtual concatenation of two sources (rows
+// [0, nA) of srcA, then srcB) -- the companion of pmwd_cell_sort_perm2.
+extern "C" int pmwd_permute_rows2(void* stream, int64_t n, const uint32_t* perm, int narr, const void* const* srcA,
+                                  int64_t nA, const void* const* srcB, void* const* dst, const int32_t* row_bytes) {
+  PMWD_REQUIRE(n >= 0 && narr >= 1 && narr <= 8 && nA >= 0, "bad sizes");
+  PMWD_REQUIRE(perm && srcA && dst && row_bytes, "null buffer");
+  if (n == 0) return PMWD_OK;
+  RowArgs A;
+  A.narr = narr;
+  A.nA = nA;
+  for (int a = 0; a < narr; ++a) {
+    PMWD_REQUIRE((nA == 0 || srcA[a]) && dst[a] && srcA[a] != dst[a], "permute needs distinct non-null buffers");
+    PMWD_REQUIRE(row_bytes[a] > 0 && row_bytes[a] % 2 == 0 && row_bytes[a] <= 64, "bad row size");
+    A.src[a] = srcA[a];
+    A.srcB[a] = srcB ? srcB[a] : nullptr;
+    A.dst[a] = dst[a];
+    A.words[a] = row_bytes[a] / 2;
+  }
+  cudaStream_t st = as_stream(stream);
+  StageTimer timer(ST_OTHER, st);
+  permute_rows_kernel<false><<<grid_for(n, 256, 8), 256, 0, st>>>(n, perm, A);
+  PMWD_LAUNCH_CHECK();
   return PMWD_OK;
 }
 
@@ -188,10 +253,12 @@ extern "C" int pmwd_permute_rows(void* stream, int64_t n, const uint32_t* perm, 
   if (n == 0) return PMWD_OK;
   RowArgs A;
   A.narr = narr;
+  A.nA = (int64_t)1 << 62;      // single source
   for (int a = 0; a < narr; ++a) {
     PMWD_REQUIRE(src[a] && dst[a] && src[a] != dst[a], "permute needs distinct non-null buffers");
     PMWD_REQUIRE(row_bytes[a] > 0 && row_bytes[a] % 2 == 0 && row_bytes[a] <= 64, "bad row size");
     A.src[a] = src[a];
+    A.srcB[a] = nullptr;
     A.dst[a] = dst[a];
     A.words[a] = row_bytes[a] / 2;
   }

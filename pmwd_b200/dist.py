@@ -884,6 +884,7 @@ class SlabStepper:
             store.migrator = comm              # Eulerian ownership: re-assigned at every storage re-sort
             # ... which keeps the halos narrow and stable: the tiled deposit's table stays valid between re-sorts
             store.slab_sweep = os.environ.get('PMWD_SLAB_SWEEP', '1') != '0'
+            store.timers = TIMERS
 
     @property
     def nsteps(self):

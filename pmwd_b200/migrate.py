@@ -107,6 +107,46 @@ def to_eulerian_movers(arrays, conf, group=None):
     return out, (send, recv)
 
 
+def exchange_movers(arrays, conf, group=None):
+    """What the integrator's re-sort uses: the owner of every local particle (uint8, one fused pass,
+    ``pmwd_slab_owner``) and the ARRIVALS only -- the particles that stay are neither copied nor compacted;
+    the caller drops the rows with ``owner != rank`` (``pmwd_cell_sort_perm2`` sorts them to the end).
+    Returns ``(owner, arrivals, nmove)``: ``arrivals`` maps every name to the received rows (by source rank),
+    ``nmove`` is the number of local rows that left."""
+    from . import _lib
+    nranks, rank = dist.get_world_size(group), dist.get_rank(group)
+    pmid, disp = arrays['pmid'], arrays['disp']
+    n = pmid.shape[0]
+    dev = disp.device
+    Mx = conf.mesh_shape[0]
+    if disp.is_cuda and pmid.dtype == torch.int16:
+        owner = torch.empty(n, dtype=torch.uint8, device=dev)
+        need = torch.empty(1, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().pmwd_slab_owner(_lib.stream_ptr(dev), n, _lib.ptr(pmid), _lib.ptr(disp),
+                                                  float(conf.cell_size), Mx, nranks, 0, Mx // nranks,
+                                                  _lib.ptr(owner), _lib.ptr(need)), 'pmwd_slab_owner')
+    else:
+        owner = owner_rank(pmid[:, 0], disp[:, 0], conf, nranks).to(torch.uint8)
+    idx_move = (owner != rank).nonzero(as_tuple=False).squeeze(1)
+    dest = owner.index_select(0, idx_move).to(torch.int64)
+    idx_move = idx_move.index_select(0, torch.sort(dest, stable=True).indices)     # grouped by destination rank
+    send, recv = _counts(dest, nranks, group)
+    ssz, rsz = send.tolist(), recv.tolist()
+    nrecv = int(sum(rsz))
+    arrivals = {}
+    for name, a in arrays.items():
+        rows = a.index_select(0, idx_move).contiguous()
+        row_bytes = a.element_size()
+        for d in a.shape[1:]:
+            row_bytes *= int(d)
+        src = rows.view(torch.uint8).reshape(rows.shape[0], row_bytes)
+        got = torch.empty((nrecv, row_bytes), dtype=torch.uint8, device=a.device)
+        dist.all_to_all_single(got, src, output_split_sizes=rsz, input_split_sizes=ssz, group=group)
+        arrivals[name] = got.view(a.dtype).reshape((nrecv,) + tuple(a.shape[1:]))
+    return owner, arrivals, int(idx_move.numel())
+
+
 def to_lagrangian(arrays, ptcl_num, group=None):
     """Inverse of any sequence of ``to_eulerian`` calls: send every particle back to the rank that
     holds its index range of the reference's particle array and sort locally by ``arrays['lag']``

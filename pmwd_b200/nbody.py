@@ -94,7 +94,8 @@ class _Store:
         self.conf = conf
         self.arrays = dict(arrays)
         self.lag = None            # uint32 view as int32 tensor: Lagrangian index of each slot
-        self._alt = None
+        self._alt = None           # spare buffer set of the re-sort (name -> tensor with >= N rows)
+        self._back = None          # the full-capacity tensors behind `arrays` / `lag` when they are views
         self._perm = None
         self._scratch = None
         self.steps_since = 0
@@ -105,6 +106,11 @@ class _Store:
         self.migrator = None       # dist.SlabComm: particles move to the rank that owns their current x plane
         self.migrations = 0
         self.slab_sweep = False    # slab runs: keep the storage in the tiled deposit's order as well
+        self.timers = None         # dist.TIMERS in slab runs: 'migrate' / 'resort' phases of the bench line
+
+    def _timed(self, name):
+        import contextlib
+        return self.timers(name) if self.timers is not None else contextlib.nullcontext()
 
     def setup_sweep(self):
         """Tiled deposit (csrc/scatter_sweep.cu) for the single-device fast path: the storage is sorted
@@ -146,25 +152,41 @@ class _Store:
         return True
 
     def reorder(self):
-        conf, a = self.conf, self.arrays
+        moved = None
+        if self.migrator is not None:
+            with self._timed('migrate'):
+                moved = self._migrate()
+        with self._timed('resort'):
+            self._resort(moved)
+
+    def _migrate(self):
+        """Eulerian ownership (slab runs): every particle moves to the rank that owns its current base plane.
+        Only the movers travel (pmwd_b200/migrate.py); the particles that stay are NOT compacted here -- the
+        re-sort that follows reads the old arrays and the arrivals as one virtual array and drops the rows
+        that left (``pmwd_cell_sort_perm2`` / ``pmwd_permute_rows2``).  `lag` carries the GLOBAL Lagrangian
+        index so that lagrangian() can send everything home again."""
+        from . import migrate
+        a, comm = self.arrays, self.migrator
         dev = a['disp'].device
         n = a['disp'].shape[0]
+        if self.lag is None:
+            self.lag = comm.rank * n + torch.arange(n, dtype=torch.int32, device=dev)
+        owner, arrivals, nmove = migrate.exchange_movers(dict(a, lag=self.lag), self.conf, comm.group)
+        self.migrations += 1
+        return owner, arrivals, nmove
+
+    def _resort(self, moved=None):
+        conf, a = self.conf, self.arrays
+        dev = a['disp'].device
+        nA = a['disp'].shape[0]
         lib = _lib.lib()
-        if self.migrator is not None:
-            # Eulerian ownership (slab runs): every particle moves to the rank that owns its current base
-            # plane (one variable-size all-to-all per array, pmwd_b200/migrate.py); `lag` then carries the
-            # GLOBAL Lagrangian index so that lagrangian() can send everything home again
-            from . import migrate
-            comm = self.migrator
-            if self.lag is None:
-                self.lag = comm.rank * n + torch.arange(n, dtype=torch.int32, device=dev)
-            got, _ = migrate.to_eulerian_movers(dict(a, lag=self.lag), conf, comm.group)
-            self.lag = got.pop('lag')
-            self.arrays = a = got
-            n = a['disp'].shape[0]
-            self._alt = self._perm = None
-            self.migrations += 1
+        if self.lag is None:
+            self.lag = torch.arange(nA, dtype=torch.int32, device=dev)   # bit pattern of uint32
+        owner, arrivals, nmove = moved if moved is not None else (None, None, 0)
+        nB = arrivals['disp'].shape[0] if arrivals is not None else 0
+        ntot, n = nA + nB, nA + nB - nmove          # rows to sort, rows of the new storage
         desc = self.desc_fn(a['pmid']) if self.desc_fn is not None else _force_desc(a['pmid'], conf)
+        desc.ptcl_num = n
         if self.slab_sweep and self.desc_fn is not None and _sweep.enabled(conf):
             # slab + halo planes: the table follows the descriptor of THIS re-sort (a later change of the
             # halo width makes it unusable until the next one; the RED kernel takes over meanwhile)
@@ -175,39 +197,49 @@ class _Store:
             else:
                 self.sweep.ok = False
                 self.sweep.fit(desc)
-        if self.lag is None:
-            self.lag = torch.arange(n, dtype=torch.int32, device=dev)   # bit pattern of uint32
-        if self._perm is None or self._perm.numel() != n:
-            self._perm = torch.empty(n, dtype=torch.int32, device=dev)
-            self._alt = {k: torch.empty_like(v) for k, v in a.items()}
-            self._alt['lag'] = torch.empty_like(self.lag)
-        # the sort's key width follows the mesh the descriptor spans (slab + halos, which grow
-        # during a run): re-query the scratch size every time and grow the buffer when needed
-        nbytes = lib.pmwd_cell_sort_scratch_bytes(C.byref(desc))
+        cur = dict(a, lag=self.lag)
+        names = list(cur)
+        # the spare buffer set: capacity with some room when the row count changes with every migration
+        # (exact-size buffers would mean fresh device allocations at every re-sort)
+        alt = self._alt
+        if alt is None or set(alt) != set(names) or any(alt[k].shape[0] < n for k in names):
+            cap = n if self.migrator is None else n + n // 16
+            alt = {k: torch.empty((cap,) + tuple(v.shape[1:]), dtype=v.dtype, device=dev) for k, v in cur.items()}
+        if self._perm is None or self._perm.numel() < ntot:
+            self._perm = torch.empty(ntot if self.migrator is None else ntot + ntot // 16, dtype=torch.int32, device=dev)
+        # the sort's scratch follows the row count and the mesh the descriptor spans: re-query every time
+        sdesc = self.desc_fn(a['pmid']) if self.desc_fn is not None else _force_desc(a['pmid'], conf)
+        sdesc.ptcl_num = ntot
+        nbytes = lib.pmwd_cell_sort_scratch_bytes(C.byref(sdesc))
         if self._scratch is None or self._scratch.numel() < nbytes:
-            self._scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            self._scratch = torch.empty(nbytes + (nbytes // 16 if self.migrator is not None else 0), dtype=torch.uint8,
+                                        device=dev)
         with torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
             ty, bw = (self.sweep.ty, self.sweep.bw) if self.sweep is not None else (0, 0)
-            _lib.check(lib.pmwd_cell_sort_perm(st, C.byref(desc), _lib.ptr(a['pmid']), _lib.ptr(a['disp']),
-                                               _lib.ptr(self._perm), _lib.ptr(self._scratch),
-                                               self._scratch.numel(), ty, bw), 'pmwd_cell_sort_perm')
-            names = list(a) + ['lag']
-            cur = dict(a, lag=self.lag)
-            src = (C.c_void_p * len(names))(*[cur[k].data_ptr() for k in names])
-            dst = (C.c_void_p * len(names))(*[self._alt[k].data_ptr() for k in names])
+            rank = self.migrator.rank if self.migrator is not None else 0
+            _lib.check(lib.pmwd_cell_sort_perm2(
+                st, C.byref(sdesc), _lib.ptr(a['pmid']), _lib.ptr(a['disp']), nA, _lib.ptr(owner), rank,
+                _lib.ptr(arrivals['pmid']) if nB else None, _lib.ptr(arrivals['disp']) if nB else None,
+                _lib.ptr(self._perm), _lib.ptr(self._scratch), self._scratch.numel(), ty, bw), 'pmwd_cell_sort_perm2')
+            vp = C.c_void_p * len(names)
+            src = vp(*[cur[k].data_ptr() for k in names])
+            srcB = vp(*[arrivals[k].data_ptr() for k in names]) if nB else None
+            dst = vp(*[alt[k].data_ptr() for k in names])
             rb = (C.c_int32 * len(names))(*[cur[k].element_size() * (cur[k].shape[1] if cur[k].ndim > 1 else 1)
                                             for k in names])
-            _lib.check(lib.pmwd_permute_rows(st, n, _lib.ptr(self._perm), len(names), src, dst, rb, 0),
-                       'pmwd_permute_rows')
-        new = {k: self._alt[k] for k in a}
-        new_lag = self._alt['lag']
-        self._alt = dict(a, lag=self.lag)
-        self.arrays, self.lag = new, new_lag
+            _lib.check(lib.pmwd_permute_rows2(st, n, _lib.ptr(self._perm), len(names), src, nA, srcB, dst, rb),
+                       'pmwd_permute_rows2')
+        # ping-pong: the buffers behind the old arrays become the spare set (checked for capacity next time)
+        self._alt = self._back if self._back is not None else cur
+        self._back = alt
+        new = {k: alt[k][:n] for k in names}
+        self.lag = new.pop('lag')
+        self.arrays = new
         self.reorders += 1
         if self.sweep is not None:
             # table of the new order from the sort's own keys (valid by construction: no read-back)
-            keys = lib.pmwd_cell_sort_sorted_keys(C.byref(desc), _lib.ptr(self._scratch))
+            keys = lib.pmwd_cell_sort_sorted_keys(C.byref(sdesc), _lib.ptr(self._scratch))
             self.sweep.build(desc, C.c_void_p(keys))
 
     def lagrangian(self, *names):
@@ -624,6 +656,8 @@ def nbody_adj(ptcl, ptcl_cot, obsvbl_cot, cosmo, conf, reverse=False, _slab=None
             if os.environ.get('PMWD_MIGRATE', '1') != '0' and _slab.comm.size > 1:
                 store.migrator = _slab.comm
                 store.slab_sweep = os.environ.get('PMWD_SLAB_SWEEP', '1') != '0'
+                from .dist import TIMERS as _T
+                store.timers = _T
         sync_max = _slab.comm.allreduce_max if _slab is not None else None
         m0 = store.arrays['disp'].abs().max()
         m0 = sync_max(m0) if sync_max is not None else float(m0)     # one decision for all ranks

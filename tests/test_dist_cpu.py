@@ -96,6 +96,13 @@ WORKER = textwrap.dedent('''
     back2 = migrate.to_lagrangian(eul2, n_all)
     for k in ('pmid', 'disp', 'vel', 'lag'):
         assert torch.equal(back2[k], mine[k]), k
+    # what the re-sort consumes: owner mask + arrivals only (the stayers are not copied)
+    owner, arr, nmove = migrate.exchange_movers(arrs, conf)
+    stay = owner == r
+    assert nmove == int((~stay).sum()) and len(arr['lag']) == len(eul['lag']) - int(stay.sum())
+    assert sorted(torch.cat([mine['lag'][stay], arr['lag']]).tolist()) == sorted(eul['lag'].tolist())
+    np.testing.assert_array_equal(arr['vel'].numpy(), vel_all[arr['lag'].numpy()])
+    np.testing.assert_array_equal(arr['pmid'].numpy(), pmid_all[arr['lag'].numpy()])
     print('rank', r, 'ok')
 ''')
 

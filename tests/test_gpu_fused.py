@@ -124,3 +124,55 @@ def test_slab_owner_matches_tensor_formula(nranks, rank):
     right = d + (2 - mx)
     ref = torch.where(d < mx, right.clamp(min=0), torch.minimum(right, Mx - d)).max().item()
     assert need.item() == ref
+
+
+@pytest.mark.parametrize('ty, bw', [(0, 0), (8, 16)])
+def test_two_source_sort_and_permute(ty, bw):
+    """pmwd_cell_sort_perm2 + pmwd_permute_rows2 (the slab re-sort with Eulerian ownership: old rows minus the
+    ones that left, plus the arrivals, read as one virtual array) == compacting by hand and sorting one array."""
+    import pmwd_b200 as pm
+    from pmwd_b200 import _lib
+    from pmwd_b200.gravity import _force_desc
+    lib, st = _lib.lib(), _lib.stream_ptr()
+    conf = pm.Configuration(1., (16, 16, 16), mesh_shape=2)
+    ptcl = pm.Particles.gen_grid(conf)
+    disp = (ptcl.disp + 2.5 * conf.cell_size * _rand(ptcl.disp.shape, 11)).contiguous()
+    vel = _rand(ptcl.disp.shape, 12)
+    n_all = disp.shape[0]
+    nA = 3000
+    g = torch.Generator(device='cuda').manual_seed(13)
+    owner = (torch.rand(nA, device='cuda', generator=g) < 0.2).to(torch.uint8)      # 1 = left for "rank 1"
+    A = dict(pmid=ptcl.pmid[:nA].contiguous(), disp=disp[:nA].contiguous(), vel=vel[:nA].contiguous())
+    B = dict(pmid=ptcl.pmid[nA:].contiguous(), disp=disp[nA:].contiguous(), vel=vel[nA:].contiguous())
+    nB = n_all - nA
+    keep = owner == 0
+    n = int(keep.sum()) + nB
+
+    def sort(desc, pmidA, dispA, na, own, pmidB, dispB):
+        perm = torch.empty(desc.ptcl_num, dtype=torch.int32, device='cuda')
+        scratch = torch.empty(lib.pmwd_cell_sort_scratch_bytes(C.byref(desc)), dtype=torch.uint8, device='cuda')
+        _lib.check(lib.pmwd_cell_sort_perm2(st, C.byref(desc), _lib.ptr(pmidA), _lib.ptr(dispA), na, _lib.ptr(own), 0,
+                                            _lib.ptr(pmidB), _lib.ptr(dispB), _lib.ptr(perm), _lib.ptr(scratch),
+                                            scratch.numel(), ty, bw), 'pmwd_cell_sort_perm2')
+        return perm
+
+    desc = _force_desc(ptcl.pmid, conf)
+    desc.ptcl_num = n_all
+    perm = sort(desc, A['pmid'], A['disp'], nA, owner, B['pmid'], B['disp'])
+    names = ('pmid', 'disp', 'vel')
+    got = {k: torch.empty((n,) + tuple(A[k].shape[1:]), dtype=A[k].dtype, device='cuda') for k in names}
+    vp = C.c_void_p * 3
+    rb = (C.c_int32 * 3)(6, 12, 12)
+    _lib.check(lib.pmwd_permute_rows2(st, n, _lib.ptr(perm), 3, vp(*[A[k].data_ptr() for k in names]), nA,
+                                      vp(*[B[k].data_ptr() for k in names]), vp(*[got[k].data_ptr() for k in names]), rb),
+               'pmwd_permute_rows2')
+    # by hand: compact, concatenate, single-source stable sort
+    cat = {k: torch.cat([A[k][keep], B[k]]).contiguous() for k in names}
+    desc1 = _force_desc(cat['pmid'], conf)
+    perm1 = sort(desc1, cat['pmid'], cat['disp'], n, None, None, None)
+    torch.cuda.synchronize()
+    for k in names:
+        assert torch.equal(got[k], cat[k][perm1.long()]), k
+    # the rows that left are the tail of the permutation
+    tail = perm[n:].long()
+    assert tail.numel() == nA - int(keep.sum()) and bool((tail < nA).all()) and bool((owner[tail] == 1).all())
