@@ -365,6 +365,12 @@ def run_ours(args):
                                vel=torch.randn(disp.shape, device=dev, generator=g))
             del store, stepper, disp, vel
             torch.cuda.empty_cache()
+            # warm-up (untimed): the adjoint over the last 3 steps of the section -- first launches of the
+            # adjoint kernels and, above all, the caching allocator's first device allocations of the ~25 GB of
+            # particle / cotangent / workspace buffers (200 ms of cudaMalloc inside the timed region otherwise:
+            # 114 vs 124 ms per step pair between two identical runs, gpurun r2x)
+            pm.nbody_adj(final, cot, None, cosmo, conf, _a_nbody=section[-min(4, len(section)):])
+            torch.cuda.synchronize()
             _lib.profile_enable(True); _lib.profile_read()
             la0 = _lib.launch_count()
             torch.cuda.synchronize()

@@ -1038,6 +1038,10 @@ def run_bench(args):
                             vel=torch.randn(disp.shape, device=dev, generator=g))
             del store, stepper, disp, vel
             torch.cuda.empty_cache()
+            # warm-up (untimed): the adjoint over the last 3 steps -- first launches and the allocator's first
+            # device allocations of the adjoint's buffers stay out of the timed region (cf. bench.py)
+            nbody_adj_slab(final, cot, cosmo, conf, comm, force=force, _a_nbody=section[-min(4, len(section)):])
+            TIMERS.read()
             TIMERS.on = True
             la0 = _lib.launch_count()
             torch.cuda.synchronize(); dist.barrier()
