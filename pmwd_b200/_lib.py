@@ -217,12 +217,15 @@ class Context:
 
     @classmethod
     def get(cls, device):
+        """The context of (device, current CUDA stream): cuFFT plans share one work area per context, so
+        two streams of one device must not share a context (``include/pmwd_b200.h``)."""
         device = torch.device(device)
         if device.index is None:
             device = torch.device('cuda', torch.cuda.current_device())
-        ctx = cls._cache.get(device)
+        key = (device, torch.cuda.current_stream(device).cuda_stream)
+        ctx = cls._cache.get(key)
         if ctx is None:
-            ctx = cls._cache[device] = cls(device)
+            ctx = cls._cache[key] = cls(device)
         return ctx
 
     def reserve(self, shape):

@@ -17,14 +17,21 @@ _workspaces = {}
 
 
 def _workspace(dev, nbytes):
-    """One persistent device workspace per device, grown on demand (memory is laid out once
-    and reused by every force evaluation; 180 GB of HBM3e make this cheap)."""
-    buf = _workspaces.get(dev)
+    """One persistent device workspace per (device, CUDA stream), grown on demand: memory is laid out once
+    and reused by every force evaluation enqueued on that stream (180 GB of HBM3e make this cheap); force
+    evaluations on different streams of one device get different workspaces and cannot race on the mesh
+    buffers.  A buffer is allocated while its stream is current, so the caching allocator's stream-ordered
+    reuse makes dropping the old one on growth safe."""
+    dev = torch.device(dev)
+    if dev.index is None:
+        dev = torch.device('cuda', torch.cuda.current_device())
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream)
+    buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
-        _workspaces.pop(dev, None)
+        _workspaces.pop(key, None)
         buf = None
         buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        _workspaces[dev] = buf
+        _workspaces[key] = buf
     return buf
 
 
