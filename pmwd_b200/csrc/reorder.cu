@@ -207,8 +207,14 @@ extern "C" int pmwd_cell_sort_perm2(void* stream, const pmwd_cic_desc* d, const 
                                                           keys_in, vals_in);
   PMWD_LAUNCH_CHECK();
   size_t cub_bytes = L.cub_bytes;
+  // sweep layout with a power-of-two tile width: the z position inside a tile row (the low log2(bw) bits) is
+  // left out of the sort -- neither the tiled deposit nor the gathers' sector counts depend on the order of
+  // the ~8 particles of one 256-byte row, and 24 instead of 30 key bits is one radix pass less
+  int begin_bit = 0;
+  if (ty > 0 && (bw & (bw - 1)) == 0 && !getenv("PMWD_SORT_FULL")) begin_bit = ilog2_ceil(bw);
+  if (begin_bit >= end_bit) begin_bit = 0;
   PMWD_CUDA_TRY(cub::DeviceRadixSort::SortPairs(base + L.cub, cub_bytes, keys_in, keys_out, vals_in,
-                                                perm, P.n, 0, end_bit, st));
+                                                perm, P.n, begin_bit, end_bit, st));
   return PMWD_OK;
 }
 

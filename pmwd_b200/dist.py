@@ -934,6 +934,16 @@ def nbody_step_slab(a_prev, a_next, ptcl, cosmo, conf, comm, force=None):
     return Particles(conf, ptcl.pmid, a['disp'], vel=a['vel'], acc=a['acc'])
 
 
+def nbody_step_slab_host(a_prev, a_next, host, cosmo, conf, comm, force=None, out=None, acc_resident=True):
+    """``nbody_step`` on this rank's slab with the state in (pinned) HOST memory: the copy schedule of
+    ``pmwd_b200.nbody_step_host`` (pmid resident, no re-upload of the accelerations the previous call wrote,
+    displacement download under the force, acceleration download under the next call's uploads) around the
+    collective slab force.  Collective: every rank calls it with its own Lagrangian slab."""
+    from .nbody import nbody_step_host
+    force = force or SlabForce(conf, comm)
+    return nbody_step_host(a_prev, a_next, host, cosmo, conf, out=out, acc_resident=acc_resident, _slab=force)
+
+
 def step_slab(a_prev, a_next, store, cosmo, conf, force):
     """One KDK step (default ``symp_splits``; nbody.py:121-140) on the store's arrays."""
     from .nbody import drift_factor, kick_factor, _f32, _kick_drift
@@ -1082,28 +1092,31 @@ def run_bench(args):
             host[k].copy_(getattr(p0, k))
         del p0
         torch.cuda.empty_cache()
-        h2d = sum(t.numel() * t.element_size() for t in host.values()) * world
+        # pmid stays resident after its first upload, acc is not re-uploaded (device mirror of the array the
+        # previous step wrote): disp + vel up, disp + vel + acc down, every step
+        h2d = sum(host[k].numel() * host[k].element_size() for k in ('disp', 'vel')) * world
         d2h = sum(host[k].numel() * host[k].element_size() for k in ('disp', 'vel', 'acc')) * world
 
         def e2e_step(j):
-            d = {k: host[k].to(dev, non_blocking=True) for k in host}
-            p = Particles(conf, d['pmid'], d['disp'], vel=d['vel'], acc=d['acc'])
-            p = nbody_step_slab(a[j], a[j + 1], p, cosmo, conf, comm, force)
-            for k in ('disp', 'vel', 'acc'):
-                host[k].copy_(getattr(p, k), non_blocking=True)
+            nbody_step_slab_host(a[j], a[j + 1], host, cosmo, conf, comm, force, out=host)
         e2e_step(0)
+        e2e_step(1 % nsched)                       # second warm-up: from here on acc is the array the API wrote
         torch.cuda.synchronize(); dist.barrier()
         e0.record()
-        for j in range(1, 1 + ke):
+        for j in range(2, 2 + ke):
             e2e_step(j % nsched)
         e1.record()
         torch.cuda.synchronize(); dist.barrier()
         ems = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
         dist.all_reduce(ems, op=dist.ReduceOp.MAX)
         ems = float(ems)
+        from .nbody import nbody_host_release
+        nbody_host_release()
     e2e = {'value': Np * ke / (ems * 1e-3), 'unit': 'particle-updates/s', 'steps': ke, 'ms_per_step': ems / ke,
            'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-           'api': 'pmwd_b200.dist.nbody_step_slab on per-rank pinned host slabs'}
+           'api': 'pmwd_b200.dist.nbody_step_slab_host: per-rank pinned host slabs in and out every step (disp, vel up; '
+                  'disp, vel, acc down; acc not re-uploaded; disp download under the force, acc download under the '
+                  'next step\'s uploads)'}
     if rank == 0:
         Nm = conf.mesh_size
         peak, peak_src = B._peaks()

@@ -438,7 +438,7 @@ def nbody_host_release(dev=None):
     _pmid_resident.clear()
 
 
-def nbody_step_host(a_prev, a_next, host, cosmo, conf, out=None, acc_resident=True):
+def nbody_step_host(a_prev, a_next, host, cosmo, conf, out=None, acc_resident=True, _slab=None):
     """``nbody_step`` for a state that lives in (pinned) HOST memory: ``host`` and the returned
     dict map ``'pmid'`` (int16), ``'disp'``, ``'vel'``, ``'acc'`` (float32) to CPU tensors of
     shape ``(N, 3)``; ``out`` may supply the output buffers (``pmid`` is passed through).
@@ -460,6 +460,9 @@ def nbody_step_host(a_prev, a_next, host, cosmo, conf, out=None, acc_resident=Tr
     Everything is enqueued asynchronously: ``torch.cuda.synchronize(device)`` before reading the outputs
     (synchronising the current stream covers ``disp`` and ``vel`` only).  Default KDK splitting on the 3-D
     fast path; other configurations take the plain copy -> ``integrate`` -> copy route.
+
+    ``_slab`` (internal, ``dist.nbody_step_slab_host``): a ``dist.SlabForce``; the arrays are then one rank's
+    Lagrangian x-slab of a slab-decomposed run and the force is the collective one.
     """
     dev = torch.device(conf.device if getattr(conf, 'device', None) is not None else 'cuda')
     if dev.type != 'cuda' or not torch.cuda.is_available():
@@ -492,6 +495,8 @@ def nbody_step_host(a_prev, a_next, host, cosmo, conf, out=None, acc_resident=Tr
         pmid = _resident_pmid(host['pmid'], dev)
         p = Particles(conf, pmid, m.disp, vel=m.vel, acc=m.acc)
         default = tuple(tuple(x) for x in conf.symp_splits) == ((0, 0.5), (1, 0.5))
+        if _slab is not None and not (default and _fast_ok(p, conf)):
+            raise NotImplementedError('the slab integrator implements the default KDK splitting on the 3-D fast path')
         if not (default and _fast_ok(p, conf)):
             if m.acc_event is not None:
                 cur.wait_event(m.acc_event)
@@ -516,7 +521,10 @@ def nbody_step_host(a_prev, a_next, host, cosmo, conf, out=None, acc_resident=Tr
         if m.acc_event is not None:
             cur.wait_event(m.acc_event)          # the force overwrites m.acc: the previous call's download of it
             m.acc_event = None                   # (running under this call's uploads) must have finished
-        force_into(p.pmid, p.disp, float(cosmo.Omega_m), conf, p.acc, p.vel, K2)
+        if _slab is not None:
+            _slab.force(p.pmid, p.disp, float(cosmo.Omega_m), p.acc, p.vel, K2)
+        else:
+            force_into(p.pmid, p.disp, float(cosmo.Omega_m), conf, p.acc, p.vel, K2)
         m.mark('force', cur)
         out['vel'].copy_(m.vel, non_blocking=True)
         m.mark('vel_down', cur)

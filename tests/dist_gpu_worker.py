@@ -55,6 +55,22 @@ def main():
     ea = rms(alpha - alpha_ref[sl]) / rms(alpha_ref)
     assert e < 1e-5 and ea < 1e-4, (e, ea)
 
+    # ---- host-array step on the slab (pmwd_b200.dist.nbody_step_slab_host) == the device step, twice (the
+    # second call takes acc from the device mirror)
+    a_n = conf.a_nbody.tolist()
+    acc0 = torch.empty_like(ic.disp)
+    F.force(pm_l, ic.disp.contiguous(), float(cosmo.Omega_m), acc0)
+    pdev = pm.Particles(conf, pm_l, ic.disp.contiguous(), vel=ic.vel.contiguous(), acc=acc0)
+    host = {k: getattr(pdev, k).cpu().pin_memory() for k in ('pmid', 'disp', 'vel', 'acc')}
+    for j in range(2):
+        pdev = pd.nbody_step_slab(a_n[j], a_n[j + 1], pdev, cosmo, conf, comm, F)
+        host = pd.nbody_step_slab_host(a_n[j], a_n[j + 1], host, cosmo, conf, comm, F, out=host if j else None)
+        torch.cuda.synchronize()
+        for k in ('disp', 'vel', 'acc'):
+            r_ = getattr(pdev, k).cpu()
+            assert (host[k] - r_).abs().max().item() <= 1e-5 * r_.abs().max().item(), (j, k)
+    pm.nbody_host_release()
+
     # ---- N-body: 10 steps, slab vs single GPU (positions within 1e-4 cell RMS / p99.9)
     ref, _ = pm.nbody(ref_ic, None, cosmo, conf)
     out = pd.nbody_slab(pm.Particles(conf, pm_l, ref_ic.disp[sl].contiguous(), vel=ref_ic.vel[sl].contiguous()),
