@@ -14,6 +14,9 @@
 // All HBM / L2-atomic bound.  Particles arrive in Lagrangian (C-order) sequence, so the 32
 // lanes of a warp touch 2..4 contiguous z-rows of the mesh: loads coalesce and the float32
 // reductions (RED.E.ADD.F32 / .F32x2) land in the same L2 sectors.
+#include <math.h>
+#include <stdlib.h>
+
 #include "cic.cuh"
 
 namespace pmwd {
@@ -24,7 +27,14 @@ struct FastParams {
   int nx_ext;       // x planes held by the mesh array (== nx on one GPU; slab + halos otherwise)
   int xoff;         // global x index of plane 0 of the array (offset / cell, an integer)
   float cell;
+  float inv_cell;   // 1 / cell if cell is a power of two (the product is then the same correctly rounded
+                    // number as the IEEE division, at a tenth of its instructions), else 0
 };
+
+// x / cell in float32, bitwise what the reference's division gives (pm_util.py:133, gather.py:108-110)
+__device__ __forceinline__ float div_cell(float x, float cell, float inv_cell) {
+  return inv_cell != 0.f ? __fmul_rn(x, inv_cell) : __fdiv_rn(x, cell);
+}
 
 int slab_xoff(const pmwd_cic_desc* d);
 bool cic_is_fast(const pmwd_cic_desc* d);
@@ -39,9 +49,9 @@ struct Stencil3G : Stencil3 {
   float sx[2], sy[2], sz[2];
 };
 
-__device__ __forceinline__ void axis_fast(int pm, float disp, float cell, int n, int* idx, float* w,
+__device__ __forceinline__ void axis_fast(int pm, float disp, float cell, float inv_cell, int n, int* idx, float* w,
                                           float* s) {
-  float t = __fdiv_rn(disp, cell);
+  float t = div_cell(disp, cell, inv_cell);
   int i0 = (int)floorf(t);
 #pragma unroll
   for (int b = 0; b < 2; ++b) {
@@ -111,9 +121,9 @@ scatter_fast_kernel(FastParams P, const short* __restrict__ pmid, const float* _
     const bool active = p < P.n;
     const int64_t pp = active ? p : P.n - 1;
     Stencil3 s;
-    axis_fast(pmid[3 * pp + 0], disp[3 * pp + 0], P.cell, P.nx, s.ix, s.wx, nullptr);
-    axis_fast(pmid[3 * pp + 1], disp[3 * pp + 1], P.cell, P.ny, s.iy, s.wy, nullptr);
-    axis_fast(pmid[3 * pp + 2], disp[3 * pp + 2], P.cell, P.nz, s.iz, s.wz, nullptr);
+    axis_fast(pmid[3 * pp + 0], disp[3 * pp + 0], P.cell, P.inv_cell, P.nx, s.ix, s.wx, nullptr);
+    axis_fast(pmid[3 * pp + 1], disp[3 * pp + 1], P.cell, P.inv_cell, P.ny, s.iy, s.wy, nullptr);
+    axis_fast(pmid[3 * pp + 2], disp[3 * pp + 2], P.cell, P.inv_cell, P.nz, s.iz, s.wz, nullptr);
     // group key: the (global) base cell; inactive tail lanes get unique keys
     const unsigned long long key =
         active ? (unsigned long long)(((int64_t)s.ix[0] * P.ny + s.iy[0]) * P.nz + s.iz[0])
@@ -176,9 +186,9 @@ gather3_kernel(FastParams P, const short* __restrict__ pmid, const float* disp,
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P.n;
        p += (int64_t)gridDim.x * blockDim.x) {
     Stencil3 s;
-    axis_fast(pmid[3 * p + 0], disp[3 * p + 0], P.cell, P.nx, s.ix, s.wx, nullptr);
-    axis_fast(pmid[3 * p + 1], disp[3 * p + 1], P.cell, P.ny, s.iy, s.wy, nullptr);
-    axis_fast(pmid[3 * p + 2], disp[3 * p + 2], P.cell, P.nz, s.iz, s.wz, nullptr);
+    axis_fast(pmid[3 * p + 0], disp[3 * p + 0], P.cell, P.inv_cell, P.nx, s.ix, s.wx, nullptr);
+    axis_fast(pmid[3 * p + 1], disp[3 * p + 1], P.cell, P.inv_cell, P.ny, s.iy, s.wy, nullptr);
+    axis_fast(pmid[3 * p + 2], disp[3 * p + 2], P.cell, P.inv_cell, P.nz, s.iz, s.wz, nullptr);
     localize_x(P, s.ix);
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
     // neighbour order n = bx + 2 by + 4 bz (axis 0 = LSB, pm_util.py:95-97), summed sequentially
@@ -228,9 +238,9 @@ force_adj_gather_kernel(FastParams P, const short* __restrict__ pmid, const floa
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P.n;
        p += (int64_t)gridDim.x * blockDim.x) {
     Stencil3G<true> s;
-    axis_fast(pmid[3 * p + 0], disp[3 * p + 0], P.cell, P.nx, s.ix, s.wx, s.sx);
-    axis_fast(pmid[3 * p + 1], disp[3 * p + 1], P.cell, P.ny, s.iy, s.wy, s.sy);
-    axis_fast(pmid[3 * p + 2], disp[3 * p + 2], P.cell, P.nz, s.iz, s.wz, s.sz);
+    axis_fast(pmid[3 * p + 0], disp[3 * p + 0], P.cell, P.inv_cell, P.nx, s.ix, s.wx, s.sx);
+    axis_fast(pmid[3 * p + 1], disp[3 * p + 1], P.cell, P.inv_cell, P.ny, s.iy, s.wy, s.sy);
+    axis_fast(pmid[3 * p + 2], disp[3 * p + 2], P.cell, P.inv_cell, P.nz, s.iz, s.wz, s.sz);
     localize_x(P, s.ix);
     const float p0 = pi[3 * p + 0], p1 = pi[3 * p + 1], p2 = pi[3 * p + 2];
     float d[4][3];
@@ -267,10 +277,10 @@ force_adj_gather_kernel(FastParams P, const short* __restrict__ pmid, const floa
     }
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      float a = __fdiv_rn(d[0][j], P.cell);
-      a = __fadd_rn(a, __fdiv_rn(d[1][j], P.cell));
-      a = __fadd_rn(a, __fdiv_rn(d[2][j], P.cell));
-      a = __fadd_rn(a, __fdiv_rn(d[3][j], P.cell));
+      float a = div_cell(d[0][j], P.cell, P.inv_cell);
+      a = __fadd_rn(a, div_cell(d[1][j], P.cell, P.inv_cell));
+      a = __fadd_rn(a, div_cell(d[2][j], P.cell, P.inv_cell));
+      a = __fadd_rn(a, div_cell(d[3][j], P.cell, P.inv_cell));
       alpha[3 * p + j] = a;
     }
     if (acc) {
@@ -293,6 +303,11 @@ static int fast_params(const pmwd_cic_desc* d, FastParams* P) {
   P->nz = d->wrap_shape[2];
   P->nx_ext = d->mesh_shape[0];
   P->cell = (float)d->cell_size;
+  {
+    int e = 0;
+    const float m = frexpf(P->cell, &e);
+    P->inv_cell = (m == 0.5f && e > -100 && e < 100 && !getenv("PMWD_CIC_DIV")) ? 1.f / P->cell : 0.f;
+  }
   P->xoff = slab_xoff(d);
   return PMWD_OK;
 }

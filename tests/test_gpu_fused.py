@@ -176,3 +176,26 @@ def test_two_source_sort_and_permute(ty, bw):
     # the rows that left are the tail of the permutation
     tail = perm[n:].long()
     assert tail.numel() == nA - int(keep.sum()) and bool((tail < nA).all()) and bool((owner[tail] == 1).all())
+
+
+def test_reciprocal_cell_path_is_bitwise_the_division(monkeypatch):
+    """Power-of-two cells: x * (1 / cell) replaces the IEEE division x / cell (pm_util.py:133, gather.py:108-110)
+    in the per-particle CIC kernels; both are the correctly rounded value of the same real number, so forcing
+    the division (PMWD_CIC_DIV=1) must not change a single bit of acc or of the displacement cotangent."""
+    import pmwd_b200 as pm
+    from pmwd_b200.gravity import force_adj_into
+    n = 32
+    conf = pm.Configuration(1., (n, n, n), mesh_shape=2, scatter_mode='deterministic')
+    ptcl = pm.Particles.gen_grid(conf)
+    disp = (ptcl.disp + 2.3 * _rand(ptcl.disp.shape, 21)).contiguous()
+    pi = _rand(ptcl.disp.shape, 22)
+    out = []
+    for force_div in (False, True):
+        if force_div:
+            monkeypatch.setenv('PMWD_CIC_DIV', '1')
+        acc, alpha = torch.empty_like(disp), torch.empty_like(disp)
+        force_adj_into(ptcl.pmid, disp, 0.3, conf, pi, acc, alpha)
+        torch.cuda.synchronize()
+        out.append((acc, alpha))
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+    assert out[0][1].abs().max().item() > 0
