@@ -101,6 +101,9 @@ int pmwd_ctx_reserve(pmwd_ctx* ctx, int rank, const int32_t* shape);
  * plans reserved after the call; 0 = one call for the whole batch, -1 (default) = the PMWD_FFT2D_CHUNK
  * environment variable, else 0 (measured on B200: chunking is slower, profiles/r02_fft2d_chunks.txt). */
 int pmwd_ctx_set_fft2d_chunk(pmwd_ctx* ctx, int planes);
+/* Lab knob: row length (complex elements, >= nz/2+1, 0 = unpadded) of the half-spectrum of 2-D plans reserved
+ * afterwards (measures what 128-byte aligned spectrum rows would buy; pmwd_force* always use unpadded rows). */
+int pmwd_ctx_set_fft2d_pad(pmwd_ctx* ctx, int row_elems);
 
 /* ---- instrumentation (no reference counterpart; used by bench.py) -------------------- */
 /* Number of hand-written kernels launched by this process so far. */

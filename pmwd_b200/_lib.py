@@ -71,6 +71,7 @@ _SIGNATURES = {
     'pmwd_ctx_destroy': (_i, [_vp]),
     'pmwd_ctx_reserve': (_i, [_vp, _i, _i32p]),
     'pmwd_ctx_set_fft2d_chunk': (_i, [_vp, _i]),
+    'pmwd_ctx_set_fft2d_pad': (_i, [_vp, _i]),
     'pmwd_fft_r2c': (_i, [_vp, _vp, _i, _i32p, _vp, _vp]),
     'pmwd_fft_c2r': (_i, [_vp, _vp, _i, _i32p, _vp, _vp, _f]),
     'pmwd_fft2d_r2c': (_i, [_vp, _vp, _i32p, _vp, _vp]),

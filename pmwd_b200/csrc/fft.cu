@@ -20,6 +20,7 @@ struct PlanPair {
   cufftHandle r2c = 0, c2r = 0;
   size_t work = 0;
   int chunk = 0;     // 2-D plans only: planes per cuFFT call (0 = the whole batch in one call)
+  int pad = 0;       // 2-D plans only: row length of the half-spectrum (>= nz/2+1)
 };
 
 }  // namespace pmwd
@@ -32,6 +33,7 @@ struct pmwd_ctx {
   void* work = nullptr;
   size_t work_bytes = 0;
   int fft2d_chunk = -1;    // planes per call of the (y, z) transforms; -1 = PMWD_FFT2D_CHUNK or the default
+  int fft2d_pad = 0;       // lab: row length (complex elements) of the half-spectrum of the 2-D plans; 0 = nz/2+1
 };
 
 namespace pmwd {
@@ -108,7 +110,7 @@ int fft2d_r2c(pmwd_ctx* ctx, cudaStream_t st, const int32_t* shape, const float*
   int rc = find_plans2d(ctx, shape, &pp);
   if (rc) return rc;
   PMWD_CUFFT_TRY(cufftSetStream(pp.r2c, st));
-  const int64_t pin = (int64_t)shape[1] * shape[2], pout = (int64_t)shape[1] * (shape[2] / 2 + 1);
+  const int64_t pin = (int64_t)shape[1] * shape[2], pout = (int64_t)shape[1] * (pp.pad ? pp.pad : shape[2] / 2 + 1);
   const int step = pp.chunk > 0 ? pp.chunk : shape[0];
   for (int x = 0; x < shape[0]; x += step)
     PMWD_CUFFT_TRY(cufftExecR2C(pp.r2c, const_cast<float*>(in) + x * pin, (cufftComplex*)out + x * pout));
@@ -120,7 +122,7 @@ int fft2d_c2r(pmwd_ctx* ctx, cudaStream_t st, const int32_t* shape, void* in, fl
   int rc = find_plans2d(ctx, shape, &pp);
   if (rc) return rc;
   PMWD_CUFFT_TRY(cufftSetStream(pp.c2r, st));
-  const int64_t pin = (int64_t)shape[1] * (shape[2] / 2 + 1), pout = (int64_t)shape[1] * shape[2];
+  const int64_t pin = (int64_t)shape[1] * (pp.pad ? pp.pad : shape[2] / 2 + 1), pout = (int64_t)shape[1] * shape[2];
   const int step = pp.chunk > 0 ? pp.chunk : shape[0];
   for (int x = 0; x < shape[0]; x += step)
     PMWD_CUFFT_TRY(cufftExecC2R(pp.c2r, (cufftComplex*)in + x * pin, out + x * pout));
@@ -164,6 +166,15 @@ extern "C" int pmwd_ctx_set_fft2d_chunk(pmwd_ctx* ctx, int planes) {
   PMWD_REQUIRE(ctx != nullptr, "null context");
   std::lock_guard<std::mutex> lk(ctx->mu);
   ctx->fft2d_chunk = planes;
+  return PMWD_OK;
+}
+
+// Lab only (tools/lab/fft2d_pad.py): row length, in complex elements, of the half-spectrum the 2-D plans reserved
+// AFTER this call read / write (>= nz/2+1; 0 = unpadded).  The force pipeline does not use padded spectra.
+extern "C" int pmwd_ctx_set_fft2d_pad(pmwd_ctx* ctx, int row_elems) {
+  PMWD_REQUIRE(ctx != nullptr && row_elems >= 0, "bad arguments");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->fft2d_pad = row_elems;
   return PMWD_OK;
 }
 
@@ -228,14 +239,17 @@ extern "C" int pmwd_ctx_reserve(pmwd_ctx* ctx, int rank, const int32_t* shape) {
       for (int c = want; c >= 1; --c) if (shape[0] % c == 0) { chunk = c; break; }
     p2.chunk = chunk;
     const long long batch = chunk > 0 ? chunk : shape[0];
+    long long rembed[2] = {shape[1], shape[2]};
+    long long cembed[2] = {shape[1], ctx->fft2d_pad >= nzc ? ctx->fft2d_pad : nzc};
     PMWD_CUFFT_TRY(cufftCreate(&p2.r2c));
     PMWD_CUFFT_TRY(cufftSetAutoAllocation(p2.r2c, 0));
-    PMWD_CUFFT_TRY(cufftMakePlanMany64(p2.r2c, 2, n2, nullptr, 1, (long long)shape[1] * shape[2], nullptr, 1,
-                                       (long long)shape[1] * nzc, CUFFT_R2C, batch, &v1));
+    PMWD_CUFFT_TRY(cufftMakePlanMany64(p2.r2c, 2, n2, rembed, 1, rembed[0] * rembed[1], cembed, 1,
+                                       cembed[0] * cembed[1], CUFFT_R2C, batch, &v1));
     PMWD_CUFFT_TRY(cufftCreate(&p2.c2r));
     PMWD_CUFFT_TRY(cufftSetAutoAllocation(p2.c2r, 0));
-    PMWD_CUFFT_TRY(cufftMakePlanMany64(p2.c2r, 2, n2, nullptr, 1, (long long)shape[1] * nzc, nullptr, 1,
-                                       (long long)shape[1] * shape[2], CUFFT_C2R, batch, &v2));
+    PMWD_CUFFT_TRY(cufftMakePlanMany64(p2.c2r, 2, n2, cembed, 1, cembed[0] * cembed[1], rembed, 1,
+                                       rembed[0] * rembed[1], CUFFT_C2R, batch, &v2));
+    p2.pad = (int)cembed[1];
     p2.work = v1 > v2 ? v1 : v2;
     if (p2.work > ctx->work_bytes) {
       PMWD_CUDA_TRY(cudaDeviceSynchronize());
