@@ -74,6 +74,8 @@ typedef struct pmwd_sweep {
   int32_t reserved;
   void* scratch;          /* device, pmwd_sweep_scratch_bytes: work counters + straggler list */
   size_t scratch_bytes;
+  void* det_halo;         /* device, pmwd_sweep_det_halo_bytes, or NULL: per-tile halo arrays of the deterministic deposit */
+  size_t det_halo_bytes;
 } pmwd_sweep;
 
 /* Which kernels a descriptor selects: 0 = general path (csrc/cic_generic.cu); 1 = fused 3-D fast
@@ -238,6 +240,18 @@ size_t pmwd_sweep_scratch_bytes(const pmwd_cic_desc* d);
  * valid table (true by construction for sorted keys). */
 int pmwd_sweep_table(void* stream, const pmwd_cic_desc* d, int ty, int bw, const uint32_t* keys,
                      uint32_t* table, void* status);
+/* Deterministic variant (PMWD_SCATTER_DETERMINISTIC inside pmwd_force* when sweep->det_halo is set): one warp
+ * sweeps one (y, z) tile over all planes, tile-interior cells are stored, halo contributions go to per-tile
+ * arrays that a second kernel adds in a fixed order -- no float atomics, bitwise reproducible for storage that
+ * was sorted (pmwd_cell_sort_perm + pmwd_sweep_table) from the very pmid / disp it is called with.  A particle
+ * outside its tile's window would still be deposited (by REDs) and is counted: pmwd_sweep_det_violations
+ * (synchronises) must return 0; pmwd_sweep_det_reset clears the counter.  Whole periodic mesh only. */
+int pmwd_scatter_sweep_det(void* stream, const pmwd_cic_desc* d, const pmwd_sweep* sweep, const void* pmid,
+                           const float* disp, const float* val, float val_scalar, int nch, float* m0,
+                           float* m1, float* m2);
+size_t pmwd_sweep_det_halo_bytes(const pmwd_cic_desc* d, int ty, int bw);
+long long pmwd_sweep_det_violations(void* stream, const pmwd_sweep* sweep);
+int pmwd_sweep_det_reset(void* stream, const pmwd_sweep* sweep);
 /* 1 if `sweep` matches the descriptor (same slab planes, scratch large enough): the tiled kernels would run. */
 int pmwd_sweep_usable(const pmwd_cic_desc* d, const pmwd_sweep* sweep);
 /* Stragglers (particles outside their tile's window) of the last recording sweep; synchronises. */

@@ -48,6 +48,8 @@ class Sweep(C.Structure):
         ('reserved', C.c_int32),
         ('scratch', C.c_void_p),
         ('scratch_bytes', C.c_size_t),
+        ('det_halo', C.c_void_p),
+        ('det_halo_bytes', C.c_size_t),
     ]
 
 
@@ -115,6 +117,10 @@ _SIGNATURES = {
     'pmwd_sweep_table': (_i, [_vp, _descp, _i, _i, _vp, _vp, _vp]),
     'pmwd_sweep_last_stragglers': (C.c_longlong, [_vp, _vp]),
     'pmwd_sweep_usable': (_i, [_descp, _vp]),
+    'pmwd_scatter_sweep_det': (_i, [_vp, _descp, _vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp]),
+    'pmwd_sweep_det_halo_bytes': (_sz, [_descp, _i, _i]),
+    'pmwd_sweep_det_violations': (C.c_longlong, [_vp, _vp]),
+    'pmwd_sweep_det_reset': (_i, [_vp, _vp]),
     'pmwd_cell_sort_scratch_bytes': (_sz, [_descp]),
     'pmwd_cell_sort_perm': (_i, [_vp, _descp, _vp, _vp, _vp, _vp, _sz, _i, _i]),
     'pmwd_cell_sort_sorted_keys': (_vp, [_descp, _vp]),

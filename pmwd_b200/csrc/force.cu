@@ -37,9 +37,10 @@ int force_adj_gather(cudaStream_t st, const pmwd_cic_desc* d, const void* pmid, 
                      const float* pi, float val, float* alpha, float* acc);
 // scatter_sweep.cu
 bool sweep_usable(const pmwd_cic_desc* d, const pmwd_sweep* sw);
+bool sweep_det_usable(const pmwd_cic_desc* d, const pmwd_sweep* sw);
 int scatter_sweep(cudaStream_t st, const pmwd_cic_desc* d, const pmwd_sweep* sw, const void* pmid,
                   const float* disp, const float* val, int vstride, float vscalar, float* mesh,
-                  bool reuse_stragglers);
+                  bool reuse_stragglers, bool deterministic);
 // scatter_det.cu
 size_t scatter_det_scratch_bytes(const pmwd_cic_desc* d);
 int scatter_det(cudaStream_t st, const pmwd_cic_desc* d, const void* pmid, const float* disp,
@@ -113,8 +114,11 @@ static int force_forward(pmwd_ctx* ctx, cudaStream_t st, const pmwd_cic_desc* d,
   // scatter.py:37-39: val = conf.mesh_size / conf.ptcl_num (python float -> float32)
   const float val = (float)((double)nm / (double)d->ptcl_num);
   if (val_out) *val_out = val;
-  // tiled sweep scatter (scatter_sweep.cu): overwrites rho, no memset
-  const bool sweeping = mode != PMWD_SCATTER_DETERMINISTIC && sweep_usable(d, sweep);
+  // tiled sweep scatter (scatter_sweep.cu): overwrites rho, no memset; in deterministic mode its
+  // reproducible variant if the caller's sweep descriptor carries the halo arrays (the integrator, which
+  // re-sorts the storage before every deposit), else the cell-sorted scatter of scatter_det.cu
+  const bool det = mode == PMWD_SCATTER_DETERMINISTIC;
+  const bool sweeping = det ? sweep_det_usable(d, sweep) : sweep_usable(d, sweep);
   if (!sweeping) {
     StageTimer t(ST_MEMSET, st);
     PMWD_CUDA_TRY(cudaMemsetAsync(rho, 0, (size_t)nm * sizeof(float), st));
@@ -123,7 +127,7 @@ static int force_forward(pmwd_ctx* ctx, cudaStream_t st, const pmwd_cic_desc* d,
   {
     StageTimer t(ST_SCATTER, st);
     if (sweeping)
-      rc = scatter_sweep(st, d, sweep, pmid, disp, nullptr, 0, val, rho, false);
+      rc = scatter_sweep(st, d, sweep, pmid, disp, nullptr, 0, val, rho, false, det);
     else if (mode == PMWD_SCATTER_DETERMINISTIC)
       rc = scatter_det(st, d, pmid, disp, nullptr, val, 1, rho, nullptr, nullptr, ws + L.det,
                        L.total - L.det);
@@ -339,7 +343,8 @@ extern "C" int pmwd_force_adj(pmwd_ctx* ctx, void* stream, const pmwd_cic_desc* 
   // V_i = scatter(pi_i): the mesh_cot of _gather_bwd (gather.py:113), SoA, in the (now free)
   // gradient-spectrum buffers
   float* V[3] = {(float*)(ws + L.g[0]), (float*)(ws + L.g[1]), (float*)(ws + L.g[2])};
-  const bool sweeping = mode != PMWD_SCATTER_DETERMINISTIC && sweep_usable(d, sweep);
+  const bool det = mode == PMWD_SCATTER_DETERMINISTIC;
+  const bool sweeping = det ? sweep_det_usable(d, sweep) : sweep_usable(d, sweep);
   if (!sweeping) {
     StageTimer t(ST_MEMSET, st);
     for (int a = 0; a < 3; ++a) PMWD_CUDA_TRY(cudaMemsetAsync(V[a], 0, (size_t)nm * sizeof(float), st));
@@ -348,7 +353,7 @@ extern "C" int pmwd_force_adj(pmwd_ctx* ctx, void* stream, const pmwd_cic_desc* 
     StageTimer t(ST_SCATTER3, st);
     if (sweeping) {
       // one sweep per channel; the straggler list recorded by the density scatter is reused
-      for (int a = 0; a < 3 && !rc; ++a) rc = scatter_sweep(st, d, sweep, pmid, disp, pi + a, 3, 0.f, V[a], true);
+      for (int a = 0; a < 3 && !rc; ++a) rc = scatter_sweep(st, d, sweep, pmid, disp, pi + a, 3, 0.f, V[a], true, det);
     } else if (mode == PMWD_SCATTER_DETERMINISTIC)
       rc = scatter_det(st, d, pmid, disp, pi, 0.f, 3, V[0], V[1], V[2], ws + L.det, L.total - L.det);
     else

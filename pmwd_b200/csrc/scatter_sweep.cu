@@ -106,12 +106,23 @@ __device__ __forceinline__ float cell_units(float d, const SweepGeom& G) {
 }
 
 // TY, BW > 0: tile shape known at compile time (the flush loop's index arithmetic folds away); 0, 0: G.ty, G.bw.
-template <int TY, int BW>
+// DET: bitwise reproducible deposit (PMWD_SCATTER_DETERMINISTIC inside the integrator).  What makes the plain
+// kernel order dependent are the float REDs onto cells that two warps reach; here nothing is shared:
+//   * one work item = one (y, z) tile over ALL planes (lx = nx, periodic mesh), so along x only the wrap-around
+//     planes nx-1, 0, 1 are visited twice -- by the same lanes of the same warp, the second time as a plain
+//     load-add-store;
+//   * the tile's own cells (incl. its first row and first column) are written with plain stores; what it
+//     deposits into its halo row / halo column / halo corner (cells of the NEXT tile along y / z) goes to
+//     per-tile halo arrays (`halo`), which sweep_det_fix_kernel adds to the mesh afterwards in a fixed order.
+// The arithmetic inside a tile is sequential in the storage order (chunk by chunk, lanes merged in a fixed
+// tree, neighbours in a fixed sequence), and which warp sweeps which tile does not matter.  Needs freshly
+// sorted storage: a straggler would be deposited by REDs; it is counted in counters[3] so that the host can refuse.
+template <int TY, int BW, bool DET>
 __global__ void __launch_bounds__(SW_MAX_WARPS * 32, 1)
 scatter_sweep_kernel(SweepGeom G, const short* __restrict__ pmid, const float* __restrict__ disp,
                      const float* __restrict__ val, int vstride, float vscalar, float* __restrict__ mesh,
                      const uint2* __restrict__ table, unsigned* __restrict__ counters,
-                     uint32_t* __restrict__ strag, int record_strag) {
+                     uint32_t* __restrict__ strag, int record_strag, float* __restrict__ halo) {
   extern __shared__ __align__(16) float smf[];
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -156,8 +167,37 @@ scatter_sweep_kernel(SweepGeom G, const short* __restrict__ pmid, const float* _
         valid = pl >= 0 && pl < G.nx_ext;
       }
       float* mpl = mesh + (int64_t)gpl * plane_elems;
-      const bool all_red = (pl <= xa + 1) || (pl >= xb - 1);
       const int ntot = (ty + 1) * ngr;
+      if (DET) {
+        // second visit of a wrap-around plane (same warp, same lanes): accumulate instead of overwrite
+        const bool again = pl >= G.nx - 1;
+        const int64_t tp = ((int64_t)pencil * G.nband + band) * G.nx + gpl;       // (tile, plane)
+        float* hy = halo + tp * bw;                                               // halo row   [bw]
+        float* hz = halo + (int64_t)nitems * G.nx * bw + tp * (ty + 1);           // halo column [ty] + corner
+#pragma unroll
+        for (int i0 = 0; i0 < ntot; i0 += 32) {
+          const int i = i0 + lane;
+          if (i < ntot) {
+            const int row = i / ngr, gq = i - row * ngr;
+            float4* sp = reinterpret_cast<float4*>(src + row * rs + 4 * gq);
+            float4 v = *sp;
+            *sp = zero4;
+            float4* dst = reinterpret_cast<float4*>(row == ty ? hy + 4 * gq : mpl + (unsigned)((y0 + row) * G.nz + z0 + 4 * gq));
+            if (again) {
+              const float4 o = *dst;
+              v.x = __fadd_rn(o.x, v.x); v.y = __fadd_rn(o.y, v.y); v.z = __fadd_rn(o.z, v.z); v.w = __fadd_rn(o.w, v.w);
+            }
+            *dst = v;
+          }
+        }
+        for (int row = lane; row <= ty; row += 32) {
+          float v = src[row * rs + bw];
+          src[row * rs + bw] = 0.f;
+          if (again) v = __fadd_rn(hz[row], v);
+          hz[row] = v;
+        }
+      } else {
+      const bool all_red = (pl <= xa + 1) || (pl >= xb - 1);
 #pragma unroll
       for (int i0 = 0; i0 < ntot; i0 += 32) {
         const int i = i0 + lane;
@@ -184,6 +224,7 @@ scatter_sweep_kernel(SweepGeom G, const short* __restrict__ pmid, const float* _
           const int gy = row == wrap_row ? 0 : y0 + row;
           atomicAdd(mpl + (unsigned)(gy * G.nz + zh), v);
         }
+      }
       }
       __syncwarp();
     };
@@ -360,7 +401,52 @@ scatter_sweep_kernel(SweepGeom G, const short* __restrict__ pmid, const float* _
     }
     for (int i = lane; i < sres_left; i += 32) strag[sres_pos + i] = i < scount ? sbuf[i] : SW_STRAG_EMPTY;
     stotal += scount;
-    if (lane == 0 && stotal) atomicAdd(&counters[2], stotal);
+    if (lane == 0 && stotal) {
+      atomicAdd(&counters[2], stotal);
+      if (DET) atomicAdd(&counters[3], stotal);      // sticky: a deterministic deposit that was not (memset never clears it)
+    }
+  }
+}
+
+// Deterministic deposit, second half: add the per-tile halo arrays to the mesh.  One thread per (plane, cell of
+// the first row of a y-tile) and one per (plane, cell of the first column of a z-tile); a cell that is both gets
+// its terms in the fixed order own + halo row (tile above) + halo column (tile before) + corner (diagonal tile).
+template <bool COLS>
+__global__ void __launch_bounds__(256)
+sweep_det_fix_kernel(SweepGeom G, float* __restrict__ mesh, const float* __restrict__ halo) {
+  const int64_t ntile = (int64_t)G.npencil * G.nband;
+  const float* hyb = halo;
+  const float* hzb = halo + ntile * G.nx * G.bw;
+  if (!COLS) {
+    const int64_t total = (int64_t)G.nx * G.npencil * G.nz;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      const int z = (int)(i % G.nz);
+      const int64_t r = i / G.nz;
+      const int pencil = (int)(r % G.npencil), pl = (int)(r / G.npencil);
+      const int band = z / G.bw, k = z - band * G.bw;
+      const int up = pencil == 0 ? G.npencil - 1 : pencil - 1;                  // the tile whose halo row this is
+      const int64_t tp = ((int64_t)up * G.nband + band) * G.nx + pl;
+      float* c = mesh + ((int64_t)pl * G.ny + (int64_t)pencil * G.ty) * G.nz + z;
+      *c = __fadd_rn(*c, hyb[tp * G.bw + k]);
+    }
+  } else {
+    const int64_t total = (int64_t)G.nx * G.ny * G.nband;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      const int band = (int)(i % G.nband);
+      const int64_t r = i / G.nband;
+      const int y = (int)(r % G.ny), pl = (int)(r / G.ny);
+      const int pencil = y / G.ty, row = y - pencil * G.ty;
+      const int prev = band == 0 ? G.nband - 1 : band - 1;                      // the tile whose halo column this is
+      const int64_t tp = ((int64_t)pencil * G.nband + prev) * G.nx + pl;
+      float* c = mesh + ((int64_t)pl * G.ny + y) * G.nz + (int64_t)band * G.bw;
+      float v = __fadd_rn(*c, hzb[tp * (G.ty + 1) + row]);
+      if (row == 0) {
+        const int up = pencil == 0 ? G.npencil - 1 : pencil - 1;
+        const int64_t td = ((int64_t)up * G.nband + prev) * G.nx + pl;
+        v = __fadd_rn(v, hzb[td * (G.ty + 1) + G.ty]);                          // the diagonal tile's corner
+      }
+      *c = v;
+    }
   }
 }
 
@@ -601,37 +687,77 @@ namespace pmwd {
 
 // One channel: mesh (NOT pre-zeroed by the caller) <- deposit of val[p * vstride] (or vscalar).
 // reuse_stragglers: the list recorded by an earlier call with the same particles is used again.
-int scatter_sweep(cudaStream_t st, const pmwd_cic_desc* d, const pmwd_sweep* sw, const void* pmid,
-                  const float* disp, const float* val, int vstride, float vscalar, float* mesh,
-                  bool reuse_stragglers) {
-  SweepGeom G;
-  PMWD_REQUIRE(sweep_geom(d, sw->ty, sw->bw, sw->lx, &G), "geometry not supported by the sweep scatter");
-  unsigned* counters = (unsigned*)sw->scratch;
-  uint32_t* strag = (uint32_t*)((char*)sw->scratch + 64);
+template <bool DET>
+static int sweep_launch(cudaStream_t st, const SweepGeom& G, int grid, size_t smem, const short* pmid, const float* disp,
+                        const float* val, int vstride, float vscalar, float* mesh, const uint2* table,
+                        unsigned* counters, uint32_t* strag, int record, float* halo) {
+  auto kernel = scatter_sweep_kernel<0, 0, DET>;
+  if (G.ty == 8 && G.bw == 64) kernel = scatter_sweep_kernel<8, 64, DET>;
+  else if (G.ty == 8 && G.bw == 32) kernel = scatter_sweep_kernel<8, 32, DET>;
+  else if (G.ty == 16 && G.bw == 32) kernel = scatter_sweep_kernel<16, 32, DET>;
   static int smem_set = 0;
-  const size_t smem = (size_t)G.nwarps * sweep_ring_bytes(G.ty, G.bw);
-  auto kernel = scatter_sweep_kernel<0, 0>;
-  if (G.ty == 8 && G.bw == 64) kernel = scatter_sweep_kernel<8, 64>;
-  else if (G.ty == 8 && G.bw == 32) kernel = scatter_sweep_kernel<8, 32>;
-  else if (G.ty == 16 && G.bw == 32) kernel = scatter_sweep_kernel<16, 32>;
   if (!smem_set) {
-    PMWD_CUDA_TRY(cudaFuncSetAttribute(scatter_sweep_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    PMWD_CUDA_TRY(cudaFuncSetAttribute(scatter_sweep_kernel<8, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    PMWD_CUDA_TRY(cudaFuncSetAttribute(scatter_sweep_kernel<8, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    PMWD_CUDA_TRY(cudaFuncSetAttribute(scatter_sweep_kernel<16, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    PMWD_CUDA_TRY(cudaFuncSetAttribute(scatter_sweep_kernel<0, 0, DET>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    PMWD_CUDA_TRY(cudaFuncSetAttribute(scatter_sweep_kernel<8, 64, DET>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    PMWD_CUDA_TRY(cudaFuncSetAttribute(scatter_sweep_kernel<8, 32, DET>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    PMWD_CUDA_TRY(cudaFuncSetAttribute(scatter_sweep_kernel<16, 32, DET>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     smem_set = 1;
   }
-  PMWD_CUDA_TRY(cudaMemsetAsync(counters, 0, reuse_stragglers ? 4 : 12, st));
-  const int64_t rows = (int64_t)G.nx_ext * G.ny;
-  sweep_zero_kernel<<<grid_for(rows * 32, 256, 8), 256, 0, st>>>(G, mesh);
+  kernel<<<grid, G.nwarps * 32, smem, st>>>(G, pmid, disp, val, vstride, vscalar, mesh, table, counters, strag, record, halo);
   PMWD_LAUNCH_CHECK();
+  return PMWD_OK;
+}
+
+// bytes of the per-tile halo arrays of the deterministic deposit: halo row [bw] + halo column and corner [ty + 1]
+// per (tile, plane)
+static size_t sweep_det_halo_bytes(const SweepGeom& G) {
+  return (size_t)G.npencil * G.nband * G.nx * (G.bw + G.ty + 1) * sizeof(float);
+}
+
+bool sweep_det_usable(const pmwd_cic_desc* d, const pmwd_sweep* sw) {
+  if (!sweep_usable(d, sw) || !sw->det_halo) return false;
+  SweepGeom G;
+  if (!sweep_geom(d, sw->ty, sw->bw, d->mesh_shape[0], &G)) return false;
+  return G.periodic && G.nseg == 1 && sw->det_halo_bytes >= sweep_det_halo_bytes(G);
+}
+
+int scatter_sweep(cudaStream_t st, const pmwd_cic_desc* d, const pmwd_sweep* sw, const void* pmid,
+                  const float* disp, const float* val, int vstride, float vscalar, float* mesh,
+                  bool reuse_stragglers, bool deterministic) {
+  SweepGeom G;
+  // deterministic: one segment over all planes (nothing is shared between work items along x)
+  PMWD_REQUIRE(sweep_geom(d, sw->ty, sw->bw, deterministic ? d->mesh_shape[0] : sw->lx, &G),
+               "geometry not supported by the sweep scatter");
+  PMWD_REQUIRE(!deterministic || sweep_det_usable(d, sw), "deterministic sweep needs the whole periodic mesh and its halo arrays");
+  unsigned* counters = (unsigned*)sw->scratch;
+  uint32_t* strag = (uint32_t*)((char*)sw->scratch + 64);
+  const size_t smem = (size_t)G.nwarps * sweep_ring_bytes(G.ty, G.bw);
+  PMWD_CUDA_TRY(cudaMemsetAsync(counters, 0, reuse_stragglers ? 4 : 12, st));
+  if (!deterministic) {
+    const int64_t rows = (int64_t)G.nx_ext * G.ny;
+    sweep_zero_kernel<<<grid_for(rows * 32, 256, 8), 256, 0, st>>>(G, mesh);
+    PMWD_LAUNCH_CHECK();
+  }
   const int64_t nitems = (int64_t)G.npencil * G.nband * G.nseg;
   const int64_t want = (nitems + G.nwarps - 1) / G.nwarps;
   const int grid = (int)(want < sm_count() ? want : sm_count());
   PMWD_REQUIRE((int64_t)grid * G.nwarps * SW_STRAG_BLOCK <= SW_STRAG_SLACK, "straggler list slack too small for this grid");
-  kernel<<<grid, G.nwarps * 32, smem, st>>>(G, (const short*)pmid, disp, val, vstride, vscalar, mesh,
-                                            (const uint2*)sw->table, counters, strag, reuse_stragglers ? 0 : 1);
-  PMWD_LAUNCH_CHECK();
+  int rc;
+  if (deterministic)
+    rc = sweep_launch<true>(st, G, grid, smem, (const short*)pmid, disp, val, vstride, vscalar, mesh,
+                            (const uint2*)sw->table, counters, strag, reuse_stragglers ? 0 : 1, (float*)sw->det_halo);
+  else
+    rc = sweep_launch<false>(st, G, grid, smem, (const short*)pmid, disp, val, vstride, vscalar, mesh,
+                             (const uint2*)sw->table, counters, strag, reuse_stragglers ? 0 : 1, nullptr);
+  if (rc) return rc;
+  if (deterministic) {
+    sweep_det_fix_kernel<false><<<grid_for((int64_t)G.nx * G.npencil * G.nz, 256, 8), 256, 0, st>>>(G, mesh, (const float*)sw->det_halo);
+    PMWD_LAUNCH_CHECK();
+    sweep_det_fix_kernel<true><<<grid_for((int64_t)G.nx * G.ny * G.nband, 256, 8), 256, 0, st>>>(G, mesh, (const float*)sw->det_halo);
+    PMWD_LAUNCH_CHECK();
+  }
+  // (deterministic: the list is empty for freshly sorted storage; anything in it is deposited all the same and
+  // counted in counters[3], which pmwd_sweep_det_violations reports)
   sweep_straggler_kernel<<<sm_count() * 4, 256, 0, st>>>(G, (const short*)pmid, disp, val, vstride, vscalar, mesh,
                                                          counters, strag);
   PMWD_LAUNCH_CHECK();
@@ -650,12 +776,55 @@ extern "C" int pmwd_scatter_sweep(void* stream, const pmwd_cic_desc* d, const pm
   PMWD_REQUIRE(sweep_usable(d, sweep), "sweep descriptor does not match the mesh descriptor");
   cudaStream_t st = as_stream(stream);
   StageTimer t(nch == 1 ? ST_SCATTER : ST_SCATTER3, st);
-  if (nch == 1) return scatter_sweep(st, d, sweep, pmid, disp, val, 1, val_scalar, m0, false);
+  if (nch == 1) return scatter_sweep(st, d, sweep, pmid, disp, val, 1, val_scalar, m0, false, false);
   float* m[3] = {m0, m1, m2};
   for (int c = 0; c < 3; ++c) {
-    int rc = scatter_sweep(st, d, sweep, pmid, disp, val + c, 3, 0.f, m[c], c > 0);
+    int rc = scatter_sweep(st, d, sweep, pmid, disp, val + c, 3, 0.f, m[c], c > 0, false);
     if (rc) return rc;
   }
+  return PMWD_OK;
+}
+
+// The same through the deterministic variant (bitwise reproducible for freshly sorted storage; the sweep
+// descriptor must carry the halo arrays, pmwd_sweep_det_halo_bytes).
+extern "C" int pmwd_scatter_sweep_det(void* stream, const pmwd_cic_desc* d, const pmwd_sweep* sweep, const void* pmid,
+                                      const float* disp, const float* val, float val_scalar, int nch, float* m0,
+                                      float* m1, float* m2) {
+  PMWD_REQUIRE(d && sweep && m0 && (d->ptcl_num == 0 || (pmid && disp)), "null buffer");
+  PMWD_REQUIRE(nch == 1 || (nch == 3 && m1 && m2 && val), "nch must be 1 or 3 (three meshes, per-particle values)");
+  PMWD_REQUIRE(sweep_det_usable(d, sweep), "sweep descriptor does not support the deterministic deposit on this mesh");
+  cudaStream_t st = as_stream(stream);
+  StageTimer t(nch == 1 ? ST_SCATTER : ST_SCATTER3, st);
+  if (nch == 1) return scatter_sweep(st, d, sweep, pmid, disp, val, 1, val_scalar, m0, false, true);
+  float* m[3] = {m0, m1, m2};
+  for (int c = 0; c < 3; ++c) {
+    int rc = scatter_sweep(st, d, sweep, pmid, disp, val + c, 3, 0.f, m[c], c > 0, true);
+    if (rc) return rc;
+  }
+  return PMWD_OK;
+}
+
+// Size of the halo arrays the deterministic deposit needs for this mesh and tile shape (0: not supported).
+extern "C" size_t pmwd_sweep_det_halo_bytes(const pmwd_cic_desc* d, int ty, int bw) {
+  if (!d) return 0;
+  SweepGeom G;
+  if (!sweep_geom(d, ty, bw, d->mesh_shape[0], &G) || !G.periodic) return 0;
+  return sweep_det_halo_bytes(G);
+}
+
+// Particles that a deterministic deposit had to hand to the (order dependent) straggler path since the scratch
+// area was last cleared by pmwd_sweep_det_reset: 0 for freshly sorted storage.  Synchronises.
+extern "C" long long pmwd_sweep_det_violations(void* stream, const pmwd_sweep* sweep) {
+  if (!sweep || !sweep->scratch) return -1;
+  unsigned c[4] = {0, 0, 0, 0};
+  if (cudaStreamSynchronize(as_stream(stream)) != cudaSuccess) return -1;
+  if (cudaMemcpy(c, sweep->scratch, sizeof(c), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return (long long)c[3];
+}
+
+extern "C" int pmwd_sweep_det_reset(void* stream, const pmwd_sweep* sweep) {
+  PMWD_REQUIRE(sweep && sweep->scratch, "null buffer");
+  PMWD_CUDA_TRY(cudaMemsetAsync((char*)sweep->scratch + 12, 0, 4, as_stream(stream)));
   return PMWD_OK;
 }
 

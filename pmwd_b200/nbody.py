@@ -106,6 +106,7 @@ class _Store:
         self.migrator = None       # dist.SlabComm: particles move to the rank that owns their current x plane
         self.migrations = 0
         self.slab_sweep = False    # slab runs: keep the storage in the tiled deposit's order as well
+        self.det_sweep = False     # deterministic mode through the reproducible tiled deposit (sort before every force)
         self.timers = None         # dist.TIMERS in slab runs: 'migrate' / 'resort' phases of the bench line
 
     def _timed(self, name):
@@ -120,13 +121,30 @@ class _Store:
                 or a['pmid'].dtype != torch.int16 or conf.reorder_every <= 0:
             return
         desc = _force_desc(a['pmid'], conf)
-        st = _sweep.SweepState(desc, a['disp'].device)
-        if st.ty > 0:
+        det = conf.scatter_mode == 'deterministic'
+        st = _sweep.SweepState(desc, a['disp'].device, det=det)
+        if st.ty > 0 and (st.det or not det):
             self.sweep = st
+            self.det_sweep = det
             self.reorder()
 
     def sweep_arg(self):
         return self.sweep.arg() if self.sweep is not None else None
+
+    def sort_for_force(self):
+        """Deterministic mode: the reproducible tiled deposit needs storage sorted from the very positions it
+        deposits, so the re-sort happens right before every force evaluation (and never in maybe_reorder)."""
+        if self.det_sweep:
+            self.reorder()
+
+    def check_det(self):
+        """End of a run in deterministic mode (one synchronisation): no deposit may have met a particle outside
+        its tile's window -- it would have gone through order-dependent REDs."""
+        if self.det_sweep and self.sweep is not None:
+            bad = self.sweep.det_violations()
+            if bad:
+                raise _lib.PmwdError(f'deterministic deposit: {bad} particle deposits went through the atomic '
+                                     'straggler path (storage not re-sorted before a force evaluation)')
 
     @property
     def ptcl(self):
@@ -135,7 +153,7 @@ class _Store:
 
     def maybe_reorder(self, sync_max=None):
         conf = self.conf
-        if conf.reorder_every <= 0 or conf.dim != 3 or self.arrays['pmid'].dtype != torch.int16:
+        if conf.reorder_every <= 0 or conf.dim != 3 or self.arrays['pmid'].dtype != torch.int16 or self.det_sweep:
             return False
         self.steps_since += 1
         if self.steps_since < conf.reorder_every:
@@ -570,6 +588,7 @@ class _Stepper:
         return len(self.a) - 1
 
     def init(self):
+        self.store.sort_for_force()
         p = self.store.ptcl
         if _fast_ok(p, self.conf):
             force_into(p.pmid, p.disp, float(self.cosmo.Omega_m), self.conf, p.acc, sweep=self.store.sweep_arg())
@@ -585,6 +604,7 @@ class _Stepper:
             k1, d, k2 = self.factors(i)
             if not self.pre:
                 _kick_drift(st.ptcl, k1, d, True, True)
+            st.sort_for_force()
             a = st.arrays
             Om = float(self.cosmo.Omega_m)
             if i + 1 < self.nsteps:
@@ -610,6 +630,7 @@ def _nbody_forward(ptcl, cosmo, conf, reverse):
         for _ in range(stepper.nsteps):
             stepper.step()
         disp, vel, acc = store.lagrangian('disp', 'vel', 'acc')
+        store.check_det()
     return Particles(conf, ptcl.pmid, disp, vel=vel, acc=acc, attr=ptcl.attr)
 
 
@@ -715,6 +736,7 @@ def nbody_adj(ptcl, ptcl_cot, obsvbl_cot, cosmo, conf, reverse=False, _slab=None
 
         def f_adj():
             flush_pending()
+            store.sort_for_force()
             a = store.arrays
             if _slab is not None:
                 _slab.force_adj(a['pmid'], a['disp'], Om, a['pi'], a['acc'], a['alpha'], sweep=store.sweep)
@@ -769,6 +791,7 @@ def nbody_adj(ptcl, ptcl_cot, obsvbl_cot, cosmo, conf, reverse=False, _slab=None
                 cosmo_cot['Omega_m'] = cosmo_cot['Omega_m'] - (S / Om) * factor
 
         disp, vel, acc, xi, pi, alpha = store.lagrangian('disp', 'vel', 'acc', 'xi', 'pi', 'alpha')
+        store.check_det()
     ptcl = Particles(conf, pmid_in, disp, vel=vel, acc=acc)
     ptcl_cot = Particles(conf, pmid_in, xi, vel=pi, acc=alpha)
     return ptcl, ptcl_cot, cosmo_cot

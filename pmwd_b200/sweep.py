@@ -17,15 +17,20 @@ LX = 64     # planes per x segment of a work item
 
 
 def enabled(conf):
-    return (getattr(conf, 'scatter_tiled', True) and conf.scatter_mode == 'atomic'
-            and os.environ.get('PMWD_SWEEP', '1') != '0')
+    if not getattr(conf, 'scatter_tiled', True) or os.environ.get('PMWD_SWEEP', '1') == '0':
+        return False
+    if conf.scatter_mode == 'deterministic':
+        return os.environ.get('PMWD_SWEEP_DET', '1') != '0'
+    return conf.scatter_mode == 'atomic'
 
 
 class SweepState:
     """Table + scratch of one particle store for one mesh descriptor."""
 
-    def __init__(self, desc, dev, lx=LX):
+    def __init__(self, desc, dev, lx=LX, det=False):
         lib = _lib.lib()
+        self.det = bool(det)       # also hold the halo arrays of the deterministic variant
+        self.halo = None
         ty, bw = C.c_int32(0), C.c_int32(0)
         ok = lib.pmwd_sweep_pick(C.byref(desc), C.byref(ty), C.byref(bw))
         self.ty, self.bw = (int(ty.value), int(bw.value)) if ok else (0, 0)
@@ -53,7 +58,15 @@ class SweepState:
         sb = lib.pmwd_sweep_scratch_bytes(C.byref(desc))
         if self.scratch is None or self.scratch.numel() < sb:
             self.scratch = torch.empty(sb + sb // 8, dtype=torch.uint8, device=self.dev)    # room to grow
+            self.scratch[:64].zero_()      # counters (incl. the sticky one of the deterministic deposit)
             self.ok = False
+        if self.det:
+            hb = lib.pmwd_sweep_det_halo_bytes(C.byref(desc), self.ty, self.bw)
+            if hb == 0:
+                self.det = False
+            elif self.halo is None or self.halo.numel() < hb:
+                self.halo = torch.empty(hb, dtype=torch.uint8, device=self.dev)
+                self.ok = False
 
     def _make_struct(self, desc):
         s = _lib.Sweep()
@@ -64,6 +77,9 @@ class SweepState:
         s.xoff = int(desc.offset[0] // a1) % int(desc.wrap_shape[0])
         s.scratch = self.scratch.data_ptr()
         s.scratch_bytes = self.scratch.numel()
+        if self.det and self.halo is not None:
+            s.det_halo = self.halo.data_ptr()
+            s.det_halo_bytes = self.halo.numel()
         self._struct = s
 
     def build(self, desc, keys_ptr, check=False):
@@ -98,6 +114,14 @@ class SweepState:
         was built for the same planes)."""
         a = self.arg()
         return a is not None and bool(_lib.lib().pmwd_sweep_usable(C.byref(desc), a))
+
+    def det_violations(self):
+        """Particles a deterministic deposit had to hand to the order-dependent straggler path (0 for storage
+        that was re-sorted before every deposit).  Synchronises."""
+        if not self.ok or not self.det:
+            return 0
+        with torch.cuda.device(self.dev):
+            return int(_lib.lib().pmwd_sweep_det_violations(_lib.stream_ptr(self.dev), C.byref(self._struct)))
 
     def stragglers(self):
         if not self.ok:
