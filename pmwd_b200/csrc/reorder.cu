@@ -39,23 +39,34 @@ struct SortParams {
 
 constexpr uint32_t SORT_KEY_GONE = 0xffffffffu;
 
+// TWO = false: one source, nobody left (the single-device re-sort): the plain loads the compiler vectorises
+// (the two-source pointer selects cost this memory-bound kernel 50 %: 0.89 -> 1.36 ms at 512^3)
+template <bool TWO>
 __global__ void __launch_bounds__(256)
 sort_keys_kernel(SortParams P, const short* __restrict__ pmid, const float* __restrict__ disp,
                  const short* __restrict__ pmidB, const float* __restrict__ dispB,
                  uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P.n;
        p += (int64_t)gridDim.x * blockDim.x) {
-    vals[p] = (uint32_t)p;
-    const bool fromA = p < P.nA;
-    if (fromA && P.ownerA && P.ownerA[p] != (uint8_t)P.rank) { keys[p] = SORT_KEY_GONE; continue; }
-    const short* pm = fromA ? pmid + 3 * p : pmidB + 3 * (p - P.nA);
-    const float* dp = fromA ? disp + 3 * p : dispB + 3 * (p - P.nA);
     int c[3];
     const int nn[3] = {P.nx, P.ny, P.nz};
+    if (TWO) {
+      vals[p] = (uint32_t)p;
+      const bool fromA = p < P.nA;
+      if (fromA && P.ownerA && P.ownerA[p] != (uint8_t)P.rank) { keys[p] = SORT_KEY_GONE; continue; }
+      const short* pm = fromA ? pmid + 3 * p : pmidB + 3 * (p - P.nA);
+      const float* dp = fromA ? disp + 3 * p : dispB + 3 * (p - P.nA);
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      float t = __fdiv_rn(dp[a], P.cell);
-      c[a] = wrap_index((int)pm[a] + (int)floorf(t), nn[a]);
+      for (int a = 0; a < 3; ++a) {
+        float t = __fdiv_rn(dp[a], P.cell);
+        c[a] = wrap_index((int)pm[a] + (int)floorf(t), nn[a]);
+      }
+    } else {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        float t = __fdiv_rn(disp[3 * p + a], P.cell);
+        c[a] = wrap_index((int)pmid[3 * p + a] + (int)floorf(t), nn[a]);
+      }
     }
     int lx = c[0] - P.xoff;           // slab-local plane keeps the key below 2^32 on big meshes
     if (lx < 0) lx += P.nx;
@@ -71,6 +82,7 @@ sort_keys_kernel(SortParams P, const short* __restrict__ pmid, const float* __re
     } else {
       keys[p] = (uint32_t)(((int64_t)(lx >> P.shift) * P.nyc + (c[1] >> P.shift)) * P.nz + c[2]);
     }
+    if (!TWO) vals[p] = (uint32_t)p;
   }
 }
 
@@ -83,7 +95,7 @@ struct RowArgs {
   int words[8];     // row size in 2-byte words (3 for int16[3], 6 for float[3], 2 for uint32)
 };
 
-template <bool INVERSE>
+template <bool INVERSE, bool TWO>
 __global__ void __launch_bounds__(256)
 permute_rows_kernel(int64_t n, const uint32_t* __restrict__ perm, RowArgs A) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
@@ -91,11 +103,11 @@ permute_rows_kernel(int64_t n, const uint32_t* __restrict__ perm, RowArgs A) {
     const int64_t j = perm[i];
     int64_t from = INVERSE ? i : j;
     const int64_t to = INVERSE ? j : i;
-    const bool second = !INVERSE && from >= A.nA;
+    const bool second = TWO && !INVERSE && from >= A.nA;
     if (second) from -= A.nA;
     for (int a = 0; a < A.narr; ++a) {
       const int w = A.words[a];
-      const void* base = second ? A.srcB[a] : A.src[a];
+      const void* base = (TWO && second) ? A.srcB[a] : A.src[a];
       if ((w & 1) == 0) {   // rows of 4-byte words
         const uint32_t* s = reinterpret_cast<const uint32_t*>(base) + from * (w >> 1);
         uint32_t* d = reinterpret_cast<uint32_t*>(A.dst[a]) + to * (w >> 1);
@@ -203,8 +215,12 @@ extern "C" int pmwd_cell_sort_perm2(void* stream, const pmwd_cic_desc* d, const 
   uint32_t* keys_in = (uint32_t*)(base + L.keys_in);
   uint32_t* vals_in = (uint32_t*)(base + L.vals_in);
   uint32_t* keys_out = (uint32_t*)(base + L.keys_out);
-  sort_keys_kernel<<<grid_for(P.n, 256, 8), 256, 0, st>>>(P, (const short*)pmid, disp, (const short*)pmidB, dispB,
-                                                          keys_in, vals_in);
+  if (nA == P.n && !ownerA)
+    sort_keys_kernel<false><<<grid_for(P.n, 256, 8), 256, 0, st>>>(P, (const short*)pmid, disp, nullptr, nullptr,
+                                                                   keys_in, vals_in);
+  else
+    sort_keys_kernel<true><<<grid_for(P.n, 256, 8), 256, 0, st>>>(P, (const short*)pmid, disp, (const short*)pmidB, dispB,
+                                                                  keys_in, vals_in);
   PMWD_LAUNCH_CHECK();
   size_t cub_bytes = L.cub_bytes;
   // sweep layout with a power-of-two tile width: the z position inside a tile row (the low log2(bw) bits) is
@@ -246,7 +262,10 @@ extern "C" int pmwd_permute_rows2(void* stream, int64_t n, const uint32_t* perm,
   }
   cudaStream_t st = as_stream(stream);
   StageTimer timer(ST_OTHER, st);
-  permute_rows_kernel<false><<<grid_for(n, 256, 8), 256, 0, st>>>(n, perm, A);
+  if (srcB && nA < ((int64_t)1 << 40))
+    permute_rows_kernel<false, true><<<grid_for(n, 256, 8), 256, 0, st>>>(n, perm, A);
+  else
+    permute_rows_kernel<false, false><<<grid_for(n, 256, 8), 256, 0, st>>>(n, perm, A);
   PMWD_LAUNCH_CHECK();
   return PMWD_OK;
 }
@@ -271,8 +290,8 @@ extern "C" int pmwd_permute_rows(void* stream, int64_t n, const uint32_t* perm, 
   cudaStream_t st = as_stream(stream);
   StageTimer timer(ST_OTHER, st);
   int grid = grid_for(n, 256, 8);
-  if (inverse) permute_rows_kernel<true><<<grid, 256, 0, st>>>(n, perm, A);
-  else permute_rows_kernel<false><<<grid, 256, 0, st>>>(n, perm, A);
+  if (inverse) permute_rows_kernel<true, false><<<grid, 256, 0, st>>>(n, perm, A);
+  else permute_rows_kernel<false, false><<<grid, 256, 0, st>>>(n, perm, A);
   PMWD_LAUNCH_CHECK();
   return PMWD_OK;
 }

@@ -520,8 +520,9 @@ def test_nbody_adjoint_vs_oracle(mode):
 def test_nbody_adjoint_config1_size_vs_oracle():
     """BASELINE config 1 at its size (64^3 particles, 128^3 mesh, 10 leapfrog steps): the reverse-time
     adjoint (nbody.py:226-276) against the float64 oracle's nbody_adj.  Cosine >= 0.9999 for the disp and
-    vel cotangents and for the growth-table cotangent; Omega_m cotangent within 1e-2 (a float32 sum over a
-    chaotic run; the bulk statistic of the particle cotangents as in the 16^3 test)."""
+    vel cotangents and for the growth-table cotangent; Omega_m cotangent within 5e-2 (a float32 sum over a
+    chaotic run, bound calibrated with the float32 oracle; the bulk statistic of the particle cotangents as in
+    the 16^3 test)."""
     pm, conf, oconf, cosmo, ocosmo, ic, ptcl = _ic(64, a_nbody_maxstep=0.1)
     assert conf.a_nbody_num == 10
     rng = np.random.default_rng(5)
@@ -549,7 +550,10 @@ def test_nbody_adjoint_config1_size_vs_oracle():
         assert np.median(e) <= 5e-4 and np.quantile(e, 0.99) <= 3e-2
     err = abs(Om.grad.item() / cc['Omega_m'] - 1)
     print('Omega_m cot rel err', err)
-    assert err <= 1e-2
+    # a float32 sum with cancellations over a chaotic run: the float32 ORACLE itself sits 2.2e-2, 4.2e-3, 4.8e-3 and
+    # 1.9e-2 from the float64 one over four draws of a 1e-6-cell IC perturbation (tools/calib_adjoint_noise.py,
+    # profiles/r02_adjoint_noise_calibration.txt); the tight checks are the cosines and the bulk statistics above
+    assert err <= 5e-2
     assert _cos(gt.grad.numpy(), cc['growth']) >= 0.9999
 
 
