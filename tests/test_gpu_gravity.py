@@ -512,8 +512,9 @@ def test_nbody_adjoint_vs_oracle(mode):
     err = abs(Om.grad.item() / cc['Omega_m'] - 1)
     print('Omega_m cot rel err', err, 'float32-oracle rel err', noise)
     # (atomic and deterministic runs of ours differ from each other by ~1e-3 on this chaotic
-    # 16^3 / 8-step configuration: that is the float32 noise level of this scalar)
-    assert err <= 1e-2
+    # 16^3 / 8-step configuration: that is the float32 noise level of this scalar; at 64^3 the float32 oracle
+    # alone is 0.4 .. 2.2 % from the float64 one, profiles/r02_adjoint_noise_calibration.txt)
+    assert err <= max(2e-2, 3 * noise)
     assert _cos(gt.grad.numpy(), cc['growth']) >= 0.9999
 
 
