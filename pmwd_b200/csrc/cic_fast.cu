@@ -27,9 +27,16 @@ struct FastParams {
   int nx_ext;       // x planes held by the mesh array (== nx on one GPU; slab + halos otherwise)
   int xoff;         // global x index of plane 0 of the array (offset / cell, an integer)
   float cell;
+  int cs;           // particle arrays are streamed once: load / store them with the .cs (evict-first) hint so
+                    // that they do not push the force-mesh lines the stencils re-use out of L2
   float inv_cell;   // 1 / cell if cell is a power of two (the product is then the same correctly rounded
                     // number as the IEEE division, at a tenth of its instructions), else 0
 };
+
+template <typename T>
+__device__ __forceinline__ T ld_p(const T* p, int cs) { return cs ? __ldcs(p) : *p; }
+template <typename T>
+__device__ __forceinline__ void st_p(T* p, T v, int cs) { if (cs) __stcs(p, v); else *p = v; }
 
 // x / cell in float32, bitwise what the reference's division gives (pm_util.py:133, gather.py:108-110)
 __device__ __forceinline__ float div_cell(float x, float cell, float inv_cell) {
@@ -186,9 +193,11 @@ gather3_kernel(FastParams P, const short* __restrict__ pmid, const float* disp,
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P.n;
        p += (int64_t)gridDim.x * blockDim.x) {
     Stencil3 s;
-    axis_fast(pmid[3 * p + 0], disp[3 * p + 0], P.cell, P.inv_cell, P.nx, s.ix, s.wx, nullptr);
-    axis_fast(pmid[3 * p + 1], disp[3 * p + 1], P.cell, P.inv_cell, P.ny, s.iy, s.wy, nullptr);
-    axis_fast(pmid[3 * p + 2], disp[3 * p + 2], P.cell, P.inv_cell, P.nz, s.iz, s.wz, nullptr);
+    const int cs = P.cs;
+    const float dp0 = ld_p(disp + 3 * p + 0, cs), dp1 = ld_p(disp + 3 * p + 1, cs), dp2 = ld_p(disp + 3 * p + 2, cs);
+    axis_fast(ld_p(pmid + 3 * p + 0, cs), dp0, P.cell, P.inv_cell, P.nx, s.ix, s.wx, nullptr);
+    axis_fast(ld_p(pmid + 3 * p + 1, cs), dp1, P.cell, P.inv_cell, P.ny, s.iy, s.wy, nullptr);
+    axis_fast(ld_p(pmid + 3 * p + 2, cs), dp2, P.cell, P.inv_cell, P.nz, s.iz, s.wz, nullptr);
     localize_x(P, s.ix);
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
     // neighbour order n = bx + 2 by + 4 bz (axis 0 = LSB, pm_util.py:95-97), summed sequentially
@@ -202,24 +211,24 @@ gather3_kernel(FastParams P, const short* __restrict__ pmid, const float* disp,
       a1 = __fadd_rn(a1, __fmul_rn(ok ? __ldg(f1 + lin) : 0.f, w));
       a2 = __fadd_rn(a2, __fmul_rn(ok ? __ldg(f2 + lin) : 0.f, w));
     }
-    acc[3 * p + 0] = a0;
-    acc[3 * p + 1] = a1;
-    acc[3 * p + 2] = a2;
+    st_p(acc + 3 * p + 0, a0, cs);
+    st_p(acc + 3 * p + 1, a1, cs);
+    st_p(acc + 3 * p + 2, a2, cs);
     if (KICK) {
-      float v0 = __fadd_rn(vel[3 * p + 0], __fmul_rn(a0, K));
-      float v1 = __fadd_rn(vel[3 * p + 1], __fmul_rn(a1, K));
-      float v2 = __fadd_rn(vel[3 * p + 2], __fmul_rn(a2, K));
+      float v0 = __fadd_rn(ld_p(vel + 3 * p + 0, cs), __fmul_rn(a0, K));
+      float v1 = __fadd_rn(ld_p(vel + 3 * p + 1, cs), __fmul_rn(a1, K));
+      float v2 = __fadd_rn(ld_p(vel + 3 * p + 2, cs), __fmul_rn(a2, K));
       if (KICK == 2) {
         v0 = __fadd_rn(v0, __fmul_rn(a0, K1n));
         v1 = __fadd_rn(v1, __fmul_rn(a1, K1n));
         v2 = __fadd_rn(v2, __fmul_rn(a2, K1n));
-        disp_rw[3 * p + 0] = __fadd_rn(disp[3 * p + 0], __fmul_rn(v0, Dn));
-        disp_rw[3 * p + 1] = __fadd_rn(disp[3 * p + 1], __fmul_rn(v1, Dn));
-        disp_rw[3 * p + 2] = __fadd_rn(disp[3 * p + 2], __fmul_rn(v2, Dn));
+        st_p(disp_rw + 3 * p + 0, __fadd_rn(dp0, __fmul_rn(v0, Dn)), cs);
+        st_p(disp_rw + 3 * p + 1, __fadd_rn(dp1, __fmul_rn(v1, Dn)), cs);
+        st_p(disp_rw + 3 * p + 2, __fadd_rn(dp2, __fmul_rn(v2, Dn)), cs);
       }
-      vel[3 * p + 0] = v0;
-      vel[3 * p + 1] = v1;
-      vel[3 * p + 2] = v2;
+      st_p(vel + 3 * p + 0, v0, cs);
+      st_p(vel + 3 * p + 1, v1, cs);
+      st_p(vel + 3 * p + 2, v2, cs);
     }
   }
 }
@@ -238,11 +247,12 @@ force_adj_gather_kernel(FastParams P, const short* __restrict__ pmid, const floa
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P.n;
        p += (int64_t)gridDim.x * blockDim.x) {
     Stencil3G<true> s;
-    axis_fast(pmid[3 * p + 0], disp[3 * p + 0], P.cell, P.inv_cell, P.nx, s.ix, s.wx, s.sx);
-    axis_fast(pmid[3 * p + 1], disp[3 * p + 1], P.cell, P.inv_cell, P.ny, s.iy, s.wy, s.sy);
-    axis_fast(pmid[3 * p + 2], disp[3 * p + 2], P.cell, P.inv_cell, P.nz, s.iz, s.wz, s.sz);
+    const int cs = P.cs;
+    axis_fast(ld_p(pmid + 3 * p + 0, cs), ld_p(disp + 3 * p + 0, cs), P.cell, P.inv_cell, P.nx, s.ix, s.wx, s.sx);
+    axis_fast(ld_p(pmid + 3 * p + 1, cs), ld_p(disp + 3 * p + 1, cs), P.cell, P.inv_cell, P.ny, s.iy, s.wy, s.sy);
+    axis_fast(ld_p(pmid + 3 * p + 2, cs), ld_p(disp + 3 * p + 2, cs), P.cell, P.inv_cell, P.nz, s.iz, s.wz, s.sz);
     localize_x(P, s.ix);
-    const float p0 = pi[3 * p + 0], p1 = pi[3 * p + 1], p2 = pi[3 * p + 2];
+    const float p0 = ld_p(pi + 3 * p + 0, cs), p1 = ld_p(pi + 3 * p + 1, cs), p2 = ld_p(pi + 3 * p + 2, cs);
     float d[4][3];
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;     // acc = gather3 of the same force values (same arithmetic as gather3_kernel)
 #pragma unroll
@@ -281,12 +291,12 @@ force_adj_gather_kernel(FastParams P, const short* __restrict__ pmid, const floa
       a = __fadd_rn(a, div_cell(d[1][j], P.cell, P.inv_cell));
       a = __fadd_rn(a, div_cell(d[2][j], P.cell, P.inv_cell));
       a = __fadd_rn(a, div_cell(d[3][j], P.cell, P.inv_cell));
-      alpha[3 * p + j] = a;
+      st_p(alpha + 3 * p + j, a, cs);
     }
     if (acc) {
-      acc[3 * p + 0] = a0;
-      acc[3 * p + 1] = a1;
-      acc[3 * p + 2] = a2;
+      st_p(acc + 3 * p + 0, a0, cs);
+      st_p(acc + 3 * p + 1, a1, cs);
+      st_p(acc + 3 * p + 2, a2, cs);
     }
   }
 }
@@ -307,6 +317,8 @@ static int fast_params(const pmwd_cic_desc* d, FastParams* P) {
     int e = 0;
     const float m = frexpf(P->cell, &e);
     P->inv_cell = (m == 0.5f && e > -100 && e < 100 && !getenv("PMWD_CIC_DIV")) ? 1.f / P->cell : 0.f;
+    const char* c = getenv("PMWD_PTCL_CS");
+    P->cs = c ? atoi(c) : 1;
   }
   P->xoff = slab_xoff(d);
   return PMWD_OK;
