@@ -468,7 +468,14 @@ sweep_zero_kernel(SweepGeom G, float* __restrict__ mesh) {
     if (whole) {
       for (int i = lane; i < nz4; i += 32) row[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     } else {
-      for (int b = lane; b < G.nband; b += 32) row[b * bw4] = make_float4(0.f, 0.f, 0.f, 0.f);
+      // whole 32-byte sectors (two float4) where the tile is wide enough: a half-sector write makes L2 fetch
+      // the other half first; the second float4 is overwritten by the sweep's plain store afterwards
+      const int b2 = 2 * G.nband;
+      if (bw4 >= 2 && (bw4 & 1) == 0) {
+        for (int i = lane; i < b2; i += 32) row[(i >> 1) * bw4 + (i & 1)] = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        for (int b = lane; b < G.nband; b += 32) row[b * bw4] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
   }
 }
@@ -758,7 +765,9 @@ int scatter_sweep(cudaStream_t st, const pmwd_cic_desc* d, const pmwd_sweep* sw,
   }
   // (deterministic: the list is empty for freshly sorted storage; anything in it is deposited all the same and
   // counted in counters[3], which pmwd_sweep_det_violations reports)
-  sweep_straggler_kernel<<<sm_count() * 4, 256, 0, st>>>(G, (const short*)pmid, disp, val, vstride, vscalar, mesh,
+  // 32 registers: 8 CTAs of 256 threads per SM; each thread has one scattered particle read in flight, so the
+  // number of resident threads is the memory-level parallelism of this latency-bound pass
+  sweep_straggler_kernel<<<sm_count() * 8, 256, 0, st>>>(G, (const short*)pmid, disp, val, vstride, vscalar, mesh,
                                                          counters, strag);
   PMWD_LAUNCH_CHECK();
   return PMWD_OK;
