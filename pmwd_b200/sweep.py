@@ -13,7 +13,8 @@ import torch
 
 from . import _lib
 
-LX = 64     # planes per x segment of a work item
+# planes per x segment of a work item: 64 (deposit 3.41-3.48 ms; 128: 3.52 ms, profiles/r02_sweep_tiles.txt)
+LX = int(os.environ.get('PMWD_SWEEP_LX', '64'))
 
 
 def enabled(conf):
