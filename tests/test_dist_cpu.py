@@ -1,4 +1,4 @@
-"""world_size-2 gloo tests (CPU) of the slab decomposition's host logic: the distributed FFT
+"""world_size-2 and -4 gloo tests (CPU) of the slab decomposition's host logic: the distributed FFT
 (2-D local transforms + one all-to-all + 1-D transform) against numpy's rfftn/irfftn of the
 gathered field, the neighbour halo reduce / fill, and the particle partition."""
 import os
@@ -112,12 +112,15 @@ def _free_port():
 
 
 @pytest.mark.timeout(300)
-def test_slab_host_logic_gloo_world2(tmp_path):
+@pytest.mark.parametrize('world', [2, 4])
+def test_slab_host_logic_gloo(tmp_path, world):
+    """World 2: every other rank is both neighbours; world 4: distinct left / right neighbours, non-neighbour
+    destinations in the particle exchange, ranks that receive nothing from some peers."""
     script = tmp_path / 'worker.py'
     script.write_text(WORKER % ROOT)
-    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(world),
            '--master-addr', '127.0.0.1', '--master-port', str(_free_port()), str(script)]
     env = dict(os.environ, CUDA_VISIBLE_DEVICES='', OMP_NUM_THREADS='1')
     r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=280)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count('ok') == 2
+    assert r.stdout.count('ok') == world
