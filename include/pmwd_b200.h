@@ -334,10 +334,14 @@ const uint32_t* pmwd_cell_sort_sorted_keys(const pmwd_cic_desc* d, const void* s
 /* Two-source variant for slab runs with Eulerian ownership: sorts the virtual concatenation of
  * A = (pmid, disp)[0, nA) -- rows with ownerA[i] != rank (pmwd_slab_owner) have left for another rank and sort
  * behind everything -- and the arrivals B = (pmidB, dispB)[0, ptcl_num - nA).  d->ptcl_num = nA + nB.  The
- * first ptcl_num - (rows gone) entries of perm are the new storage order (indices >= nA refer to B). */
+ * first ptcl_num - (rows gone) entries of perm are the new storage order (indices >= nA refer to B).
+ * vel / velB / pred (vel may be NULL): the keys are computed from the PREDICTED positions disp + vel * pred, so
+ * that the order is centred on the force evaluations until the next re-sort (the deposit and the gathers tolerate
+ * any order; only their speed depends on it). */
 int pmwd_cell_sort_perm2(void* stream, const pmwd_cic_desc* d, const void* pmid, const float* disp, int64_t nA,
                          const uint8_t* ownerA, int rank, const void* pmidB, const float* dispB, uint32_t* perm,
-                         void* scratch, size_t scratch_bytes, int ty, int bw);
+                         void* scratch, size_t scratch_bytes, int ty, int bw, const float* vel, const float* velB,
+                         float pred);
 /* For each of `narr` row-major arrays (row_bytes[a] bytes per particle, even):
  * inverse == 0: dst[i] = src[perm[i]];  inverse != 0: dst[perm[i]] = src[i]. */
 int pmwd_permute_rows(void* stream, int64_t n, const uint32_t* perm, int narr,

@@ -124,7 +124,7 @@ _SIGNATURES = {
     'pmwd_cell_sort_scratch_bytes': (_sz, [_descp]),
     'pmwd_cell_sort_perm': (_i, [_vp, _descp, _vp, _vp, _vp, _vp, _sz, _i, _i]),
     'pmwd_cell_sort_sorted_keys': (_vp, [_descp, _vp]),
-    'pmwd_cell_sort_perm2': (_i, [_vp, _descp, _vp, _vp, _i64, _vp, _i, _vp, _vp, _vp, _vp, _sz, _i, _i]),
+    'pmwd_cell_sort_perm2': (_i, [_vp, _descp, _vp, _vp, _i64, _vp, _i, _vp, _vp, _vp, _vp, _sz, _i, _i, _vp, _vp, _f]),
     'pmwd_permute_rows': (_i, [_vp, _i64, _vp, _i, C.POINTER(_vp), C.POINTER(_vp), _i32p, _i]),
     'pmwd_permute_rows2': (_i, [_vp, _i64, _vp, _i, C.POINTER(_vp), _i64, C.POINTER(_vp), C.POINTER(_vp), _i32p]),
     'pmwd_slab_owner': (_i, [_vp, _i64, _vp, _vp, _d, _i, _i, _i, _i, _vp, _vp]),

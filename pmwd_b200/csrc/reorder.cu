@@ -35,6 +35,11 @@ struct SortParams {
   int64_t nA;
   const uint8_t* ownerA;
   int rank;
+  // keys from PREDICTED positions disp + vel * pred (vel == NULL: the positions as they are): the storage order is
+  // then centred on the force evaluations until the next re-sort instead of being exact now and 2 steps stale last
+  const float* vel;
+  const float* velB;
+  float pred;
 };
 
 constexpr uint32_t SORT_KEY_GONE = 0xffffffffu;
@@ -56,15 +61,18 @@ sort_keys_kernel(SortParams P, const short* __restrict__ pmid, const float* __re
       if (fromA && P.ownerA && P.ownerA[p] != (uint8_t)P.rank) { keys[p] = SORT_KEY_GONE; continue; }
       const short* pm = fromA ? pmid + 3 * p : pmidB + 3 * (p - P.nA);
       const float* dp = fromA ? disp + 3 * p : dispB + 3 * (p - P.nA);
+      const float* vp = P.vel ? (fromA ? P.vel + 3 * p : P.velB + 3 * (p - P.nA)) : nullptr;
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
-        float t = __fdiv_rn(dp[a], P.cell);
+        const float x = vp ? __fadd_rn(dp[a], __fmul_rn(vp[a], P.pred)) : dp[a];
+        float t = __fdiv_rn(x, P.cell);
         c[a] = wrap_index((int)pm[a] + (int)floorf(t), nn[a]);
       }
     } else {
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
-        float t = __fdiv_rn(disp[3 * p + a], P.cell);
+        const float x = P.vel ? __fadd_rn(disp[3 * p + a], __fmul_rn(P.vel[3 * p + a], P.pred)) : disp[3 * p + a];
+        float t = __fdiv_rn(x, P.cell);
         c[a] = wrap_index((int)pmid[3 * p + a] + (int)floorf(t), nn[a]);
       }
     }
@@ -168,7 +176,7 @@ extern "C" const uint32_t* pmwd_cell_sort_sorted_keys(const pmwd_cic_desc* d, co
 extern "C" int pmwd_cell_sort_perm2(void* stream, const pmwd_cic_desc* d, const void* pmid, const float* disp,
                                     int64_t nA, const uint8_t* ownerA, int rank, const void* pmidB,
                                     const float* dispB, uint32_t* perm, void* scratch, size_t scratch_bytes,
-                                    int ty, int bw) {
+                                    int ty, int bw, const float* vel, const float* velB, float pred) {
   PMWD_REQUIRE(d && d->dim == 3 && d->pmid_bytes == 2 && !d->general,
                "cell sort supports the 3-D int16 fast path");
   PMWD_REQUIRE(perm && scratch, "null buffer");
@@ -179,6 +187,10 @@ extern "C" int pmwd_cell_sort_perm2(void* stream, const pmwd_cic_desc* d, const 
   P.nA = nA;
   P.ownerA = ownerA;
   P.rank = rank;
+  const bool predict = vel != nullptr && pred != 0.f && (nA == d->ptcl_num || velB != nullptr);
+  P.vel = predict ? vel : nullptr;
+  P.velB = predict ? velB : nullptr;
+  P.pred = predict ? pred : 0.f;
   P.nx = d->wrap_shape[0]; P.ny = d->wrap_shape[1]; P.nz = d->wrap_shape[2];
   P.nx_ext = d->mesh_shape[0];
   P.xoff = slab_xoff(d);
@@ -239,7 +251,7 @@ extern "C" int pmwd_cell_sort_perm(void* stream, const pmwd_cic_desc* d, const v
                                    size_t scratch_bytes, int ty, int bw) {
   PMWD_REQUIRE(d != nullptr, "null descriptor");
   return pmwd_cell_sort_perm2(stream, d, pmid, disp, d->ptcl_num, nullptr, 0, nullptr, nullptr, perm, scratch,
-                              scratch_bytes, ty, bw);
+                              scratch_bytes, ty, bw, nullptr, nullptr, 0.f);
 }
 
 // dst[i] = (srcA ++ srcB)[perm[i]] for i < n: gather from the virtual concatenation of two sources (rows

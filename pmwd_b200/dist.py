@@ -910,7 +910,10 @@ class SlabStepper:
                          sweep=self.store.sweep)
         self.pre = nxt is not None
         self.i += 1
-        self.store.maybe_reorder(sync_max=self.comm.allreduce_max)
+        every = self.conf.reorder_every
+        # (the gather pass has already applied drift self.i; the next one is what the forces to come will see)
+        pred = 0.5 * (every - 1) * self.inner.factors(self.i + 1)[1] if (self.pre and self.i + 1 < self.nsteps) else 0.0
+        self.store.maybe_reorder(sync_max=self.comm.allreduce_max, predict=pred)
 
 
 def nbody_adj_slab(ptcl, ptcl_cot, cosmo, conf, comm, reverse=False, force=None, _a_nbody=None):

@@ -151,7 +151,11 @@ class _Store:
         a = self.arrays
         return Particles(self.conf, a['pmid'], a['disp'], vel=a['vel'], acc=a['acc'])
 
-    def maybe_reorder(self, sync_max=None):
+    def maybe_reorder(self, sync_max=None, predict=0.0):
+        """Re-sort every ``conf.reorder_every`` steps.  ``predict``: sort by the PREDICTED positions
+        ``disp + vel * predict`` (a drift factor), so that the order is centred on the force evaluations until
+        the next re-sort instead of being exact for the first and two drifts stale for the last
+        (``PMWD_SORT_PREDICT=0`` turns it off)."""
         conf = self.conf
         if conf.reorder_every <= 0 or conf.dim != 3 or self.arrays['pmid'].dtype != torch.int16 or self.det_sweep:
             return False
@@ -166,16 +170,18 @@ class _Store:
             if m < conf.reorder_min_disp * conf.cell_size:
                 return False
             self.active = True
-        self.reorder()
+        if os.environ.get('PMWD_SORT_PREDICT', '1') == '0':
+            predict = 0.0
+        self.reorder(predict)
         return True
 
-    def reorder(self):
+    def reorder(self, predict=0.0):
         moved = None
         if self.migrator is not None:
             with self._timed('migrate'):
                 moved = self._migrate()
         with self._timed('resort'):
-            self._resort(moved)
+            self._resort(moved, predict)
 
     def _migrate(self):
         """Eulerian ownership (slab runs): every particle moves to the rank that owns its current base plane.
@@ -193,7 +199,7 @@ class _Store:
         self.migrations += 1
         return owner, arrivals, nmove
 
-    def _resort(self, moved=None):
+    def _resort(self, moved=None, predict=0.0):
         conf, a = self.conf, self.arrays
         dev = a['disp'].device
         nA = a['disp'].shape[0]
@@ -239,7 +245,9 @@ class _Store:
             _lib.check(lib.pmwd_cell_sort_perm2(
                 st, C.byref(sdesc), _lib.ptr(a['pmid']), _lib.ptr(a['disp']), nA, _lib.ptr(owner), rank,
                 _lib.ptr(arrivals['pmid']) if nB else None, _lib.ptr(arrivals['disp']) if nB else None,
-                _lib.ptr(self._perm), _lib.ptr(self._scratch), self._scratch.numel(), ty, bw), 'pmwd_cell_sort_perm2')
+                _lib.ptr(self._perm), _lib.ptr(self._scratch), self._scratch.numel(), ty, bw,
+                _lib.ptr(a['vel']) if predict else None, _lib.ptr(arrivals['vel']) if (predict and nB) else None,
+                float(predict)), 'pmwd_cell_sort_perm2')
             vp = C.c_void_p * len(names)
             src = vp(*[cur[k].data_ptr() for k in names])
             srcB = vp(*[arrivals[k].data_ptr() for k in names]) if nB else None
@@ -616,7 +624,16 @@ class _Stepper:
                 force_into(a['pmid'], a['disp'], Om, self.conf, a['acc'], a['vel'], k2, sweep=st.sweep_arg())
                 self.pre = False
         self.i += 1
-        st.maybe_reorder()
+        st.maybe_reorder(predict=self.predict())
+
+    def predict(self):
+        """Drift to add to the positions the re-sort keys are computed from.  The pipelined step has already
+        applied the next step's drift, so the forces until the next re-sort see the positions now, one drift and
+        two drifts later (``reorder_every`` = 3): centre the order on them."""
+        every = self.conf.reorder_every
+        if not self.pre or every < 2 or self.i + 1 >= self.nsteps:
+            return 0.0
+        return 0.5 * (every - 1) * self.factors(self.i + 1)[1]
 
 
 def _nbody_forward(ptcl, cosmo, conf, reverse):
@@ -701,6 +718,7 @@ def nbody_adj(ptcl, ptcl_cot, obsvbl_cot, cosmo, conf, reverse=False, _slab=None
         records = []   # (kind, slot, column, factor, grads)
 
         pending = []     # a trailing kick-only update waiting to share its pass with the next kick+drift
+        last_drift = 0.0
 
         def _kd_call(K, D, do_kick, do_drift, slot):
             a = store.arrays
@@ -773,7 +791,9 @@ def nbody_adj(ptcl, ptcl_cot, obsvbl_cot, cosmo, conf, reverse=False, _slab=None
                 if d != 0:
                     f_adj()
                     a_acc = a_disp
-            store.maybe_reorder(sync_max=sync_max)
+                    last_drift = fd
+            # the forces until the next re-sort come one, two and three drifts from here (reorder_every = 3)
+            store.maybe_reorder(sync_max=sync_max, predict=0.5 * (conf.reorder_every + 1) * last_drift)
 
         flush_pending()
         if _slab is not None:

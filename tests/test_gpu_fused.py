@@ -153,7 +153,7 @@ def test_two_source_sort_and_permute(ty, bw):
         scratch = torch.empty(lib.pmwd_cell_sort_scratch_bytes(C.byref(desc)), dtype=torch.uint8, device='cuda')
         _lib.check(lib.pmwd_cell_sort_perm2(st, C.byref(desc), _lib.ptr(pmidA), _lib.ptr(dispA), na, _lib.ptr(own), 0,
                                             _lib.ptr(pmidB), _lib.ptr(dispB), _lib.ptr(perm), _lib.ptr(scratch),
-                                            scratch.numel(), ty, bw), 'pmwd_cell_sort_perm2')
+                                            scratch.numel(), ty, bw, None, None, 0.0), 'pmwd_cell_sort_perm2')
         return perm
 
     desc = _force_desc(ptcl.pmid, conf)
