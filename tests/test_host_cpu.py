@@ -201,3 +201,38 @@ def test_slab_descriptor_selects_the_fast_path_for_any_cell_size(spacing, mesh_s
                 assert _lib.lib().pmwd_cic_fast_path(C.byref(desc)) == 1, (conf.cell_size, rank, h)
     full = SlabForce(conf, types.SimpleNamespace(x0=0, mx=Mx, rank=0, size=1))._desc(pmid, 0)
     assert _lib.lib().pmwd_cic_fast_path(C.byref(full)) == 2
+
+
+def test_resort_prediction_uses_the_coming_drift():
+    """The storage re-sort's keys come from disp + vel * predict: after the pipelined step i (whose gather pass has
+    already applied drift i+1) the forces until the next re-sort see the positions now and one / two drifts later,
+    so predict = (reorder_every - 1) / 2 x drift_factor of step i+2 (nbody.py:12-22), and 0 when no step follows,
+    when the step was not pipelined, or with reorder_every < 2.  Host logic only (no kernels are launched)."""
+    from pmwd_b200.nbody import _Stepper, drift_factor, _f32
+
+    conf = pm.Configuration(1., (4, 4, 4), mesh_shape=2, device='cpu', a_nbody_maxstep=0.2)
+    cosmo = pm.boltzmann(pm.SimpleLCDM(conf), conf)
+    a = conf.a_nbody.tolist()
+
+    class _FakeStore:
+        ptcl = pm.Particles.gen_grid(conf)
+
+    st = _Stepper(_FakeStore(), a, cosmo, conf)
+    st.fused = True
+    n = st.nsteps
+    assert n >= 4
+    for i_done in range(1, n + 1):            # state right after step i_done - 1: self.i == i_done
+        st.i, st.pre = i_done, i_done < n
+        got = st.predict()
+        if i_done + 1 >= n:
+            assert got == 0.0
+        else:
+            j = i_done + 1                    # the step whose drift takes x_{i_done} to x_{i_done + 1}
+            am = a[j] * 0.5 + a[j + 1] * 0.5
+            want = _f32(drift_factor(am, a[j], a[j + 1], cosmo, conf))
+            assert got == pytest.approx(0.5 * (conf.reorder_every - 1) * want, rel=1e-12) and got > 0
+    st.i, st.pre = 1, False                   # not pipelined: the positions at sort time are the next force's
+    assert st.predict() == 0.0
+    st2 = _Stepper(_FakeStore(), a, cosmo, conf.replace(reorder_every=1))
+    st2.i, st2.pre = 1, True
+    assert st2.predict() == 0.0
