@@ -6,12 +6,15 @@ The reference is single-device (docs/papers/adjoint/adjoint.tex:1743-1744); this
 
   * mesh: x-slabs, ``Mx / P`` planes per rank; spectra after the distributed FFT are y-slabs
     ``[Mx][My / P][Mz/2+1]`` (no transpose back: the k-space kernel runs on that layout);
-  * particles: Lagrangian x-slabs = contiguous ranges of the reference's C-ordered arrays, so
-    outputs concatenate to the reference order and nothing migrates;
-  * per force: scatter into slab + halo planes -> neighbour reduce-add of halos -> slab FFT
-    (local 2-D R2C over (y, z), ONE all-to-all, 1-D C2C over x) -> fused k-space kernel ->
-    3 x (1-D inverse, all-to-all, local 2-D C2R) -> neighbour halo copy -> 3-mesh gather;
-  * the halo width follows the all-reduced max |disp_x| every step;
+  * particles: the inputs and outputs of every entry point are Lagrangian x-slabs = contiguous ranges of the
+    reference's C-ordered arrays (outputs concatenate to the reference order); INSIDE the integrator every particle
+    lives on the rank that owns its current base plane and is re-assigned at every storage re-sort (Eulerian
+    ownership, ``migrate.py`` + ``nbody._Store``; ``PMWD_MIGRATE=0`` keeps Lagrangian ownership);
+  * per force: halo width (one fused pass + all-reduce) -> tiled deposit into slab + halo planes (RED kernel when
+    the halo width changed since the last re-sort) -> neighbour reduce-add of halos -> local 2-D R2C over (y, z)
+    -> transpose straight into the peers' symmetric-memory buffers on the copy engines -> fused x-pass on the
+    y-slab layout -> 3 x (transpose, local 2-D C2R) -> neighbour halo copy -> 3-mesh gather (+ kick / drift);
+    NCCL all-to-all transposes and cuFFT 1-D passes remain as fallbacks;
   * the adjoint uses the same plumbing; its float64 dot products are all-reduced once.
 
 A slab is described to the kernels with the reference's own ``(offset, mesh shape)`` enmesh
