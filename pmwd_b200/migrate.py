@@ -63,7 +63,9 @@ def to_eulerian(arrays, conf, group=None):
 
 
 def to_eulerian_movers(arrays, conf, group=None):
-    """Same result set as :func:`to_eulerian` (order differs: the particles that stay come first, in
+    """(First version of the integrator's exchange, kept as the reference for :func:`exchange_movers` in the
+    tests: it also compacts the stayers, which the re-sort now does on the fly.)
+    Same result set as :func:`to_eulerian` (order differs: the particles that stay come first, in
     their old order, then the arrivals by source rank), but only the particles that change rank travel:
     the owner comes from one fused pass (``pmwd_slab_owner``), the movers (a few per cent) are compacted and
     exchanged, the stayers are compacted with one gather per array."""
